@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- latent symbols/s, encode + decode, bit-exact (BASELINE.json metric).
+
+A step = one pass of the whole hot path over one batch of synthetic W+ latents:
+  quantise (codebook argmin) -> encode -> compact -> decode (+ fused dequantise).
+Default workload = BASELINE.json configs[1]: 1024 latents of 16x512 at 8 bits per GPU
+("enc_like" synthetic latents).  With N GPUs every rank codes its own 1024
+streams (weak scaling, no collective on the hot path; the only NCCL traffic is the optional size
+gather after the timed region).
+
+  python bench.py [--gpus N --steps K --warmup W]          this framework
+  python bench.py --impl reference [...]                    the CPU coder on the host cores
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "latent symbols/sec enc+dec (bit-exact)"
+UNIT = "symbols/s"
+R, C = 16, 512
+SYMS = R * C
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--bits", type=int, default=8)
+    ap.add_argument("--kind", default="enc_like")
+    ap.add_argument("--cpu-sample-streams", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synth(kind, B, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    if kind == "enc_like":
+        return torch.randn(B, R, C, generator=g) * 0.14
+    if kind == "wide":
+        return torch.randn(B, R, C, generator=g) * 0.4
+    if kind == "uniform":
+        return torch.rand(B, R, C, generator=g) * 2 - 1
+    raise ValueError(kind)
+
+
+def workload_name(args):
+    return "cfg2: %d synthetic W+ latents 16x512 (%s) per GPU, %d-bit codebook quantise + CABAC round trip" % (
+        args.batch, args.kind, args.bits)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (oracle/latent_oracle.c) on the host cores -- a reported baseline
+# ------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_roundtrip_rate(codes_np, n, threads, repeats=1):
+    """codes_np int32 [S,16,512]: encode+decode every stream with the C oracle on `threads` host
+    threads (ctypes releases the GIL). Returns (symbols/s, seconds, streams)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as orc
+    orc.lib()
+    S = codes_np.shape[0]
+
+    def one(i):
+        st, _ = orc.roundtrip_stream(codes_np[i:i + 1], n, "repaired")
+        return st
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        for _ in range(repeats):
+            sts = list(ex.map(one, range(S)))
+    dt = time.perf_counter() - t0
+    assert not any(sts), "CPU oracle round trip failed"
+    return S * repeats * SYMS / dt, dt, S * repeats
+
+
+def cpu_sample(args, n):
+    """A bounded sample of the bench workload for the CPU legs: quantised with the oracle."""
+    import torch
+
+    from oracle import oracle as orc
+    threads = host_threads()
+    S = args.cpu_sample_streams
+    if S <= 0:
+        # one stream costs ~26 ms (n=256) / ~120 ms (n=1024) / ~3 ms (n=16) of one core
+        per = {16: 0.003, 256: 0.03, 1024: 0.13}.get(n, 0.03)
+        S = int(min(args.batch, max(2 * threads, 15.0 * threads / per)))
+    lat = synth(args.kind, S, 1000 + 2 * 100000).numpy()
+    cb = torch.linspace(-1, 1, n).float().numpy()
+    return orc.quantize_codebook(lat, cb), threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (C port of it -- the reference itself is Python
+    and cannot travel to the GPU box) on all host threads; each step = a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 1 << args.bits
+    codes, threads = cpu_sample(args, n)
+    for _ in range(min(args.warmup, 1)):
+        cpu_roundtrip_rate(codes[: max(2, threads)], n, threads)
+    t_total, streams = 0.0, 0
+    for _ in range(args.steps):
+        _, dt, s = cpu_roundtrip_rate(codes, n, threads)
+        t_total += dt
+        streams += s
+    value = streams * SYMS / t_total
+    sample = "%d streams/step x %d steps of the bench workload (seeded %s latents), C port of the reference coder, %s" % (
+        codes.shape[0], args.steps, args.kind, cpu_model())
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_streams_per_step": int(codes.shape[0])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in ln.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# this framework
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from image_compression_2_b200 import LatentPipeline, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = 1 << args.bits
+    B = args.batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # every rank codes its own shard of the global batch (world*B streams), inputs generated on the
+    # CPU so the oracle and the kernels see the same bits
+    lo, hi = sharding.shard_range(world * B, rank, world)
+    lat_host = synth(args.kind, B, 1000 + 2 * 100000 + rank).pin_memory()
+    lat = lat_host.to(dev)
+    pipe = LatentPipeline(n_symbols=n, R=R, C=C, quantizer="codebook")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    stream = torch.cuda.current_stream()
+
+    def step_device(events=None):
+        idx = pipe.quantize(lat)
+        enc = pipe.encode(idx)
+        if events is not None:
+            events[0].record(stream)
+        dec_idx, deq, dstatus, dfault = pipe.decode(enc.data, enc.offsets, enc.nbits, B)
+        if events is not None:
+            events[1].record(stream)
+        return idx, enc, dec_idx, deq, dstatus
+
+    # ---- parity gate on this rank's actual workload before any timing
+    idx, enc, dec_idx, deq, dstatus = step_device()
+    torch.cuda.synchronize()
+    assert int(enc.status.abs().sum()) == 0 and int(dstatus.abs().sum()) == 0, "coder fault in the bench workload"
+    assert torch.equal(dec_idx.view(B, R, C), idx), "round trip is not the identity"
+    assert torch.equal(deq.view(B, R, C), pipe.codebook[idx.long()]), "dequantised latents differ"
+    coded_bits = float(enc.nbits.double().mean())
+    parity_note = "round-trip identity on all streams"
+    if rank == 0:
+        from oracle import oracle as orc
+        streams, nbits_h, _, _ = enc.to_host()
+        idx_h = idx.cpu().numpy()
+        for b in range(0, B, max(1, B // 8)):
+            ref = orc.encode_stream(idx_h[b:b + 1], n, "repaired")
+            assert nbits_h[b] == ref["nbits"] and streams[b] == ref["packed"], "bitstream differs from the oracle"
+        parity_note += "; %d sampled bitstreams bit-identical to the CPU oracle" % len(range(0, B, max(1, B // 8)))
+
+    # ---- device-resident metric
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        flush.zero_()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_steps, t_dec = [], []
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device((d0, d1))
+        e1.record(stream)
+        e1.synchronize()
+        t_steps.append(e0.elapsed_time(e1))
+        t_dec.append(d0.elapsed_time(d1))
+    barrier()
+    t_total = torch.tensor([sum(t_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    ms_total = float(t_total)
+
+    # ---- end-to-end metric: host buffers in, host buffers out, copies inside the timed region
+    for _ in range(2):
+        res = pipe.roundtrip_host(lat_host)
+    barrier()
+    e_times = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = pipe.roundtrip_host(lat_host)
+        e_times.append(time.perf_counter() - t0)
+    barrier()
+    assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any()
+    assert torch.equal(res["deq"], pipe.codebook.cpu()[idx.cpu().long()]), "e2e result differs"
+    e_total = torch.tensor([sum(e_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_total, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # optional size gather (not timed; the only collective this framework has)
+    sizes, _ = sharding.gather_shard_bytes(int(enc.offsets[-1]), device=dev)
+
+    if rank == 0:
+        total_syms = world * B * SYMS
+        value = total_syms * args.steps / (ms_total * 1e-3)
+        e2e_value = total_syms * args.steps / float(e_total)
+        # roofline of the dominant kernel (the decoder).  Algorithmic bytes per symbol of that
+        # launch: coded bits/8 read + 4 B int32 index + 4 B fp32 dequantised value written
+        # (DESIGN.md section 5).  It is NOT an HBM-bound kernel; the fraction is reported as is.
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dec_ms = sum(t_dec) / len(t_dec)
+        bytes_per_launch = B * SYMS * (coded_bits / SYMS / 8.0 + 8.0)
+        achieved = bytes_per_launch / (dec_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "streams_per_gpu": B, "symbols_per_stream": SYMS,
+                       "n_symbols": n, "coder_mode": "repaired", "coded_bits_per_symbol": coded_bits / SYMS,
+                       "l2": "flushed between timed steps (256 MiB memset, untimed)", "parallelism": "streams sharded by image, no collective",
+                       "parity": parity_note, "streams_per_s": value / SYMS},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(res["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(res["d2h_bytes"]), "ms_per_step": 1e3 * float(e_total) / args.steps},
+            "gpu_launches": 5 * args.steps,
+            "roofline": {"kernel": "lc_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                         "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms_total / args.steps),
+                         "note": "latency/issue-bound serial coder, not HBM-bound; see DESIGN.md section 5"},
+            "clocks": clocks,
+            "rank_bytes": [int(x) for x in sizes.tolist()],
+        }
+        if not args.no_cpu_baseline:
+            codes, threads = cpu_sample(args, n)
+            cv, cdt, cs = cpu_roundtrip_rate(codes, n, threads)
+            line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d streams of the same workload in %.1f s, C port of the reference coder "
+                                              "(oracle/latent_oracle.c), %s" % (cs, cdt, cpu_model())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,273 @@
+"""Tensor-level API over the C ABI (include/latentcodec.h): device tensors in, device tensors out.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in the hand-written
+CUDA kernels of liblatentcodec.so.  Every function refuses non-CUDA tensors: there is no CPU path.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native
+
+MODE_VERBATIM, MODE_REPAIRED = 0, 1
+MODES = {"verbatim": MODE_VERBATIM, "repaired": MODE_REPAIRED, 0: 0, 1: 1}
+
+STATUS_OK = 0
+STATUS_NAMES = {0: "OK", 1: "ENC_BIT_OVERFLOW", 2: "DEC_SYMBOL_OOB", 3: "DEC_ZERO_RANGE", 4: "DEC_NEG_SYMBOL",
+                5: "OUT_OVERFLOW", 6: "BAD_SYMBOL", 7: "POOL_OVERFLOW"}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t, name, dtype):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: this package has no CPU path" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# quantisers
+# ------------------------------------------------------------------------------------------------
+
+def quantize_affine(w, bits, want_idx=True, want_wq=True):
+    """Quantiser A (stylegan3_hvae_full.py:313-316). Returns (idx int32 | None, wq fp32 | None)."""
+    lib = _native.load()
+    w = _need_cuda(w, "w", torch.float32)
+    idx = torch.empty(w.shape, dtype=torch.int32, device=w.device) if want_idx else None
+    wq = torch.empty_like(w) if want_wq else None
+    _native.check(lib.lc_quantize_affine(w.data_ptr(), w.numel(), int(bits), _ptr(idx), _ptr(wq), _stream()),
+                  "lc_quantize_affine")
+    return idx, wq
+
+
+def dequantize_affine(idx, bits):
+    """Dequantiser A: idx/(2^bits-1)*2-1 (stylegan3_hvae_full.py:315-316)."""
+    lib = _native.load()
+    idx = _need_cuda(idx, "idx", torch.int32)
+    out = torch.empty(idx.shape, dtype=torch.float32, device=idx.device)
+    _native.check(lib.lc_dequantize_affine(idx.data_ptr(), idx.numel(), int(bits), out.data_ptr(), _stream()),
+                  "lc_dequantize_affine")
+    return out
+
+
+def codebook_is_sorted(codebook):
+    cb = codebook.detach().float().cpu()
+    return bool((cb[1:] >= cb[:-1]).all()) if cb.numel() > 1 else True
+
+
+def quantize_codebook(z, codebook, want_deq=False, sorted_ascending=None):
+    """Quantiser B (gumbel_softmax_compression.py:97,118): first-minimum argmin over the codebook.
+    Returns (idx int32, codebook[idx] fp32 | None)."""
+    lib = _native.load()
+    z = _need_cuda(z, "z", torch.float32)
+    cb = _need_cuda(codebook.to(z.device), "codebook", torch.float32)
+    if sorted_ascending is None:
+        sorted_ascending = codebook_is_sorted(cb)
+    idx = torch.empty(z.shape, dtype=torch.int32, device=z.device)
+    deq = torch.empty_like(z) if want_deq else None
+    _native.check(lib.lc_quantize_codebook(z.data_ptr(), z.numel(), cb.data_ptr(), cb.numel(),
+                                           1 if sorted_ascending else 0, idx.data_ptr(), _ptr(deq), _stream()),
+                  "lc_quantize_codebook")
+    return idx, deq
+
+
+def dequantize_codebook(idx, codebook):
+    """Dequantiser B: codebook[idx] (cabac_compression.py:531)."""
+    lib = _native.load()
+    idx = _need_cuda(idx, "idx", torch.int32)
+    cb = _need_cuda(codebook.to(idx.device), "codebook", torch.float32)
+    out = torch.empty(idx.shape, dtype=torch.float32, device=idx.device)
+    _native.check(lib.lc_dequantize_codebook(idx.data_ptr(), idx.numel(), cb.data_ptr(), cb.numel(), out.data_ptr(),
+                                             _stream()), "lc_dequantize_codebook")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# coder
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class StreamLayout:
+    """How a batch tensor maps onto independent streams."""
+    B: int        # independent streams (fresh model each)
+    imgs: int     # images per stream sharing coder + model
+    R: int
+    C: int
+    has_ctx: int
+
+    @property
+    def total(self):
+        return self.imgs * self.R * self.C
+
+
+def layout_independent(shape):
+    """[B,R,C] -> B independent streams (the batch semantics this framework adds)."""
+    if len(shape) != 3:
+        raise ValueError("expected [B,R,C], got %s" % (tuple(shape),))
+    return StreamLayout(int(shape[0]), 1, int(shape[1]), int(shape[2]), 1)
+
+
+def layout_reference(shape):
+    """The reference's own semantics for cabac_encode(data): ONE stream; a 3-D shape (B,R,C) has
+    (left,up) contexts per image with a shared model (cabac_compression.py:91-114, 330-337); any
+    other rank uses the single global context (:115-117)."""
+    shape = tuple(int(s) for s in shape)
+    if len(shape) == 3:
+        return StreamLayout(1, shape[0], shape[1], shape[2], 1)
+    total = int(np.prod(shape)) if len(shape) else 1
+    return StreamLayout(1, 1, 1, total, 0)
+
+
+@dataclass
+class EncodedBatch:
+    """Device-resident result of encode_batch."""
+    data: torch.Tensor      # uint8, compacted streams (16-byte aligned starts)
+    offsets: torch.Tensor   # int64 [B+1]
+    nbits: torch.Tensor     # int32 [B]
+    status: torch.Tensor    # int32 [B]
+    fault_index: torch.Tensor  # int32 [B]
+    layout: StreamLayout
+    n_symbols: int
+    mode: int
+
+    def to_host(self):
+        """-> (list of packed `bytes` per stream, nbits ndarray, status ndarray, fault ndarray); synchronises."""
+        offs = self.offsets.cpu().numpy()
+        nbits = self.nbits.cpu().numpy()
+        status = self.status.cpu().numpy()
+        fault = self.fault_index.cpu().numpy()
+        used = int(offs[-1])
+        blob = self.data[:used].cpu().numpy()
+        out = []
+        for b in range(self.layout.B):
+            nb = (int(nbits[b]) + 7) // 8 if status[b] == 0 else 0
+            out.append(blob[offs[b]:offs[b] + nb].tobytes())
+        return out, nbits, status, fault
+
+
+class CoderWorkspace:
+    """Caches the scratch / slot / output buffers for a (device, layout, n) so steady-state calls
+    allocate nothing."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes, device, dtype=torch.uint8):
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes or buf.device != device:
+            buf = torch.empty(int(nbytes), dtype=dtype, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+_default_ws = CoderWorkspace()
+
+
+def _check_n(n):
+    n = int(n)
+    if n < 2 or n > 1024 or (n & (n - 1)):
+        raise ValueError("n_symbols must be a power of two in [2,1024] on the CUDA path, got %d" % n)
+    return n
+
+
+def encode_batch(idx, layout, n_symbols, mode="repaired", adaptation_rate=0.05, slot_bytes=None, workspace=None):
+    """cabac_encode for layout.B independent streams (cabac_compression.py:315-359).
+    idx: int32 CUDA tensor with layout.B * layout.total elements. Returns EncodedBatch (async)."""
+    lib = _native.load()
+    idx = _need_cuda(idx, "idx", torch.int32)
+    n = _check_n(n_symbols)
+    if idx.numel() != layout.B * layout.total:
+        raise ValueError("idx has %d elements, layout needs %d" % (idx.numel(), layout.B * layout.total))
+    ws = workspace or _default_ws
+    dev = idx.device
+    B = layout.B
+    m = MODES[mode]
+    if B == 0:
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return EncodedBatch(torch.zeros(0, dtype=torch.uint8, device=dev), torch.zeros(1, dtype=torch.int64, device=dev),
+                            z, z.clone(), z.clone(), layout, n, m)
+    scratch_bytes = lib.lc_coder_scratch_bytes(B, layout.imgs, layout.R, layout.C, n, layout.has_ctx)
+    if scratch_bytes < 0:
+        raise ValueError("unsupported stream shape for the CUDA coder: %s" % (layout,))
+    if slot_bytes is None:
+        slot_bytes = lib.lc_encode_slot_bytes(layout.imgs, layout.R, layout.C, n)
+    slot_bytes = (int(slot_bytes) + 15) // 16 * 16
+    scratch = ws.get(("scratch", dev), scratch_bytes, dev)
+    slots = ws.get(("slots", dev), B * slot_bytes, dev)
+    out = torch.empty(B * slot_bytes, dtype=torch.uint8, device=dev)
+    offsets = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    nbits = torch.empty(B, dtype=torch.int32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    fault = torch.empty(B, dtype=torch.int32, device=dev)
+    rc = lib.lc_encode_batch(idx.data_ptr(), B, layout.imgs, layout.R, layout.C, n, float(adaptation_rate), m,
+                             layout.has_ctx, scratch.data_ptr(), scratch.numel(), slots.data_ptr(), slot_bytes,
+                             out.data_ptr(), out.numel(), offsets.data_ptr(), nbits.data_ptr(), status.data_ptr(),
+                             fault.data_ptr(), _stream())
+    _native.check(rc, "lc_encode_batch")
+    return EncodedBatch(out, offsets, nbits, status, fault, layout, n, m)
+
+
+def decode_batch(data, offsets, nbits, layout, n_symbols, mode="repaired", adaptation_rate=0.05, codebook=None,
+                 workspace=None):
+    """cabac_decode for layout.B independent streams (cabac_compression.py:363-406).
+    data uint8 CUDA (stream b = ceil(nbits[b]/8) bytes at offsets[b], offsets multiples of 4, buffer padded to a
+    multiple of 4); offsets int64 [>=B]; nbits int32 [B].
+    Returns (idx int32 [B,total], deq fp32 [B,total] | None, status int32 [B], fault_index int32 [B])."""
+    lib = _native.load()
+    data = _need_cuda(data, "data", torch.uint8)
+    offsets = _need_cuda(offsets, "offsets", torch.int64)
+    nbits = _need_cuda(nbits, "nbits", torch.int32)
+    n = _check_n(n_symbols)
+    ws = workspace or _default_ws
+    dev = data.device
+    B = layout.B
+    idx = torch.empty((B, layout.total), dtype=torch.int32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    fault = torch.empty(B, dtype=torch.int32, device=dev)
+    deq, cb = None, None
+    if codebook is not None:
+        cb = _need_cuda(codebook.to(dev), "codebook", torch.float32)
+        if cb.numel() < n:
+            raise ValueError("codebook has %d entries, need %d" % (cb.numel(), n))
+        deq = torch.empty((B, layout.total), dtype=torch.float32, device=dev)
+    if B == 0:
+        return idx, deq, status, fault
+    scratch_bytes = lib.lc_coder_scratch_bytes(B, layout.imgs, layout.R, layout.C, n, layout.has_ctx)
+    if scratch_bytes < 0:
+        raise ValueError("unsupported stream shape for the CUDA coder: %s" % (layout,))
+    scratch = ws.get(("scratch", dev), scratch_bytes, dev)
+    rc = lib.lc_decode_batch(data.data_ptr(), offsets.data_ptr(), nbits.data_ptr(), B, layout.imgs, layout.R, layout.C,
+                             n, float(adaptation_rate), MODES[mode], layout.has_ctx, scratch.data_ptr(),
+                             scratch.numel(), idx.data_ptr(), _ptr(cb), _ptr(deq), status.data_ptr(), fault.data_ptr(),
+                             _stream())
+    _native.check(rc, "lc_decode_batch")
+    return idx, deq, status, fault
+
+
+def pack_streams_for_device(streams, device):
+    """Host helper: lay out a list of packed `bytes` with 16-byte aligned starts and upload.
+    Returns (data uint8, offsets int64 [B+1], nbits int32 [B]) on `device`."""
+    B = len(streams)
+    offs = np.zeros(B + 1, np.int64)
+    nbits = np.zeros(B, np.int32)
+    pos = 0
+    for i, s in enumerate(streams):
+        offs[i] = pos
+        nbits[i] = len(s) * 8
+        pos += (len(s) + 15) // 16 * 16
+    offs[B] = pos
+    blob = np.zeros(max(pos, 16), np.uint8)
+    for i, s in enumerate(streams):
+        blob[offs[i]:offs[i] + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    return (torch.from_numpy(blob).to(device), torch.from_numpy(offs).to(device), torch.from_numpy(nbits).to(device))

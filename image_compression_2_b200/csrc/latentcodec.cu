@@ -1,0 +1,425 @@
+// liblatentcodec.so -- CUDA kernels (sm_100a) and the C ABI declared in include/latentcodec.h.
+// Build: see image_compression_2_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a
+// --fmad=false -lineinfo).  No tensor cores: nothing on this path is a dense contraction.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/latentcodec.h"
+#include "lc_coder.cuh"
+
+#define LC_CUDA_RET()                                                     \
+    do {                                                                  \
+        cudaError_t e__ = cudaGetLastError();                             \
+        if (e__ != cudaSuccess) return -1000 - (int)e__;                  \
+    } while (0)
+
+static int lc_num_sms()
+{
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 148; // B200; keeps the sizing helpers usable on a machine without a GPU
+    }
+    cached = n;
+    return n;
+}
+
+// =================================================================================================
+// K1: quantiser A / dequantiser A  (stylegan3_hvae_full.py:313-316).  HBM-bound, 128-bit accesses.
+// =================================================================================================
+__device__ __forceinline__ float lc_qa_round(float w, float scale)
+{
+    const float a = __fadd_rn(w, 1.0f);
+    const float b = __fmul_rn(a, 0.5f);
+    const float c = __fmul_rn(b, scale);
+    return rintf(c); // torch.round: half to even
+}
+__device__ __forceinline__ float lc_qa_deq(float q, float scale)
+{
+    const float d = __fdiv_rn(q, scale);
+    const float e = __fmul_rn(d, 2.0f);
+    return __fsub_rn(e, 1.0f);
+}
+__device__ __forceinline__ int lc_qa_int(float q)
+{
+    return (q == q && fabsf(q) < 2.0e9f) ? (int)q : (int)0x80000000;
+}
+
+__global__ void __launch_bounds__(256) lc_quant_affine_kernel(const float *__restrict__ w, long long n_elem, float scale,
+                                                              int *__restrict__ idx_out, float *__restrict__ wq_out)
+{
+    const long long n4 = n_elem >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(w) + i);
+        float4 q;
+        q.x = lc_qa_round(v.x, scale); q.y = lc_qa_round(v.y, scale);
+        q.z = lc_qa_round(v.z, scale); q.w = lc_qa_round(v.w, scale);
+        if (idx_out) {
+            int4 o; o.x = lc_qa_int(q.x); o.y = lc_qa_int(q.y); o.z = lc_qa_int(q.z); o.w = lc_qa_int(q.w);
+            __stcs(reinterpret_cast<int4 *>(idx_out) + i, o);
+        }
+        if (wq_out) {
+            float4 o; o.x = lc_qa_deq(q.x, scale); o.y = lc_qa_deq(q.y, scale);
+            o.z = lc_qa_deq(q.z, scale); o.w = lc_qa_deq(q.w, scale);
+            __stcs(reinterpret_cast<float4 *>(wq_out) + i, o);
+        }
+    }
+    // tail (n_elem not a multiple of 4)
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
+        const float q = lc_qa_round(w[i], scale);
+        if (idx_out) idx_out[i] = lc_qa_int(q);
+        if (wq_out) wq_out[i] = lc_qa_deq(q, scale);
+    }
+}
+
+__global__ void __launch_bounds__(256) lc_dequant_affine_kernel(const int *__restrict__ idx, long long n_elem, float scale,
+                                                                float *__restrict__ w_out)
+{
+    const long long n4 = n_elem >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int4 v = __ldcs(reinterpret_cast<const int4 *>(idx) + i);
+        float4 o;
+        o.x = lc_qa_deq((float)v.x, scale); o.y = lc_qa_deq((float)v.y, scale);
+        o.z = lc_qa_deq((float)v.z, scale); o.w = lc_qa_deq((float)v.w, scale);
+        __stcs(reinterpret_cast<float4 *>(w_out) + i, o);
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride)
+        w_out[i] = lc_qa_deq((float)idx[i], scale);
+}
+
+// =================================================================================================
+// K2: quantiser B (gumbel_softmax_compression.py:97,118) without the [N,n] distance matrix: the
+// codebook sits in shared memory; for an ascending codebook the rounded fp32 distances are
+// monotone either side of the nearest entry, so a lower-bound search plus a walk over equal
+// distances gives torch.argmin's first minimum exactly.
+// =================================================================================================
+__device__ __forceinline__ float lc_dist(float z, float c) { return fabsf(__fsub_rn(z, c)); }
+
+__device__ __forceinline__ int lc_argmin_sorted(const float *cb, int n, float z, float guess_scale)
+{
+    if (!(z == z)) return 0; // NaN: every distance is NaN, argmin returns 0
+    // first k with cb[k] >= z, seeded by the affine position of z between the end points
+    int k;
+    {
+        float g = (z - cb[0]) * guess_scale;
+        g = g < 0.0f ? 0.0f : (g > (float)(n - 1) ? (float)(n - 1) : g);
+        k = (int)g;
+        while (k < n && cb[k] < z) k++;
+        while (k > 0 && cb[k - 1] >= z) k--;
+    }
+    int best;
+    if (k == 0) best = 0;
+    else if (k == n) best = n - 1;
+    else best = (lc_dist(z, cb[k]) < lc_dist(z, cb[k - 1])) ? k : k - 1;
+    float d = lc_dist(z, cb[best]);
+    while (best > 0 && lc_dist(z, cb[best - 1]) <= d) { best--; d = lc_dist(z, cb[best]); }
+    while (best < n - 1 && lc_dist(z, cb[best + 1]) < d) { best++; d = lc_dist(z, cb[best]); }
+    return best;
+}
+
+__device__ __forceinline__ int lc_argmin_scan(const float *cb, int n, float z)
+{
+    float best = lc_dist(z, cb[0]);
+    int bi = 0;
+    for (int k = 1; k < n; k++) {
+        const float d = lc_dist(z, cb[k]);
+        if (d < best) { best = d; bi = k; }
+    }
+    return bi;
+}
+
+__global__ void __launch_bounds__(256) lc_quant_codebook_kernel(const float *__restrict__ z, long long n_elem,
+                                                                const float *__restrict__ codebook, int n, int sorted,
+                                                                int *__restrict__ idx_out, float *__restrict__ deq_out)
+{
+    extern __shared__ float cb[];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cb[i] = codebook[i];
+    __syncthreads();
+    const float span = cb[n - 1] - cb[0];
+    const float guess_scale = (sorted && span > 0.0f) ? (float)(n - 1) / span : 0.0f;
+    const long long n4 = n_elem >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(z) + i);
+        int4 o;
+        if (sorted) {
+            o.x = lc_argmin_sorted(cb, n, v.x, guess_scale); o.y = lc_argmin_sorted(cb, n, v.y, guess_scale);
+            o.z = lc_argmin_sorted(cb, n, v.z, guess_scale); o.w = lc_argmin_sorted(cb, n, v.w, guess_scale);
+        } else {
+            o.x = lc_argmin_scan(cb, n, v.x); o.y = lc_argmin_scan(cb, n, v.y);
+            o.z = lc_argmin_scan(cb, n, v.z); o.w = lc_argmin_scan(cb, n, v.w);
+        }
+        __stcs(reinterpret_cast<int4 *>(idx_out) + i, o);
+        if (deq_out) {
+            float4 d; d.x = cb[o.x]; d.y = cb[o.y]; d.z = cb[o.z]; d.w = cb[o.w];
+            __stcs(reinterpret_cast<float4 *>(deq_out) + i, d);
+        }
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
+        const int o = sorted ? lc_argmin_sorted(cb, n, z[i], guess_scale) : lc_argmin_scan(cb, n, z[i]);
+        idx_out[i] = o;
+        if (deq_out) deq_out[i] = cb[o];
+    }
+}
+
+__global__ void __launch_bounds__(256) lc_dequant_codebook_kernel(const int *__restrict__ idx, long long n_elem,
+                                                                  const float *__restrict__ codebook, int n,
+                                                                  float *__restrict__ w_out)
+{
+    extern __shared__ float cb[];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cb[i] = codebook[i];
+    __syncthreads();
+    const float nanv = __int_as_float(0x7fc00000);
+    const long long n4 = n_elem >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int4 v = __ldcs(reinterpret_cast<const int4 *>(idx) + i);
+        float4 o;
+        o.x = (unsigned)v.x < (unsigned)n ? cb[v.x] : nanv; o.y = (unsigned)v.y < (unsigned)n ? cb[v.y] : nanv;
+        o.z = (unsigned)v.z < (unsigned)n ? cb[v.z] : nanv; o.w = (unsigned)v.w < (unsigned)n ? cb[v.w] : nanv;
+        __stcs(reinterpret_cast<float4 *>(w_out) + i, o);
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride)
+        w_out[i] = (unsigned)idx[i] < (unsigned)n ? cb[idx[i]] : nanv;
+}
+
+// =================================================================================================
+// K3 / K5: the coder kernels (one warp per block, persistent over streams) -- lc_coder.cuh
+// =================================================================================================
+__global__ void __launch_bounds__(32) lc_encode_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
+                                                       unsigned char *slots, uint32_t slot_bytes, int *nbits, int *status,
+                                                       int *fault, char *scratch)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lc_encode_block(cfg, codes, B, slots, slot_bytes, nbits, status, fault, scratch, lc_smem);
+}
+
+__global__ void __launch_bounds__(32) lc_decode_kernel(LcCoderCfg cfg, const unsigned char *__restrict__ bytes,
+                                                       const long long *__restrict__ offsets, const int *__restrict__ nbits,
+                                                       int B, int *out, const float *__restrict__ deq_table, float *deq_out,
+                                                       int *status, int *fault, char *scratch)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lc_decode_block(cfg, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, lc_smem);
+}
+
+// =================================================================================================
+// K4: stream compaction -- exclusive scan of the 16-byte-aligned stream sizes, then a word copy
+// =================================================================================================
+__global__ void __launch_bounds__(1024) lc_scan_sizes_kernel(const int *__restrict__ nbits, int *status, int B,
+                                                             long long capacity, long long *offsets)
+{
+    __shared__ long long warp_sums[32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + threadIdx.x;
+        long long sz = 0;
+        if (b < B && status[b] == LC_OK) sz = ((((long long)nbits[b] + 7) >> 3) + 15) & ~15ll;
+        long long incl = sz;
+        for (int off = 1; off < 32; off <<= 1) {
+            const long long t = __shfl_up_sync(LC_FULL_MASK, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            long long ws = warp_sums[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                const long long t = __shfl_up_sync(LC_FULL_MASK, ws, off);
+                if (lane >= off) ws += t;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        const long long excl = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + incl - sz;
+        if (b < B) {
+            offsets[b] = excl;
+            if (sz > 0 && excl + sz > capacity) status[b] = LC_OUT_OVERFLOW;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[B] = carry_s;
+}
+
+__global__ void __launch_bounds__(128) lc_compact_kernel(const unsigned char *__restrict__ slots, long long slot_bytes,
+                                                         const int *__restrict__ nbits, const int *__restrict__ status,
+                                                         const long long *__restrict__ offsets, unsigned char *out)
+{
+    const int b = blockIdx.x;
+    if (status[b] != LC_OK) return;
+    const long long nbytes = ((long long)nbits[b] + 7) >> 3;
+    const int nwords = (int)((nbytes + 3) >> 2);       // the encoder zero-pads its last word
+    const int npad = (int)(((nbytes + 15) & ~15ll) >> 2); // words of the aligned segment
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(slots + (long long)b * slot_bytes);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + offsets[b]);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) dst[i] = i < nwords ? src[i] : 0u;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+static int lc_make_cfg(LcCoderCfg &cfg, int imgs, int R, int C, int n, double rate, int mode, int has_ctx)
+{
+    cfg = LcCoderCfg();
+    cfg.n = n; cfg.R = R; cfg.C = C; cfg.imgs = imgs; cfg.has_ctx = has_ctx ? 1 : 0; cfg.mode = mode; cfg.rate = rate;
+    if (mode != LC_MODE_VERBATIM && mode != LC_MODE_REPAIRED) return -22;
+    return lc_cfg_finalize(&cfg);
+}
+
+static int lc_grid_for(const LcCoderCfg &cfg, int B)
+{
+    int per_sm = (int)((227u * 1024u) / (cfg.sm_bytes + 1024u));
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)lc_num_sms() * per_sm;
+    if (g > B) g = B;
+    return g < 1 ? 1 : (int)g;
+}
+
+static int lc_ew_grid(long long n_elem)
+{
+    long long blocks = (n_elem / 4 + 255) / 256;
+    const long long cap = (long long)lc_num_sms() * 8; // 2048 threads per SM
+    if (blocks > cap) blocks = cap;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+extern "C" {
+
+int lc_version(void) { return LC_ABI_VERSION; }
+
+int lc_quantize_affine(const float *w, int64_t n_elem, int bits, int32_t *idx_out, float *wq_out, void *stream)
+{
+    if (n_elem < 0 || bits < 1 || bits > 24 || !w) return -22;
+    if (n_elem == 0 || (!idx_out && !wq_out)) return 0;
+    if ((((uintptr_t)w | (uintptr_t)idx_out | (uintptr_t)wq_out) & 15) != 0) return -22;
+    lc_quant_affine_kernel<<<lc_ew_grid(n_elem), 256, 0, (cudaStream_t)stream>>>(w, n_elem, (float)((1 << bits) - 1),
+                                                                                 idx_out, wq_out);
+    LC_CUDA_RET();
+    return 0;
+}
+
+int lc_dequantize_affine(const int32_t *idx, int64_t n_elem, int bits, float *w_out, void *stream)
+{
+    if (n_elem < 0 || bits < 1 || bits > 24 || !idx || !w_out) return -22;
+    if (n_elem == 0) return 0;
+    if ((((uintptr_t)idx | (uintptr_t)w_out) & 15) != 0) return -22;
+    lc_dequant_affine_kernel<<<lc_ew_grid(n_elem), 256, 0, (cudaStream_t)stream>>>(idx, n_elem, (float)((1 << bits) - 1),
+                                                                                   w_out);
+    LC_CUDA_RET();
+    return 0;
+}
+
+int lc_quantize_codebook(const float *z, int64_t n_elem, const float *codebook, int n, int sorted_ascending,
+                         int32_t *idx_out, float *deq_out, void *stream)
+{
+    if (n_elem < 0 || n < 1 || n > 4096 || !z || !codebook || !idx_out) return -22;
+    if (n_elem == 0) return 0;
+    if ((((uintptr_t)z | (uintptr_t)idx_out | (uintptr_t)deq_out) & 15) != 0) return -22;
+    lc_quant_codebook_kernel<<<lc_ew_grid(n_elem), 256, (size_t)n * 4, (cudaStream_t)stream>>>(
+        z, n_elem, codebook, n, sorted_ascending ? 1 : 0, idx_out, deq_out);
+    LC_CUDA_RET();
+    return 0;
+}
+
+int lc_dequantize_codebook(const int32_t *idx, int64_t n_elem, const float *codebook, int n, float *w_out, void *stream)
+{
+    if (n_elem < 0 || n < 1 || n > 4096 || !idx || !codebook || !w_out) return -22;
+    if (n_elem == 0) return 0;
+    if ((((uintptr_t)idx | (uintptr_t)w_out) & 15) != 0) return -22;
+    lc_dequant_codebook_kernel<<<lc_ew_grid(n_elem), 256, (size_t)n * 4, (cudaStream_t)stream>>>(idx, n_elem, codebook, n,
+                                                                                                 w_out);
+    LC_CUDA_RET();
+    return 0;
+}
+
+int lc_coder_grid(int B, int imgs, int R, int C, int n_symbols, int has_ctx)
+{
+    LcCoderCfg cfg;
+    if (B < 1 || lc_make_cfg(cfg, imgs, R, C, n_symbols, 0.05, LC_MODE_REPAIRED, has_ctx)) return -22;
+    return lc_grid_for(cfg, B);
+}
+
+int64_t lc_coder_scratch_bytes(int B, int imgs, int R, int C, int n_symbols, int has_ctx)
+{
+    LcCoderCfg cfg;
+    if (B < 1 || lc_make_cfg(cfg, imgs, R, C, n_symbols, 0.05, LC_MODE_REPAIRED, has_ctx)) return -22;
+    return (int64_t)lc_grid_for(cfg, B) * (int64_t)cfg.scratch_stride;
+}
+
+int64_t lc_encode_slot_bytes(int imgs, int R, int C, int n_symbols)
+{
+    if (imgs < 1 || R < 1 || C < 1 || n_symbols < 2) return -22;
+    int lg = 0;
+    while ((1 << lg) < n_symbols) lg++;
+    // adaptive coding of i.i.d.-like latents costs about log2(n) bits/symbol; allow 1.5x + slack.
+    // A stream that still does not fit reports LC_STATUS_OUT_OVERFLOW and can be retried larger.
+    const int64_t total = (int64_t)imgs * R * C;
+    const int64_t bytes = (total * (lg + 2) * 3 / 2) / 8 + 256;
+    return (bytes + 15) & ~(int64_t)15;
+}
+
+int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_symbols, double adaptation_rate, int mode,
+                    int has_ctx, void *scratch, int64_t scratch_bytes, uint8_t *slots, int64_t slot_bytes,
+                    uint8_t *out_bytes, int64_t out_capacity, int64_t *out_offsets, int32_t *out_nbits, int32_t *status,
+                    int32_t *fault_index, void *stream)
+{
+    LcCoderCfg cfg;
+    if (B < 0 || !idx || !scratch || !slots || !out_nbits || !status || !fault_index) return -22;
+    if (B == 0) return 0;
+    int rc = lc_make_cfg(cfg, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx);
+    if (rc) return rc;
+    if (slot_bytes < 16 || (slot_bytes & 15) || slot_bytes > 0xfffffff0ll) return -22;
+    if (out_bytes && !out_offsets) return -22;
+    if ((((uintptr_t)slots | (uintptr_t)out_bytes | (uintptr_t)scratch) & 15) != 0) return -22;
+    const int grid = lc_grid_for(cfg, B);
+    if (scratch_bytes < (int64_t)grid * (int64_t)cfg.scratch_stride) return -12;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg.sm_bytes > 48 * 1024)
+        cudaFuncSetAttribute(lc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+    lc_encode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, idx, B, slots, (uint32_t)slot_bytes, out_nbits, status,
+                                                     fault_index, (char *)scratch);
+    LC_CUDA_RET();
+    if (out_bytes) {
+        lc_scan_sizes_kernel<<<1, 1024, 0, st>>>(out_nbits, status, B, out_capacity, (long long *)out_offsets);
+        LC_CUDA_RET();
+        lc_compact_kernel<<<B, 128, 0, st>>>(slots, slot_bytes, out_nbits, status, (const long long *)out_offsets, out_bytes);
+        LC_CUDA_RET();
+    }
+    return 0;
+}
+
+int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t *nbits, int B, int imgs, int R, int C,
+                    int n_symbols, double adaptation_rate, int mode, int has_ctx, void *scratch, int64_t scratch_bytes,
+                    int32_t *idx_out, const float *deq_table, float *deq_out, int32_t *status, int32_t *fault_index,
+                    void *stream)
+{
+    LcCoderCfg cfg;
+    if (B < 0 || !bytes || !offsets || !nbits || !scratch || !idx_out || !status || !fault_index) return -22;
+    if (B == 0) return 0;
+    if (deq_out && !deq_table) return -22;
+    int rc = lc_make_cfg(cfg, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx);
+    if (rc) return rc;
+    if ((((uintptr_t)bytes) & 3) != 0 || (((uintptr_t)scratch) & 15) != 0) return -22;
+    const int grid = lc_grid_for(cfg, B);
+    if (scratch_bytes < (int64_t)grid * (int64_t)cfg.scratch_stride) return -12;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg.sm_bytes > 48 * 1024)
+        cudaFuncSetAttribute(lc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+    lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out, deq_table,
+                                                     deq_out, status, fault_index, (char *)scratch);
+    LC_CUDA_RET();
+    return 0;
+}
+
+} // extern "C"

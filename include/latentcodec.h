@@ -1,0 +1,115 @@
+/*
+ * latentcodec.h -- C ABI of liblatentcodec.so: the B200 (sm_100a) implementation of the latent
+ * quantise -> entropy-code -> decode -> dequantise path of yubster4525/image_compression_2.
+ *
+ * The reference has no FFI; its boundary is the Python call surface.  Each
+ * entry point below names the reference code it replaces (file:line under /root/reference).  The
+ * Python drop-in classes in image_compression_2_b200/ bind these through ctypes; INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name says host; sizes are in elements unless
+ *    they say bytes; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *  - all calls are asynchronous on `stream`, keep no global state and never synchronise;
+ *  - return value: 0 on success, a negative errno-style value (-EINVAL = -22) for arguments the
+ *    implementation does not support, or -1000 - cudaError for a CUDA launch error;
+ *  - per-stream faults of the coder are reported in `status[b]` / `fault_index[b]` (LC_STATUS_*),
+ *    mirroring the exceptions the reference raises; kernels never trap.
+ */
+#ifndef LATENTCODEC_H
+#define LATENTCODEC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_ABI_VERSION 1
+
+/* coder modes */
+#define LC_CODER_VERBATIM 0 /* /root/reference/cabac_compression.py as shipped (defect D3 kept)      */
+#define LC_CODER_REPAIRED 1 /* `| full_range` -> `| half_range` at :210/:308, 32-bit mask at :309    */
+
+/* per-stream status words */
+#define LC_STATUS_OK 0
+#define LC_STATUS_ENC_BIT_OVERFLOW 1 /* reference: ValueError, bytearray.append out of range (:193-197) */
+#define LC_STATUS_DEC_SYMBOL_OOB 2   /* reference: IndexError at cumulative_probs[symbol+1] (:291)       */
+#define LC_STATUS_DEC_ZERO_RANGE 3   /* reference: ZeroDivisionError (:285)                              */
+#define LC_STATUS_DEC_NEG_SYMBOL 4   /* reference: symbol -1 / negative-index wraparound (:288-292)      */
+#define LC_STATUS_OUT_OVERFLOW 5     /* per-stream output slot too small                                 */
+#define LC_STATUS_BAD_SYMBOL 6       /* input index outside [0,n_symbols) (reference: IndexError :343)   */
+#define LC_STATUS_POOL_OVERFLOW 7    /* internal scratch exhausted (never expected)                      */
+
+int lc_version(void);
+
+/* ---- quantisers ------------------------------------------------------------------------------ */
+
+/* Quantiser A + dequantiser A: StyleGAN3Compressor.compress, stylegan3_hvae_full.py:313-316.
+ * idx = round_half_even(((w+1)*0.5)*(2^bits-1)) (no clamp), wq = idx/(2^bits-1)*2-1, five separately
+ * rounded fp32 operations.  idx_out and wq_out may each be NULL. */
+int lc_quantize_affine(const float *w, int64_t n_elem, int bits, int32_t *idx_out, float *wq_out, void *stream);
+
+/* Dequantiser A alone (same lines): w_out = idx/(2^bits-1)*2-1. */
+int lc_dequantize_affine(const int32_t *idx, int64_t n_elem, int bits, float *w_out, void *stream);
+
+/* Quantiser B: GumbelSoftmaxDiscretization.forward -> encoding_indices,
+ * gumbel_softmax_compression.py:97,118: argmin_k |z - codebook[k]| in fp32, first minimum.
+ * `codebook` (n fp32, n <= 4096) comes from the host's torch.linspace (:49-52); `sorted_ascending`
+ * != 0 enables the search path (otherwise all n entries are scanned).  deq_out (may be NULL)
+ * receives codebook[idx] (cabac_compression.py:531). */
+int lc_quantize_codebook(const float *z, int64_t n_elem, const float *codebook, int n, int sorted_ascending,
+                         int32_t *idx_out, float *deq_out, void *stream);
+
+/* Dequantiser B: codebook[idx], cabac_compression.py:531 / gumbel_softmax_compression.py:258.
+ * Indices outside [0,n) produce NaN. */
+int lc_dequantize_codebook(const int32_t *idx, int64_t n_elem, const float *codebook, int n, float *w_out,
+                           void *stream);
+
+/* ---- entropy coder --------------------------------------------------------------------------- */
+
+/* A launch codes B independent streams; each stream has `imgs` images of R x C symbols that share
+ * one coder and one FRESH ContextModel (imgs > 1 reproduces the reference's batched
+ * cabac_encode(data[B,R,C]) call, cabac_compression.py:330-337).  has_ctx = 0 selects the single
+ * global context the reference uses for non-3-D shapes (:115-117).  n_symbols must be a power of
+ * two in [2,1024]; imgs*R*C <= 2^22; C <= 8192 when has_ctx. */
+
+/* bytes of device scratch lc_encode_batch / lc_decode_batch need for these arguments */
+int64_t lc_coder_scratch_bytes(int B, int imgs, int R, int C, int n_symbols, int has_ctx);
+
+/* recommended per-stream output slot size in bytes (multiple of 16) */
+int64_t lc_encode_slot_bytes(int imgs, int R, int C, int n_symbols);
+
+/* cabac_encode, cabac_compression.py:315-359 (+ ContextModel :60-162, ArithmeticCoder :166-245).
+ *   idx        int32 [B][imgs*R*C]
+ *   slots      workspace, B * slot_bytes bytes; stream b is written MSB-first packed at
+ *              slots + b*slot_bytes (slot_bytes a multiple of 16)
+ *   out_bytes  may be NULL.  Otherwise the streams are compacted into it: stream b starts at
+ *              out_offsets[b] (16-byte aligned), out_offsets[B] = total bytes used; streams that
+ *              faulted take no space.  If out_offsets[B] would exceed out_capacity nothing is
+ *              copied for the streams that do not fit and their status becomes OUT_OVERFLOW.
+ *   out_offsets int64 [B+1] (required iff out_bytes != NULL)
+ *   out_nbits  int32 [B]: the number of bits the reference encoder appends; bytes = ceil(nbits/8)
+ *   status, fault_index  int32 [B]; fault_index = symbols completely coded before the fault */
+int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_symbols, double adaptation_rate,
+                    int mode, int has_ctx, void *scratch, int64_t scratch_bytes, uint8_t *slots, int64_t slot_bytes,
+                    uint8_t *out_bytes, int64_t out_capacity, int64_t *out_offsets, int32_t *out_nbits,
+                    int32_t *status, int32_t *fault_index, void *stream);
+
+/* cabac_decode, cabac_compression.py:363-406 (+ ArithmeticCoder :247-311).
+ *   bytes, offsets[B], nbits[B]: stream b = ceil(nbits[b]/8) bytes at bytes + offsets[b];
+ *              offsets[b] must be a multiple of 4 and the buffer readable to the next multiple of 4
+ *   idx_out    int32 [B][imgs*R*C], zeros from the fault position on
+ *   deq_table / deq_out: optional fused dequantiser B (deq_out = deq_table[idx], fp32), may be NULL */
+int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t *nbits, int B, int imgs, int R, int C,
+                    int n_symbols, double adaptation_rate, int mode, int has_ctx, void *scratch,
+                    int64_t scratch_bytes, int32_t *idx_out, const float *deq_table, float *deq_out, int32_t *status,
+                    int32_t *fault_index, void *stream);
+
+/* number of thread blocks (= resident streams) the coder kernels launch for B streams */
+int lc_coder_grid(int B, int imgs, int R, int C, int n_symbols, int has_ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATENTCODEC_H */

@@ -1,0 +1,142 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- runs the coder's device code (lc_coder.cuh) on the CPU through the
+ * SIMT emulator in cuda_emul.h.  Built by tests/hostsim/build.py with g++ -ffp-contract=off.
+ * Used by tests/test_hostsim.py to check the warp-cooperative logic without a GPU.
+ */
+#define LC_HOSTSIM 1
+#include "cuda_emul.h"
+
+#include <vector>
+
+#include "../../image_compression_2_b200/csrc/lc_coder.cuh"
+
+namespace emu {
+Warp *g_warp = nullptr;
+
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+
+static void lane_entry()
+{
+    Warp *w = g_warp;
+    w->fn(w->arg);
+    w->done[w->cur] = true;
+    emu_switch(&w->lane_sp[w->cur], w->main_sp);
+    abort(); // a finished lane is never resumed
+}
+
+void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid)
+{
+    static const size_t STACK = 256 * 1024;
+    Warp w;
+    memset(&w, 0, sizeof(w));
+    w.fn = fn; w.arg = arg; w.block = block; w.grid = grid;
+    for (int i = 0; i < 32; i++) {
+        w.lane_stack[i] = (char *)aligned_alloc(64, STACK);
+        uintptr_t top = ((uintptr_t)w.lane_stack[i] + STACK) & ~(uintptr_t)15;
+        uint64_t *sp = (uint64_t *)top;
+        *--sp = 0;                      // fake return address of lane_entry
+        *--sp = (uint64_t)&lane_entry;  // popped by emu_switch's ret
+        for (int r = 0; r < 6; r++) *--sp = 0;
+        w.lane_sp[i] = sp;
+    }
+    Warp *saved = g_warp;
+    g_warp = &w;
+    int alive = 32;
+    while (alive > 0) {
+        const uint64_t gen0 = w.gen;
+        const int arrived0 = w.arrived;
+        const int alive0 = alive;
+        for (int i = 0; i < 32; i++) {
+            if (w.done[i]) continue;
+            w.cur = i;
+            emu_switch(&w.main_sp, w.lane_sp[i]);
+            if (w.done[i]) alive--;
+        }
+        if (alive > 0 && w.gen == gen0 && w.arrived == arrived0 && alive == alive0)
+            die("deadlock: lanes wait at a collective that not all 32 lanes reach", -1);
+    }
+    g_warp = saved;
+    for (int i = 0; i < 32; i++) free(w.lane_stack[i]);
+}
+} // namespace emu
+
+struct EncArgs {
+    LcCoderCfg cfg; const int *codes; int B; unsigned char *out_slots; uint32_t slot_bytes;
+    int *nbits, *status, *fault; char *scratch; char *smem;
+};
+static void enc_body(void *p)
+{
+    EncArgs *a = (EncArgs *)p;
+    lc_encode_block(a->cfg, a->codes, a->B, a->out_slots, a->slot_bytes, a->nbits, a->status, a->fault, a->scratch,
+                    a->smem);
+}
+struct DecArgs {
+    LcCoderCfg cfg; const unsigned char *bytes; const long long *offsets; const int *nbits; int B; int *out; const float *deq_table;
+    float *deq_out; int *status, *fault; char *scratch; char *smem;
+};
+static void dec_body(void *p)
+{
+    DecArgs *a = (DecArgs *)p;
+    lc_decode_block(a->cfg, a->bytes, a->offsets, a->nbits, a->B, a->out, a->deq_table, a->deq_out, a->status, a->fault,
+                    a->scratch, a->smem);
+}
+
+static int make_cfg(LcCoderCfg &cfg, int imgs, int R, int C, int n, double rate, int mode, int has_ctx)
+{
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.n = n; cfg.R = R; cfg.C = C; cfg.imgs = imgs; cfg.has_ctx = has_ctx; cfg.mode = mode; cfg.rate = rate;
+    return lc_cfg_finalize(&cfg);
+}
+
+extern "C" int hostsim_encode(const int *codes, int B, int imgs, int R, int C, int n, double rate, int mode,
+                              int has_ctx, unsigned char *out_slots, unsigned slot_bytes, int *nbits, int *status,
+                              int *fault, int grid)
+{
+    EncArgs a;
+    int rc = make_cfg(a.cfg, imgs, R, C, n, rate, mode, has_ctx);
+    if (rc) return rc;
+    std::vector<char> scratch((size_t)grid * a.cfg.scratch_stride + 256);
+    std::vector<char> smem(a.cfg.sm_bytes + 64);
+    a.codes = codes; a.B = B; a.out_slots = out_slots; a.slot_bytes = slot_bytes;
+    a.nbits = nbits; a.status = status; a.fault = fault; a.scratch = scratch.data();
+    a.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    for (int b = 0; b < grid; b++) emu::run_warp(enc_body, &a, (unsigned)b, (unsigned)grid);
+    return 0;
+}
+
+extern "C" int hostsim_decode(const unsigned char *bytes, const long long *offsets, const int *nbits, int B, int imgs, int R, int C,
+                              int n, double rate, int mode, int has_ctx, int *out, const float *deq_table,
+                              float *deq_out, int *status, int *fault, int grid)
+{
+    DecArgs a;
+    int rc = make_cfg(a.cfg, imgs, R, C, n, rate, mode, has_ctx);
+    if (rc) return rc;
+    std::vector<char> scratch((size_t)grid * a.cfg.scratch_stride + 256);
+    std::vector<char> smem(a.cfg.sm_bytes + 64);
+    a.bytes = bytes; a.offsets = offsets; a.nbits = nbits; a.B = B; a.out = out; a.deq_table = deq_table; a.deq_out = deq_out;
+    a.status = status; a.fault = fault; a.scratch = scratch.data();
+    a.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a, (unsigned)b, (unsigned)grid);
+    return 0;
+}

@@ -1,0 +1,132 @@
+"""The drop-in compressor classes (reference Python surface) on the GPU, with stub encoder/generator."""
+import pickle
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.stubs import StubEncoder, StubGenerator
+
+pytestmark = pytest.mark.gpu
+
+
+def _x(B):
+    return torch.zeros(B, 3, 256, 256, device="cuda")
+
+
+def test_stylegan3_compressor_npz(tmp_path):
+    from image_compression_2_b200 import StyleGAN3Compressor
+    enc, gen = StubEncoder().cuda(), StubGenerator().cuda()
+    comp = StyleGAN3Compressor(enc, gen)
+    x = _x(2)
+    for bits in (4, 8, 10):
+        wq = comp.compress(x, quantization_bits=bits)
+        assert wq.shape == (2, 16, 512) and wq.dtype == torch.float32 and wq.is_cuda
+        _, ref = O.quantize_affine(enc.means_for(2).numpy(), bits)
+        assert np.array_equal(wq.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    fn = str(tmp_path / "lat")
+    ret = comp.save_compressed(x, fn, quantization_bits=8)
+    assert ret == (1572864, 16384.0, 96.0)  # B=2 @256x256, 8 bits
+    data = np.load(fn + ".npz")
+    assert sorted(data.files) == ["bits", "comp_size", "compression_ratio", "orig_size", "resolution", "w"]
+    assert data["w"].dtype == np.float32 and data["w"].shape == (2, 16, 512)
+    assert data["resolution"].dtype == np.int64 and data["resolution"].tolist() == [256, 256]
+    assert data["bits"].dtype == np.int64 and data["orig_size"].dtype == np.int64
+    assert data["comp_size"].dtype == np.float64 and data["compression_ratio"].dtype == np.float64
+    img, ratio = comp.load_compressed(fn + ".npz")
+    assert float(ratio) == 96.0 and img.shape[0] == 2
+    assert torch.equal(img, gen.synthesis(comp.compress(x, 8)))
+
+
+def test_gumbel_compressor_codes_and_npz(tmp_path):
+    from image_compression_2_b200 import GumbelSoftmaxCompressor
+    enc, gen = StubEncoder().cuda(), StubGenerator().cuda()
+    comp = GumbelSoftmaxCompressor(enc, gen, n_embeddings=256).cuda()
+    x = _x(2)
+    codes = comp.compress(x)
+    assert codes.dtype == torch.int64 and codes.device.type == "cpu" and codes.shape == (2, 16, 512)
+    cb = torch.linspace(-1, 1, 256).float().numpy()
+    assert np.array_equal(codes.numpy(), O.quantize_codebook(enc.means_for(2).numpy(), cb))
+    fn = str(tmp_path / "codes")
+    ret = comp.save_compressed(x, fn)
+    assert ret == (1572864, 16384.0, 96.0)
+    data = np.load(fn + ".npz")
+    assert sorted(data.files) == ["codes", "comp_size", "compression_ratio", "n_embeddings", "orig_size", "resolution"]
+    assert data["codes"].dtype == np.int64 and data["n_embeddings"].dtype == np.int64
+    img, ratio = comp.load_compressed(fn + ".npz")
+    w = torch.from_numpy(cb[codes.numpy()]).cuda()
+    assert torch.equal(img, gen.synthesis(w)) and float(ratio) == 96.0
+    deq, perplexity, flat = comp.discretization(enc.means_for(2).cuda())
+    assert torch.equal(flat.cpu(), codes.reshape(-1)) and float(perplexity) > 1
+
+
+def test_cabac_compressor_packed_container_roundtrip(tmp_path):
+    from image_compression_2_b200 import CABACCompressor
+    enc, gen = StubEncoder().cuda(), StubGenerator().cuda()
+    comp = CABACCompressor(enc, gen, n_embeddings=256)
+    comp.discretization.cuda()
+    x = _x(1)
+    encoded, meta = comp.compress(x)
+    cb = torch.linspace(-1, 1, 256).float().numpy()
+    codes = O.quantize_codebook(enc.means_for(1).numpy(), cb)
+    ref = O.encode_stream(codes, 256, "repaired")
+    assert encoded == ref["packed"]
+    assert meta["shape"] == (1, 16, 512) and meta["n_embeddings"] == 256 and meta["use_cabac"] is True
+    assert meta["orig_size"] == 8192.0 and meta["comp_size"] == len(ref["packed"])
+    fn = str(tmp_path / "img.cabac")
+    stats = comp.save_compressed(x, fn)
+    assert stats == (meta["orig_size"], meta["comp_size"], meta["compression_ratio"])
+    img, ratio = comp.load_compressed(fn)
+    assert torch.equal(img, gen.synthesis(torch.from_numpy(cb[codes]).cuda())) and ratio == meta["compression_ratio"]
+    # use_cabac=False: raw int32 codes, as in the reference
+    raw, meta2 = comp.compress(x, use_cabac=False)
+    assert raw == codes.astype(np.int32).tobytes() and meta2["comp_size"] == codes.size * 4
+    assert torch.equal(comp.decompress(raw, meta2), img)
+
+
+def test_cabac_compressor_reference_container_bytes(tmp_path):
+    """container='reference' writes exactly what cabac_compression.py:555-561 writes (defects D1, D4)."""
+    from image_compression_2_b200 import CABACCompressor
+    enc, gen = StubEncoder(seed=3).cuda(), StubGenerator().cuda()
+    comp = CABACCompressor(enc, gen, n_embeddings=256, container="reference")
+    comp.discretization.cuda()
+    x = _x(1)
+    fn = str(tmp_path / "ref.cabac")
+    orig, comp_size, ratio = comp.save_compressed(x, fn)
+    cb = torch.linspace(-1, 1, 256).float().numpy()
+    ref = O.encode_stream(O.quantize_codebook(enc.means_for(1).numpy(), cb), 256, "repaired")
+    assert comp_size == ref["nbits"]  # counts bits as bytes, like the reference
+    blob = open(fn, "rb").read()
+    assert struct.unpack("I", blob[:4])[0] == 6
+    meta = {"shape": (1, 16, 512), "n_embeddings": 256, "use_cabac": True, "orig_size": orig, "comp_size": comp_size,
+            "compression_ratio": ratio}
+    pk = pickle.dumps(meta)
+    assert blob[4:4 + len(pk)] == pk
+    assert blob[4 + len(pk):] == ref["bits"].tobytes()
+
+
+def test_pipeline_host_roundtrip():
+    from image_compression_2_b200 import LatentPipeline
+    from tests.helpers import synth_latents
+    B = 32
+    lat = synth_latents("enc_like", B, 77).pin_memory()
+    for quantizer in ("codebook", "affine"):
+        pipe = LatentPipeline(n_symbols=256, quantizer=quantizer)
+        res = pipe.roundtrip_host(lat)
+        assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any()
+        if quantizer == "codebook":
+            cb = pipe.codebook.cpu().numpy()
+            idx = O.quantize_codebook(lat.numpy(), cb)
+            want = cb[idx]
+        else:
+            idx, want = O.quantize_affine(lat.numpy(), 8)
+        assert np.array_equal(res["deq"].numpy().view(np.uint32), want.view(np.uint32))
+        offs, nbits = res["offsets"].numpy(), res["nbits"].numpy()
+        blob = res["bytes"].numpy()
+        for b in range(0, B, 5):
+            ref = O.encode_stream(idx[b:b + 1], 256, "repaired")
+            assert nbits[b] == ref["nbits"]
+            assert blob[offs[b]:offs[b] + len(ref["packed"])].tobytes() == ref["packed"]
+        assert res["h2d_bytes"] > lat.numel() * 4 and res["d2h_bytes"] > lat.numel() * 4

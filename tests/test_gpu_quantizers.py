@@ -1,0 +1,90 @@
+"""K1/K2 on the B200 through the C ABI, against the reference's golden vectors and the C oracle. Bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.helpers import golden, synth_latents
+
+pytestmark = pytest.mark.gpu
+
+
+def _eq_f32(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return np.array_equal(a.view(np.uint32)[~np.isnan(a)], b.view(np.uint32)[~np.isnan(b)]) and \
+        np.array_equal(np.isnan(a), np.isnan(b))
+
+
+def test_quantiser_a_golden():
+    from image_compression_2_b200 import codec
+    q = golden("quantizers.npz")
+    w = torch.from_numpy(q["w"]).cuda()
+    for bits in (4, 6, 8, 10):
+        idx, wq = codec.quantize_affine(w, bits)
+        ref_idx = q["a_idx_%d" % bits]
+        fin = np.isfinite(ref_idx) & (np.abs(ref_idx) < 2e9)
+        assert np.array_equal(idx.cpu().numpy()[fin], ref_idx[fin].astype(np.int32))
+        assert _eq_f32(wq.cpu().numpy(), q["a_wq_%d" % bits])
+        good = torch.from_numpy(np.where(fin, ref_idx, 0).astype(np.int32)).cuda()
+        assert _eq_f32(codec.dequantize_affine(good, bits).cpu().numpy()[fin], q["a_wq_%d" % bits][fin])
+
+
+def test_quantiser_b_golden():
+    from image_compression_2_b200 import codec
+    q = golden("quantizers.npz")
+    for n in (16, 64, 256, 1024):
+        z = torch.from_numpy(q["b_z_%d" % n]).cuda()
+        cb = torch.from_numpy(q["codebook_%d" % n]).cuda()
+        for sorted_flag in (True, False):
+            idx, deq = codec.quantize_codebook(z, cb, want_deq=True, sorted_ascending=sorted_flag)
+            assert np.array_equal(idx.cpu().numpy(), q["b_idx_%d" % n]), (n, sorted_flag)
+            assert _eq_f32(deq.cpu().numpy(), q["b_deq_%d" % n])
+        assert _eq_f32(codec.dequantize_codebook(idx, cb).cpu().numpy(), q["b_deq_%d" % n])
+
+
+def test_config1_quantisers():
+    from image_compression_2_b200 import codec
+    c = golden("config1.npz")
+    means = torch.from_numpy(c["means"]).cuda()
+    for bits in (4, 8, 10):
+        idx, wq = codec.quantize_affine(means, bits)
+        assert np.array_equal(idx.cpu().numpy(), c["a_idx_%d" % bits].astype(np.int32))
+        assert _eq_f32(wq.cpu().numpy(), c["a_wq_%d" % bits])
+    idx, deq = codec.quantize_codebook(means, torch.from_numpy(c["codebook_256"]).cuda(), want_deq=True)
+    assert np.array_equal(idx.cpu().numpy(), c["b_idx_256"])
+    assert _eq_f32(deq.cpu().numpy(), c["b_deq_256"])
+
+
+@pytest.mark.parametrize("kind", ["enc_like", "wide", "uniform", "hier"])
+def test_quantisers_random_vs_oracle(kind):
+    from image_compression_2_b200 import codec
+    lat = synth_latents(kind, 64, 4242)
+    # ragged length: exercises the non-multiple-of-4 tail
+    flat = lat.reshape(-1)[: lat.numel() - 3].contiguous()
+    for x in (lat, flat):
+        xg = x.cuda()
+        for bits in (4, 8, 10):
+            n = 1 << bits
+            idx, wq = codec.quantize_affine(xg, bits)
+            oi, ow = O.quantize_affine(x.numpy(), bits)
+            assert np.array_equal(idx.cpu().numpy(), oi) and _eq_f32(wq.cpu().numpy(), ow)
+            cb = torch.linspace(-1, 1, n).float()
+            bi, bd = codec.quantize_codebook(xg, cb.cuda(), want_deq=True)
+            ob = O.quantize_codebook(x.numpy(), cb.numpy())
+            assert np.array_equal(bi.cpu().numpy(), ob)
+            assert _eq_f32(bd.cpu().numpy(), cb.numpy()[ob])
+
+
+def test_unsorted_codebook_uses_full_scan():
+    from image_compression_2_b200 import codec
+    g = torch.Generator().manual_seed(3)
+    cb = torch.rand(100, generator=g) * 2 - 1
+    z = torch.randn(4096, generator=g) * 0.6
+    idx, _ = codec.quantize_codebook(z.cuda(), cb.cuda())
+    assert np.array_equal(idx.cpu().numpy(), O.quantize_codebook(z.numpy(), cb.numpy()))
+
+
+def test_cpu_tensor_is_refused():
+    from image_compression_2_b200 import codec
+    with pytest.raises(RuntimeError):
+        codec.quantize_affine(torch.zeros(16), 8)

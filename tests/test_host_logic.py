@@ -1,0 +1,152 @@
+"""CPU-only checks of the host side: the C ABI library loads and exports every declared symbol,
+the sizing helpers, stream layouts, containers, sharding (gloo, world_size 2) and error mapping."""
+import os
+import pickle
+import re
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from image_compression_2_b200 import _native
+    lib = _native.load()
+    header = open(os.path.join(ROOT, "include", "latentcodec.h")).read()
+    declared = set(re.findall(r"\b(lc_[a-z_0-9]+)\s*\(", header))
+    assert declared >= {"lc_version", "lc_quantize_affine", "lc_dequantize_affine", "lc_quantize_codebook",
+                        "lc_dequantize_codebook", "lc_coder_scratch_bytes", "lc_encode_slot_bytes", "lc_encode_batch",
+                        "lc_decode_batch", "lc_coder_grid"}
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(_native.SIGNATURES) == declared
+    assert lib.lc_version() == 1
+
+
+def test_sizing_helpers_without_gpu():
+    from image_compression_2_b200 import _native
+    lib = _native.load()
+    assert lib.lc_coder_grid(1024, 1, 16, 512, 256, 1) == 1024
+    assert lib.lc_coder_grid(65536, 1, 16, 512, 256, 1) % 148 == 0
+    per_warp = lib.lc_coder_scratch_bytes(1, 1, 16, 512, 256, 1)
+    assert per_warp >= 16384 * 8 + 41 * 8192
+    assert lib.lc_coder_scratch_bytes(7, 1, 16, 512, 256, 1) == 7 * per_warp
+    assert lib.lc_encode_slot_bytes(1, 16, 512, 256) % 16 == 0
+    # unsupported: non power of two alphabet, too many symbols
+    assert lib.lc_coder_scratch_bytes(1, 1, 16, 512, 100, 1) == -22
+    assert lib.lc_coder_scratch_bytes(1, 1, 16, 512, 2048, 1) == -22
+    assert lib.lc_coder_grid(0, 1, 16, 512, 256, 1) == -22
+
+
+def test_ops_refuse_cpu_tensors_and_missing_gpu():
+    from image_compression_2_b200 import codec, coder
+    with pytest.raises(RuntimeError):
+        codec.quantize_affine(torch.zeros(4, 4), 8)
+    with pytest.raises(RuntimeError):
+        codec.quantize_codebook(torch.zeros(4, 4), torch.linspace(-1, 1, 16))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            coder.cabac_encode(np.zeros((1, 2, 4), np.int32), coder.ContextModel(16))
+
+
+def test_layouts():
+    from image_compression_2_b200 import codec
+    lay = codec.layout_reference((3, 16, 512))
+    assert (lay.B, lay.imgs, lay.R, lay.C, lay.has_ctx, lay.total) == (1, 3, 16, 512, 1, 3 * 8192)
+    lay = codec.layout_reference((600,))
+    assert (lay.B, lay.imgs, lay.R, lay.C, lay.has_ctx) == (1, 1, 1, 600, 0)
+    lay = codec.layout_reference((2, 3, 4, 5))
+    assert lay.has_ctx == 0 and lay.total == 120
+    lay = codec.layout_independent((7, 16, 512))
+    assert (lay.B, lay.imgs, lay.total) == (7, 1, 8192)
+    with pytest.raises(ValueError):
+        codec.layout_independent((16, 512))
+
+
+def test_status_to_exception_mapping():
+    from image_compression_2_b200 import coder
+    coder.raise_for_status(0, 0, "x")
+    for st, exc in ((1, ValueError), (2, IndexError), (3, ZeroDivisionError), (4, coder.DecodeFault), (6, IndexError),
+                    (5, RuntimeError), (7, RuntimeError)):
+        with pytest.raises(exc):
+            coder.raise_for_status(st, 12, "x")
+    cm = coder.ContextModel()
+    assert (cm.n_symbols, cm.context_size, cm.adaptation_rate) == (256, 5, 0.05) and cm.is_fresh()
+
+
+def test_cabac_containers(tmp_path):
+    from image_compression_2_b200 import containers
+    meta = {"shape": (1, 16, 512), "n_embeddings": 256, "use_cabac": True, "orig_size": 8192.0, "comp_size": 10,
+            "compression_ratio": 819.2}
+    fn = str(tmp_path / "a.cabac")
+    containers.write_cabac(fn, b"0123456789", meta, "packed")
+    payload, m = containers.read_cabac(fn)
+    assert payload == b"0123456789" and m == meta
+    containers.write_cabac(fn, b"\x00\x01\x01", meta, "reference")
+    blob = open(fn, "rb").read()
+    assert struct.unpack("I", blob[:4])[0] == len(meta) == 6  # defect D4 reproduced
+    assert blob[4:] == pickle.dumps(meta) + b"\x00\x01\x01"
+    with pytest.raises(Exception):
+        containers.read_cabac(fn)  # ... and, like the reference's loader, it cannot be read back
+
+
+def test_npz_containers(tmp_path):
+    from image_compression_2_b200 import containers
+    w = np.zeros((2, 16, 512), np.float32)
+    fn = str(tmp_path / "w")
+    containers.write_latent_npz(fn, w, torch.Size([256, 256]), 8, 1572864, 16384.0)
+    d = np.load(fn + ".npz")
+    assert {k: (d[k].dtype.str, d[k].shape) for k in d.files} == {
+        "w": ("<f4", (2, 16, 512)), "resolution": ("<i8", (2,)), "bits": ("<i8", ()), "orig_size": ("<i8", ()),
+        "comp_size": ("<f8", ()), "compression_ratio": ("<f8", ())}
+    assert float(d["compression_ratio"]) == 96.0
+
+
+def test_pack_streams_layout():
+    from image_compression_2_b200 import codec
+    data, offs, nbits = codec.pack_streams_for_device([b"abc", b"", b"x" * 17], "cpu")
+    assert offs.tolist() == [0, 16, 16, 48] and nbits.tolist() == [24, 0, 136]
+    assert data[:3].numpy().tobytes() == b"abc" and data[16:33].numpy().tobytes() == b"x" * 17
+
+
+def test_shard_ranges():
+    from image_compression_2_b200.sharding import shard_range
+    for B, G in ((65536, 8), (1024, 3), (5, 8), (0, 4)):
+        spans = [shard_range(B, r, G) for r in range(G)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from image_compression_2_b200.sharding import shard_range, gather_shard_bytes, global_stream_offsets
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+r = dist.get_rank()
+lo, hi = shard_range(11, r, 2)
+local_sizes = torch.tensor([16 * (i + 1) for i in range(lo, hi)])
+local_offsets = torch.cumsum(local_sizes, 0) - local_sizes
+sizes, base = gather_shard_bytes(int(local_sizes.sum()))
+assert sizes.tolist() == [sum(16 * (i + 1) for i in range(0, 6)), sum(16 * (i + 1) for i in range(6, 11))], sizes
+glob = global_stream_offsets(local_offsets, base)
+want = torch.cumsum(torch.tensor([16 * (i + 1) for i in range(11)]), 0) - torch.tensor([16 * (i + 1) for i in range(11)])
+assert glob.tolist() == want[lo:hi].tolist()
+dist.barrier(); dist.destroy_process_group(); print("rank", r, "ok")
+'''
+
+
+def test_size_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
