@@ -4,8 +4,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cub/block/block_radix_sort.cuh>
+
 #include "../../include/latentcodec.h"
 #include "lc_coder.cuh"
+#include "lc_encoder_par.cuh"
 
 #define LC_CUDA_RET()                                                     \
     do {                                                                  \
@@ -208,6 +211,72 @@ __global__ void __launch_bounds__(32) lc_decode_kernel(LcCoderCfg cfg, const uns
 }
 
 // =================================================================================================
+// K3-parallel: the encoder split by context group (lc_encoder_par.cuh)
+//   phase S: keys + stable sort by key (one 256-thread block per stream, CUB block radix sort)
+//   phase A: exact intervals per position, one warp per context group, 8 warps per stream
+//   phase B: the serial range coder over those intervals, one warp per stream
+// =================================================================================================
+typedef cub::BlockRadixSort<uint32_t, 256, LC_PAR_MAX_SYMBOLS / 256, unsigned short> LcBlockSort;
+
+__global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const int *__restrict__ codes,
+                                                          uint32_t *__restrict__ skeys, unsigned short *__restrict__ spos,
+                                                          int *__restrict__ first_bad)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    LcBlockSort::TempStorage &temp = *reinterpret_cast<LcBlockSort::TempStorage *>(lc_smem);
+    __shared__ int s_first_bad;
+    constexpr int ITEMS = LC_PAR_MAX_SYMBOLS / 256;
+    const int total = cfg.total, n = cfg.n, C = cfg.C, RC = cfg.R * cfg.C;
+    const int *c = codes + (size_t)blockIdx.x * total;
+    if (threadIdx.x == 0) s_first_bad = total;
+    __syncthreads();
+    for (int p = threadIdx.x; p < total; p += 256) {
+        const int s = c[p];
+        if (s < 0 || s >= n) atomicMin(&s_first_bad, p);
+    }
+    __syncthreads();
+    const int fb = s_first_bad;
+    uint32_t keys[ITEMS];
+    unsigned short vals[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const int p = (int)threadIdx.x * ITEMS + i; // blocked arrangement = position order (stable sort keeps it)
+        vals[i] = (unsigned short)p;
+        uint32_t k = LC_PAR_KEY_PAD;
+        if (p < fb) {
+            const int q = p % RC, cc = q % C, rr = q / C;
+            const int left = cc > 0 ? c[p - 1] : -1;
+            const int up = rr > 0 ? c[p - C] : -1;
+            k = (uint32_t)(left + 1) * (uint32_t)(n + 1) + (uint32_t)(up + 1);
+        }
+        keys[i] = k;
+    }
+    LcBlockSort(temp).Sort(keys, vals, 0, 22); // real keys < 2^21; padding (low 22 bits all ones) sorts last
+    uint32_t *ok = skeys + (size_t)blockIdx.x * LC_PAR_MAX_SYMBOLS + (size_t)threadIdx.x * ITEMS;
+    unsigned short *ov = spos + (size_t)blockIdx.x * LC_PAR_MAX_SYMBOLS + (size_t)threadIdx.x * ITEMS;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) { ok[i] = keys[i]; ov[i] = vals[i]; }
+    if (threadIdx.x == 0) first_bad[blockIdx.x] = fb;
+}
+
+__global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
+                                                             const uint32_t *__restrict__ skeys,
+                                                             const unsigned short *__restrict__ spos,
+                                                             const int *__restrict__ first_bad, double *clo, double *chi)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lc_enc_phase_a_block(cfg, codes, B, skeys, spos, first_bad, clo, chi, lc_smem);
+}
+
+__global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
+                                                            const double *__restrict__ clo, const double *__restrict__ chi,
+                                                            unsigned char *slots, uint32_t slot_bytes, int *nbits,
+                                                            int *status, int *fault)
+{
+    lc_enc_phase_b_block(cfg, B, first_bad, clo, chi, slots, slot_bytes, nbits, status, fault);
+}
+
+// =================================================================================================
 // K4: stream compaction -- exclusive scan of the 16-byte-aligned stream sizes, then a word copy
 // =================================================================================================
 __global__ void __launch_bounds__(1024) lc_scan_sizes_kernel(const int *__restrict__ nbits, int *status, int B,
@@ -286,6 +355,22 @@ static int lc_grid_for(const LcCoderCfg &cfg, int B)
     return g < 1 ? 1 : (int)g;
 }
 
+// parallel-encoder workspace per stream: sorted keys (4 B) + positions (2 B) + two float64 bounds
+#define LC_PAR_STREAM_BYTES ((int64_t)LC_PAR_MAX_SYMBOLS * (4 + 2 + 8 + 8) + 16)
+#define LC_PAR_TILE 2048
+
+static bool lc_use_parallel_encoder(const LcCoderCfg &cfg) { return cfg.has_ctx && cfg.total <= LC_PAR_MAX_SYMBOLS; }
+
+static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
+{
+    int64_t need = (int64_t)lc_grid_for(cfg, B) * (int64_t)cfg.scratch_stride;
+    if (lc_use_parallel_encoder(cfg)) {
+        const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES;
+        if (par > need) need = par;
+    }
+    return need;
+}
+
 static int lc_ew_grid(long long n_elem)
 {
     long long blocks = (n_elem / 4 + 255) / 256;
@@ -354,7 +439,7 @@ int64_t lc_coder_scratch_bytes(int B, int imgs, int R, int C, int n_symbols, int
 {
     LcCoderCfg cfg;
     if (B < 1 || lc_make_cfg(cfg, imgs, R, C, n_symbols, 0.05, LC_MODE_REPAIRED, has_ctx)) return -22;
-    return (int64_t)lc_grid_for(cfg, B) * (int64_t)cfg.scratch_stride;
+    return lc_scratch_need(cfg, B);
 }
 
 int64_t lc_encode_slot_bytes(int imgs, int R, int C, int n_symbols)
@@ -382,14 +467,42 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
     if (slot_bytes < 16 || (slot_bytes & 15) || slot_bytes > 0xfffffff0ll) return -22;
     if (out_bytes && !out_offsets) return -22;
     if ((((uintptr_t)slots | (uintptr_t)out_bytes | (uintptr_t)scratch) & 15) != 0) return -22;
-    const int grid = lc_grid_for(cfg, B);
-    if (scratch_bytes < (int64_t)grid * (int64_t)cfg.scratch_stride) return -12;
+    if (scratch_bytes < lc_scratch_need(cfg, B)) return -12;
     cudaStream_t st = (cudaStream_t)stream;
-    if (cfg.sm_bytes > 48 * 1024)
-        cudaFuncSetAttribute(lc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
-    lc_encode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, idx, B, slots, (uint32_t)slot_bytes, out_nbits, status,
-                                                     fault_index, (char *)scratch);
-    LC_CUDA_RET();
+    if (lc_use_parallel_encoder(cfg)) {
+        const size_t sort_smem = sizeof(LcBlockSort::TempStorage);
+        const size_t a_smem = (size_t)8 * cfg.n * 8;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+            cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
+            attr_done = true;
+        }
+        for (int b0 = 0; b0 < B; b0 += LC_PAR_TILE) {
+            const int nb = (B - b0) < LC_PAR_TILE ? (B - b0) : LC_PAR_TILE;
+            char *ws = (char *)scratch;
+            uint32_t *skeys = (uint32_t *)ws;                 ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 4;
+            double *clo = (double *)ws;                       ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 8;
+            double *chi = (double *)ws;                       ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 8;
+            unsigned short *spos = (unsigned short *)ws;      ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 2;
+            int *first_bad = (int *)ws;
+            const int *codes = idx + (size_t)b0 * cfg.total;
+            lc_enc_sort_kernel<<<nb, 256, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad);
+            LC_CUDA_RET();
+            lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, clo, chi);
+            LC_CUDA_RET();
+            lc_enc_phase_b_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, clo, chi, slots + (size_t)b0 * slot_bytes,
+                                                    (uint32_t)slot_bytes, out_nbits + b0, status + b0, fault_index + b0);
+            LC_CUDA_RET();
+        }
+    } else {
+        const int grid = lc_grid_for(cfg, B);
+        if (cfg.sm_bytes > 48 * 1024)
+            cudaFuncSetAttribute(lc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+        lc_encode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, idx, B, slots, (uint32_t)slot_bytes, out_nbits, status,
+                                                         fault_index, (char *)scratch);
+        LC_CUDA_RET();
+    }
     if (out_bytes) {
         lc_scan_sizes_kernel<<<1, 1024, 0, st>>>(out_nbits, status, B, out_capacity, (long long *)out_offsets);
         LC_CUDA_RET();
@@ -412,7 +525,7 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
     if (rc) return rc;
     if ((((uintptr_t)bytes) & 3) != 0 || (((uintptr_t)scratch) & 15) != 0) return -22;
     const int grid = lc_grid_for(cfg, B);
-    if (scratch_bytes < (int64_t)grid * (int64_t)cfg.scratch_stride) return -12;
+    if (scratch_bytes < lc_scratch_need(cfg, B)) return -12;
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg.sm_bytes > 48 * 1024)
         cudaFuncSetAttribute(lc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);

@@ -51,6 +51,14 @@ struct LcWarp {
     int status;
 };
 
+#ifdef LC_HOSTSIM
+struct LcStats { long long syms, fresh, search_fail, interval_fail, enc_interval_fail; };
+static LcStats g_lc_stats;
+#define LC_STAT(field) do { if ((threadIdx.x & 31) == 0) g_lc_stats.field++; } while (0)
+#else
+#define LC_STAT(field) do { } while (0)
+#endif
+
 struct LcInterval {
     int sym;
     double clo, chi;
@@ -484,6 +492,7 @@ __device__ __forceinline__ long long lc_encode_stream(LcWarp &W, const int *code
             iv.chi = iv.clo + lp.ps;
         }
         if (!lc_interval_apply(iv, W.delta, low, high)) {
+            LC_STAT(enc_interval_fail);
             if (!W.dense_ready) lc_dense_fresh(W);
             iv = lc_exact_cum_enc(W.dense, s);
             lc_interval_apply(iv, W.delta, low, high);
@@ -560,10 +569,13 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
         } else {
             fast = lc_search_fast(W, v, iv);
         }
-        if (!fast) { if (!W.dense_ready) lc_dense_fresh(W); iv = lc_exact_search_dec(W.dense, W.n, v); }
+        LC_STAT(syms);
+        if (!W.found) LC_STAT(fresh);
+        if (!fast) { LC_STAT(search_fail); if (!W.dense_ready) lc_dense_fresh(W); iv = lc_exact_search_dec(W.dense, W.n, v); }
         if (iv.sym >= W.n) { W.status = LC_DEC_SYMBOL_OOB; break; }
         if (iv.sym < 0) { W.status = LC_DEC_NEG_SYMBOL; break; }
         if (!lc_interval_apply(iv, W.delta, low, high)) {
+            LC_STAT(interval_fail);
             if (!W.dense_ready) lc_dense_fresh(W);
             iv = lc_exact_search_dec(W.dense, W.n, v);
             lc_interval_apply(iv, W.delta, low, high);

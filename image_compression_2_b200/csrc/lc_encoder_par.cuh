@@ -1,0 +1,190 @@
+// Parallel encoder (streams of at most LC_PAR_MAX_SYMBOLS symbols with (left,up) contexts).
+//
+// The encoder knows every symbol up front, and a context's probability vector depends only on the
+// ordered symbols seen IN THAT CONTEXT (cabac_compression.py:128,143,157 are the only accesses to
+// context_models[ctx]).  So cabac_encode (cabac_compression.py:315-359) splits into
+//   phase S  per stream: context key of every position, stable sort of positions by key
+//            (kernel lc_enc_sort_kernel in latentcodec.cu, CUB block radix sort);
+//   phase A  per context group, in parallel over all groups of all streams: evolve the dense
+//            float64 model exactly as ContextModel.update_model does (:119-144) and write, for
+//            every position, the exact interval (cum[s], cum[s+1]) of np.cumsum (:346-347);
+//            updates after a group's last visit are never read and are skipped;
+//   phase B  per stream, serial: ArithmeticCoder.encode_symbol / renormalise / underflow /
+//            finish (:189-245) consuming those intervals -- two multiplies, two truncations and
+//            the bit emission per symbol.
+// Phase A is the float64-heavy part and runs at full occupancy; phase B is a short dependent
+// chain.  Results are bit-identical to the serial evaluation because every float64 operation is
+// the same operation on the same operands in the same order.
+#pragma once
+#include "lc_coder.cuh"
+
+#define LC_PAR_MAX_SYMBOLS 8192
+#define LC_PAR_KEY_PAD 0xFFFFFFFFu
+
+// exact np.cumsum prefix: sum of dense[0..s) in index order (all lanes compute the same value)
+__device__ __forceinline__ double lc_dense_prefix(const double *dense, int s)
+{
+    double T = 0.0;
+    int i = 0;
+    for (; i + 4 <= s; i += 4) {
+        const double a = dense[i], b = dense[i + 1], c = dense[i + 2], d = dense[i + 3];
+        T = LC_DADD(T, a); T = LC_DADD(T, b); T = LC_DADD(T, c); T = LC_DADD(T, d);
+    }
+    for (; i < s; i++) T = LC_DADD(T, dense[i]);
+    return T;
+}
+
+// ContextModel.update_model (:119-144) on the dense image held in shared memory
+__device__ __forceinline__ void lc_dense_update(LcWarp &W, int s)
+{
+    const double p_old = W.dense[s];
+    const double p_new = LC_DADD(p_old, LC_DMUL(W.rate, LC_DSUB(1.0, p_old)));
+    __syncwarp();
+    if (W.lane == 0) W.dense[s] = p_new;
+    __syncwarp();
+    const double total = lc_pairwise_total(W);
+    __syncwarp(); // every lane has read the image before it is scaled in place
+    const double others = LC_DSUB(total, p_new);
+    const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, p_new), others) : 0.0;
+    for (int i = W.lane; i < W.n; i += 32)
+        if (i != s) W.dense[i] = LC_DMUL(W.dense[i], f);
+    __syncwarp();
+}
+
+// Phase A for one warp.  skeys/spos: this stream's positions sorted by (key, position); entries at
+// index >= total are padding.  clo/chi: float64 [total], indexed by position.
+__device__ __forceinline__ void lc_enc_phase_a_warp(LcWarp &W, const int *__restrict__ codes,
+                                                    const uint32_t *__restrict__ skeys,
+                                                    const unsigned short *__restrict__ spos, double *clo, double *chi,
+                                                    int total, int warp_id, int n_warps)
+{
+    for (int chunk = warp_id; chunk * 32 < total; chunk += n_warps) {
+        const int j = chunk * 32 + W.lane;
+        const bool valid = j < total;
+        const uint32_t kj = valid ? skeys[j] : 0u;
+        const bool head = valid && (j == 0 || skeys[j - 1] != kj);
+        if (head) { // first visit of a context: uniform model, cum[i] = i/n exactly
+            const int p = spos[j];
+            const int s = codes[p];
+            clo[p] = LC_DMUL((double)s, W.u0);
+            chi[p] = LC_DMUL((double)(s + 1), W.u0);
+        }
+        const bool multi = head && (j + 1 < total) && (skeys[j + 1] == kj);
+        unsigned m = __ballot_sync(LC_FULL_MASK, multi);
+        while (m) {
+            const int l = __ffs((int)m) - 1;
+            m &= m - 1;
+            int t = chunk * 32 + l;
+            const uint32_t key = skeys[t];
+            for (int i = W.lane; i < W.n; i += 32) W.dense[i] = W.u0;
+            __syncwarp();
+            for (;;) {
+                const int p = spos[t];
+                const int s = codes[p];
+                const bool last = (t + 1 >= total) || (skeys[t + 1] != key);
+                if (t != chunk * 32 + l) {
+                    const double T = lc_dense_prefix(W.dense, s);
+                    if (W.lane == 0) { clo[p] = T; chi[p] = LC_DADD(T, W.dense[s]); }
+                }
+                if (last) break;
+                lc_dense_update(W, s);
+                t++;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Phase B for one stream (one warp): the range coder over precomputed exact intervals.
+__device__ __forceinline__ long long lc_enc_phase_b_stream(LcWarp &W, const double *__restrict__ clo,
+                                                           const double *__restrict__ chi, int limit, uint32_t *out,
+                                                           uint32_t cap_words, int *fault_index)
+{
+    LcBitWriter bw; lc_bw_init(bw, out, cap_words);
+    long long low = 0, high = LC_FULL - 1, outstanding = 0;
+    const long long fix = (W.mode == LC_MODE_VERBATIM) ? LC_FULL : LC_HALF; // defect D3
+    double my_lo = 0.0, my_hi = 0.0;
+    int pos = 0;
+    W.status = LC_OK;
+    for (; pos < limit; pos++) {
+        const int l = pos & 31;
+        if (l == 0) {
+            const int p = pos + W.lane;
+            if (p < limit) { my_lo = clo[p]; my_hi = chi[p]; }
+        }
+        LcInterval iv;
+        iv.clo = __shfl_sync(LC_FULL_MASK, my_lo, l);
+        iv.chi = __shfl_sync(LC_FULL_MASK, my_hi, l);
+        iv.exact = 1; iv.sym = 0;
+        lc_interval_apply(iv, 0.0, low, high);
+        while ((high & LC_HALF) == (low & LC_HALF)) {
+            const long long bit = high >> 31;
+            if (bit < 0 || bit > 1 || (outstanding > 0 && (1 - bit) < 0)) { W.status = LC_ENC_BIT_OVERFLOW; break; }
+            lc_bw_put(bw, (int)bit, 1, W.lane);
+            if (outstanding > 0) lc_bw_put(bw, (int)(1 - bit), outstanding, W.lane);
+            outstanding = 0;
+            low = (low << 1) & (LC_FULL - 1);
+            high = ((high << 1) & (LC_FULL - 1)) | 1;
+        }
+        if (W.status != LC_OK) break;
+        while ((low & LC_QUARTER) != 0 && (high & LC_QUARTER) == 0) {
+            outstanding += 1;
+            low = (low << 1) & (LC_HALF - 1);
+            high = ((high << 1) & (LC_HALF - 1)) | fix | 1;
+        }
+        if (bw.ovf) { W.status = LC_OUT_OVERFLOW; break; }
+    }
+    *fault_index = pos;
+    if (W.status != LC_OK) return 0;
+    outstanding += 1;
+    const int first = (low & LC_QUARTER) != 0 ? 1 : 0;
+    lc_bw_put(bw, first, 1, W.lane);
+    lc_bw_put(bw, 1 - first, outstanding, W.lane);
+    lc_bw_finish(bw, W.lane);
+    if (bw.ovf) { W.status = LC_OUT_OVERFLOW; return 0; }
+    return bw.nbits;
+}
+
+// ---- block entry points --------------------------------------------------------------------------
+
+// Phase A: one block per stream, blockDim.x/32 warps share the stream's groups.  `smem` holds one
+// dense image (n doubles) per warp.  first_bad[b] (= total when the stream is clean) is the position of
+// the first out-of-range symbol found by phase S: only the positions before it are sorted (the
+// rest carry padding keys) and coded, then phase B reports LC_BAD_SYMBOL there -- exactly where
+// the serial encoder stops.
+__device__ __forceinline__ void lc_enc_phase_a_block(const LcCoderCfg &cfg, const int *codes, int B,
+                                                     const uint32_t *skeys, const unsigned short *spos,
+                                                     const int *first_bad, double *clo, double *chi, char *smem)
+{
+    const int warp_id = (int)(threadIdx.x >> 5), n_warps = (int)(blockDim.x >> 5);
+    LcWarp W;
+    lc_warp_init(W, cfg, smem, (char *)0);
+    W.dense = (double *)smem + (size_t)warp_id * cfg.n;
+    for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
+        const size_t o = (size_t)sidx * LC_PAR_MAX_SYMBOLS;
+        const int fb = first_bad[sidx];
+        lc_enc_phase_a_warp(W, codes + (size_t)sidx * cfg.total, skeys + o, spos + o, clo + o, chi + o,
+                            fb < cfg.total ? fb : cfg.total, warp_id, n_warps);
+    }
+}
+
+// Phase B: one warp per stream (blockDim.x = 32).
+__device__ __forceinline__ void lc_enc_phase_b_block(const LcCoderCfg &cfg, int B, const int *first_bad,
+                                                     const double *clo, const double *chi, unsigned char *out_slots,
+                                                     uint32_t slot_bytes, int *nbits, int *status, int *fault)
+{
+    LcWarp W;
+    lc_warp_init(W, cfg, (char *)0, (char *)0);
+    for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
+        const size_t o = (size_t)sidx * LC_PAR_MAX_SYMBOLS;
+        const int fb = first_bad[sidx];
+        const int limit = fb < cfg.total ? fb : cfg.total;
+        int fi = 0;
+        long long nb = lc_enc_phase_b_stream(W, clo + o, chi + o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
+                                             slot_bytes / 4, &fi);
+        int st = W.status;
+        if (st == LC_OK && fb < cfg.total) { st = LC_BAD_SYMBOL; fi = fb; nb = 0; }
+        if (W.lane == 0) { nbits[sidx] = (int)nb; status[sidx] = st; fault[sidx] = fi; }
+        __syncwarp();
+    }
+}

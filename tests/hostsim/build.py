@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 SO = os.path.join(HERE, "_build", "libhostsim.so")
 SRCS = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "cuda_emul.h"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_coder.cuh"),
-        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_common.cuh")]
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_common.cuh"),
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_par.cuh")]
 _lib = None
 
 
@@ -87,3 +88,21 @@ def decode(streams, n, shape, mode=1, rate=0.05, grid=None, codebook=None):
                               _p(status, ctypes.c_int), _p(fault, ctypes.c_int), grid)
     assert rc == 0, rc
     return out.reshape(shape), status, fault, deq
+
+
+def encode_par(codes, n, mode=1, rate=0.05, slot_bytes=None, grid=None, nwarps=3):
+    """Parallel encoder (phase S on the host, phases A/B emulated). codes: (B,R,C) or (B,imgs,R,C)."""
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    B, imgs, R, C, has_ctx = _shape(codes.shape)
+    assert has_ctx
+    total = imgs * R * C
+    if slot_bytes is None:
+        slot_bytes = ((total * 12 + 64) + 3) // 4 * 4
+    grid = grid or min(B, 3)
+    out = np.zeros((B, slot_bytes), np.uint8)
+    nbits = np.zeros(B, np.int32); status = np.zeros(B, np.int32); fault = np.zeros(B, np.int32)
+    rc = lib().hostsim_encode_par(_p(codes, ctypes.c_int), B, imgs, R, C, int(n), ctypes.c_double(rate), int(mode),
+                                  _p(out, ctypes.c_ubyte), ctypes.c_uint(slot_bytes), _p(nbits, ctypes.c_int),
+                                  _p(status, ctypes.c_int), _p(fault, ctypes.c_int), grid, nwarps)
+    assert rc == 0, rc
+    return out, nbits, status, fault

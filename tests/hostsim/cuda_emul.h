@@ -6,7 +6,8 @@
  * One warp = 32 coroutines (hand-rolled x86-64 stack switch) scheduled round-robin on one OS
  * thread.  Warp collectives (__shfl*_sync, __ballot_sync, __syncwarp) are rendezvous points; the
  * emulator aborts if the 32 lanes do not all reach the SAME collective call site (divergence bug)
- * or if a lane exits while others wait.  One block = one warp (that is how the coder launches).
+ * or if a lane exits while others wait.  Blocks may have several warps as long as the warps do
+ * not synchronise with one another (they are then run one after the other).
  */
 #pragma once
 #include <cmath>
@@ -43,16 +44,16 @@ struct Warp {
     int site[32];
     void (*fn)(void *);
     void *arg;
-    unsigned block, grid;
+    unsigned block, grid, warp, nwarps;
 };
 
 extern Warp *g_warp;
 
 extern "C" void emu_switch(void **save_sp, void *load_sp);
 
-inline Dim tid() { return Dim{(unsigned)g_warp->cur, 0, 0}; }
+inline Dim tid() { return Dim{g_warp->warp * 32u + (unsigned)g_warp->cur, 0, 0}; }
 inline Dim bid() { return Dim{g_warp->block, 0, 0}; }
-inline Dim bdim() { return Dim{32, 1, 1}; }
+inline Dim bdim() { return Dim{32u * g_warp->nwarps, 1, 1}; }
 inline Dim gdim() { return Dim{g_warp->grid, 1, 1}; }
 
 inline void yield_to_main() {
@@ -132,7 +133,7 @@ inline unsigned ballot(int pred, int site) {
     return m;
 }
 
-void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid);
+void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned warp = 0, unsigned nwarps = 1);
 
 } // namespace emu
 
@@ -142,7 +143,7 @@ void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid);
 #define gridDim (emu::gdim())
 
 #define __shfl_sync(mask, v, src) emu::shfl((v), (src), __LINE__)
-#define __shfl_xor_sync(mask, v, lanemask) emu::shfl((v), (int)(emu::tid().x ^ (unsigned)(lanemask)), __LINE__)
+#define __shfl_xor_sync(mask, v, lanemask) emu::shfl((v), (int)((emu::tid().x & 31u) ^ (unsigned)(lanemask)), __LINE__)
 #define __shfl_up_sync(mask, v, delta) emu::shfl_up((v), (delta), __LINE__)
 #define __shfl_down_sync(mask, v, delta) emu::shfl_down((v), (delta), __LINE__)
 #define __ballot_sync(mask, pred) emu::ballot((pred), __LINE__)

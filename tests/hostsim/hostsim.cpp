@@ -9,6 +9,9 @@
 #include <vector>
 
 #include "../../image_compression_2_b200/csrc/lc_coder.cuh"
+#include "../../image_compression_2_b200/csrc/lc_encoder_par.cuh"
+#include <algorithm>
+#include <numeric>
 
 namespace emu {
 Warp *g_warp = nullptr;
@@ -45,12 +48,12 @@ static void lane_entry()
     abort(); // a finished lane is never resumed
 }
 
-void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid)
+void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned warp, unsigned nwarps)
 {
     static const size_t STACK = 256 * 1024;
     Warp w;
     memset(&w, 0, sizeof(w));
-    w.fn = fn; w.arg = arg; w.block = block; w.grid = grid;
+    w.fn = fn; w.arg = arg; w.block = block; w.grid = grid; w.warp = warp; w.nwarps = nwarps;
     for (int i = 0; i < 32; i++) {
         w.lane_stack[i] = (char *)aligned_alloc(64, STACK);
         uintptr_t top = ((uintptr_t)w.lane_stack[i] + STACK) & ~(uintptr_t)15;
@@ -138,5 +141,72 @@ extern "C" int hostsim_decode(const unsigned char *bytes, const long long *offse
     a.status = status; a.fault = fault; a.scratch = scratch.data();
     a.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a, (unsigned)b, (unsigned)grid);
+    return 0;
+}
+
+extern "C" void hostsim_stats(long long *out, int reset)
+{
+    out[0] = g_lc_stats.syms; out[1] = g_lc_stats.fresh; out[2] = g_lc_stats.search_fail;
+    out[3] = g_lc_stats.interval_fail; out[4] = g_lc_stats.enc_interval_fail;
+    if (reset) memset(&g_lc_stats, 0, sizeof(g_lc_stats));
+}
+
+// ---- parallel encoder: phase S restated on the host (the real kernel uses a CUB block sort and is
+// checked on the GPU), phases A and B run through the emulator
+struct ParAArgs { LcCoderCfg cfg; const int *codes; int B; const uint32_t *skeys; const unsigned short *spos;
+                  const int *first_bad; double *clo, *chi; char *smem; };
+static void para_body(void *p)
+{
+    ParAArgs *a = (ParAArgs *)p;
+    lc_enc_phase_a_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->clo, a->chi, a->smem);
+}
+struct ParBArgs { LcCoderCfg cfg; int B; const int *first_bad; const double *clo, *chi; unsigned char *out_slots;
+                  uint32_t slot_bytes; int *nbits, *status, *fault; };
+static void parb_body(void *p)
+{
+    ParBArgs *a = (ParBArgs *)p;
+    lc_enc_phase_b_block(a->cfg, a->B, a->first_bad, a->clo, a->chi, a->out_slots, a->slot_bytes, a->nbits, a->status,
+                         a->fault);
+}
+
+extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int C, int n, double rate, int mode,
+                                  unsigned char *out_slots, unsigned slot_bytes, int *nbits, int *status, int *fault,
+                                  int grid, int nwarps)
+{
+    LcCoderCfg cfg;
+    int rc = make_cfg(cfg, imgs, R, C, n, rate, mode, 1);
+    if (rc) return rc;
+    if (cfg.total > LC_PAR_MAX_SYMBOLS) return -22;
+    const int total = cfg.total, RC = R * C;
+    std::vector<uint32_t> skeys((size_t)B * LC_PAR_MAX_SYMBOLS, LC_PAR_KEY_PAD);
+    std::vector<unsigned short> spos((size_t)B * LC_PAR_MAX_SYMBOLS, 0);
+    std::vector<int> first_bad(B);
+    for (int b = 0; b < B; b++) {
+        const int *c = codes + (size_t)b * total;
+        int fb = total;
+        for (int p = 0; p < total; p++) if (c[p] < 0 || c[p] >= n) { fb = p; break; }
+        first_bad[b] = fb;
+        std::vector<uint32_t> keys(LC_PAR_MAX_SYMBOLS, LC_PAR_KEY_PAD);
+        for (int p = 0; p < fb; p++) {
+            const int q = p % RC, cc = q % C, rr = q / C;
+            const int left = cc > 0 ? c[p - 1] : -1, up = rr > 0 ? c[p - C] : -1;
+            keys[p] = (uint32_t)(left + 1) * (uint32_t)(n + 1) + (uint32_t)(up + 1);
+        }
+        std::vector<int> order(LC_PAR_MAX_SYMBOLS);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return keys[x] < keys[y]; });
+        for (int j = 0; j < LC_PAR_MAX_SYMBOLS; j++) {
+            skeys[(size_t)b * LC_PAR_MAX_SYMBOLS + j] = keys[order[j]];
+            spos[(size_t)b * LC_PAR_MAX_SYMBOLS + j] = (unsigned short)order[j];
+        }
+    }
+    std::vector<double> clo((size_t)B * LC_PAR_MAX_SYMBOLS, -1.0), chi((size_t)B * LC_PAR_MAX_SYMBOLS, -1.0);
+    std::vector<char> smem((size_t)nwarps * n * 8 + 64);
+    ParAArgs a{cfg, codes, B, skeys.data(), spos.data(), first_bad.data(), clo.data(), chi.data(),
+               (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15)};
+    for (int b = 0; b < grid; b++)
+        for (int w = 0; w < nwarps; w++) emu::run_warp(para_body, &a, (unsigned)b, (unsigned)grid, (unsigned)w, (unsigned)nwarps);
+    ParBArgs bb{cfg, B, first_bad.data(), clo.data(), chi.data(), out_slots, slot_bytes, nbits, status, fault};
+    for (int b = 0; b < grid; b++) emu::run_warp(parb_body, &bb, (unsigned)b, (unsigned)grid);
     return 0;
 }

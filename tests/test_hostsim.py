@@ -106,3 +106,49 @@ def test_bad_symbol_is_reported():
     codes[0, 1, 3] = 16
     out, nbits, status, fault = H.encode(codes, 16, 1)
     assert status[0] == 6 and fault[0] == 43
+
+
+# ---- parallel encoder (phase A / phase B device code; phase S restated on the host) ---------------
+
+def test_parallel_encoder_matches_reference_vectors():
+    ran = 0
+    for fixture in ("kat.npz", "coder_small.npz", "coder_full.npz"):
+        for name, rec in coder_cases(golden(fixture)).items():
+            n, codes = int(rec["n"]), rec["codes"]
+            if not _pow2(n) or codes.ndim != 3 or codes.size > 8192:
+                continue
+            out, nbits, status, fault = H.encode_par(codes[None], n, MODE[rec["mode"]], nwarps=1 + ran % 4)
+            if "enc_error" in rec:
+                assert status[0] == ERR_TO_STATUS[str(rec["enc_error"][0])], name
+                assert fault[0] == int(rec["enc_fault_index"]), name
+            else:
+                packed = rec["packed"].tobytes()
+                assert status[0] == 0 and nbits[0] == int(rec["nbits"]), name
+                assert out[0, : len(packed)].tobytes() == packed, name
+            ran += 1
+    assert ran > 200
+
+
+def test_parallel_encoder_batches_and_faults():
+    rng = np.random.default_rng(21)
+    for n, shape in ((16, (4, 16, 512)), (256, (3, 16, 512)), (1024, (2, 16, 512)), (64, (5, 3, 100))):
+        codes = np.clip(np.round(rng.normal(n / 2, max(1.0, n / 14), shape)), 0, n - 1).astype(np.int32)
+        out, nbits, status, fault = H.encode_par(codes, n, 1, grid=2, nwarps=4)
+        for b in range(shape[0]):
+            ref = O.encode_stream(codes[b:b + 1], n, "repaired")
+            assert status[b] == 0 and nbits[b] == ref["nbits"]
+            assert out[b, : len(ref["packed"])].tobytes() == ref["packed"]
+    # a bad symbol stops the stream exactly where the serial encoder stops
+    codes = rng.integers(0, 16, (2, 4, 64)).astype(np.int32)
+    codes[1, 2, 7] = 99
+    out, nbits, status, fault = H.encode_par(codes, 16, 1)
+    assert status.tolist() == [0, 6] and fault[1] == 2 * 64 + 7
+    # verbatim mode: the D3 fault precedes a later bad symbol, as in the serial order
+    codes = np.clip(np.round(rng.normal(128, 20, (1, 16, 512))), 0, 255).astype(np.int32)
+    codes[0, 15, 500] = 300
+    ref = O.encode_stream(np.where(codes > 255, 0, codes), 256, "verbatim")
+    out, nbits, status, fault = H.encode_par(codes, 256, 0)
+    assert ref["status"] == 1 and status[0] == 1 and fault[0] == ref["fault_index"]
+    # tiny output slot
+    out, nbits, status, fault = H.encode_par(rng.integers(0, 256, (1, 4, 64)).astype(np.int32), 256, 1, slot_bytes=64)
+    assert status[0] == 5
