@@ -9,6 +9,7 @@
 #include "../../include/latentcodec.h"
 #include "lc_coder.cuh"
 #include "lc_encoder_par.cuh"
+#include "lc_decoder_fast.cuh"
 
 #define LC_CUDA_RET()                                                     \
     do {                                                                  \
@@ -204,10 +205,20 @@ __global__ void __launch_bounds__(32) lc_encode_kernel(LcCoderCfg cfg, const int
 __global__ void __launch_bounds__(32) lc_decode_kernel(LcCoderCfg cfg, const unsigned char *__restrict__ bytes,
                                                        const long long *__restrict__ offsets, const int *__restrict__ nbits,
                                                        int B, int *out, const float *__restrict__ deq_table, float *deq_out,
-                                                       int *status, int *fault, char *scratch)
+                                                       int *status, int *fault, char *scratch, int only_flagged)
 {
     extern __shared__ __align__(16) char lc_smem[];
-    lc_decode_block(cfg, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, lc_smem);
+    lc_decode_block(cfg, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, lc_smem, only_flagged);
+}
+
+__global__ void __launch_bounds__(32) lc_fast_decode_kernel(LcCoderCfg cfg, const unsigned char *__restrict__ bytes,
+                                                            const long long *__restrict__ offsets,
+                                                            const int *__restrict__ nbits, int B, int *out,
+                                                            const float *__restrict__ deq_table, float *deq_out,
+                                                            int *status, int *fault, char *scratch)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lc_fast_decode_block(cfg, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, lc_smem);
 }
 
 // =================================================================================================
@@ -529,8 +540,22 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg.sm_bytes > 48 * 1024)
         cudaFuncSetAttribute(lc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+    if (cfg.mode == LC_MODE_REPAIRED && cfg.has_ctx) {
+        // fast kernel; streams it cannot finish (a context with more than 32 distinct symbols) are
+        // flagged and redone from scratch by the generic kernel
+        if (cfg.sm_bytes > 48 * 1024)
+            cudaFuncSetAttribute(lc_fast_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+        lc_fast_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
+                                                              deq_table, deq_out, status, fault_index, (char *)scratch);
+        LC_CUDA_RET();
+        lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
+                                                         deq_table, deq_out, status, fault_index, (char *)scratch,
+                                                         LC_NEEDS_GENERIC);
+        LC_CUDA_RET();
+        return 0;
+    }
     lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out, deq_table,
-                                                     deq_out, status, fault_index, (char *)scratch);
+                                                     deq_out, status, fault_index, (char *)scratch, 0);
     LC_CUDA_RET();
     return 0;
 }

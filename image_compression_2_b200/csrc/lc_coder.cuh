@@ -398,6 +398,19 @@ __device__ __forceinline__ void lc_bw_put(LcBitWriter &b, int val, long long cou
         if (b.ovf) return;
     }
 }
+// append the low nb bits of v (nb in 0..32), MSB first
+__device__ __forceinline__ void lc_bw_put_bits(LcBitWriter &b, uint32_t v, int nb, int lane)
+{
+    if (nb == 0 || b.ovf) return;
+    b.nbits += nb;
+    const int room = 32 - b.nacc;
+    if (nb < room) { b.acc = (b.acc << nb) | v; b.nacc += nb; return; }
+    const int rem = nb - room; // bits left for the next word (0..31)
+    b.acc = (room == 32 ? 0u : (b.acc << room)) | (rem == 0 ? v : (v >> rem));
+    b.nacc = 32;
+    lc_bw_flush_word(b, lane);
+    if (rem) { b.acc = v & ((1u << rem) - 1u); b.nacc = rem; }
+}
 __device__ __forceinline__ void lc_bw_finish(LcBitWriter &b, int lane)
 {
     if (b.nacc > 0) { b.acc <<= (32 - b.nacc); lc_bw_flush_word(b, lane); }
@@ -642,12 +655,14 @@ __device__ __forceinline__ void lc_encode_block(const LcCoderCfg &cfg, const int
 // readable up to the next multiple of 4 past each stream) and holds ceil(nbits[b]/8) bytes.
 __device__ __forceinline__ void lc_decode_block(const LcCoderCfg &cfg, const unsigned char *bytes, const long long *offsets,
                                                 const int *nbits, int B, int *out, const float *deq_table,
-                                                float *deq_out, int *status, int *fault, char *scratch, char *smem)
+                                                float *deq_out, int *status, int *fault, char *scratch, char *smem,
+                                                int only_flagged)
 {
     LcWarp W;
     lc_warp_init(W, cfg, smem, scratch + (size_t)blockIdx.x * cfg.scratch_stride);
     for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
         int fi = 0;
+        if (only_flagged && status[sidx] != only_flagged) continue; // redo pass for streams the fast decoder handed over
         const long long o0 = offsets[sidx];
         const long long nby = ((long long)nbits[sidx] + 7) >> 3;
         lc_decode_stream(W, bytes + o0, nby, out + (size_t)sidx * cfg.total, deq_table,

@@ -117,20 +117,42 @@ __device__ __forceinline__ long long lc_enc_phase_b_stream(LcWarp &W, const doub
         iv.chi = __shfl_sync(LC_FULL_MASK, my_hi, l);
         iv.exact = 1; iv.sym = 0;
         lc_interval_apply(iv, 0.0, low, high);
-        while ((high & LC_HALF) == (low & LC_HALF)) {
-            const long long bit = high >> 31;
-            if (bit < 0 || bit > 1 || (outstanding > 0 && (1 - bit) < 0)) { W.status = LC_ENC_BIT_OVERFLOW; break; }
-            lc_bw_put(bw, (int)bit, 1, W.lane);
-            if (outstanding > 0) lc_bw_put(bw, (int)(1 - bit), outstanding, W.lane);
-            outstanding = 0;
-            low = (low << 1) & (LC_FULL - 1);
-            high = ((high << 1) & (LC_FULL - 1)) | 1;
-        }
-        if (W.status != LC_OK) break;
-        while ((low & LC_QUARTER) != 0 && (high & LC_QUARTER) == 0) {
-            outstanding += 1;
-            low = (low << 1) & (LC_HALF - 1);
-            high = ((high << 1) & (LC_HALF - 1)) | fix | 1;
+        if (W.mode == LC_MODE_REPAIRED) {
+            // low and high stay below 2^32 in this mode, so the bit-at-a-time loops of
+            // _renormalize_encoder / _handle_underflow (:189-210) have closed forms
+            uint32_t lo = (uint32_t)low, hi = (uint32_t)high;
+            const int d = __clz((int)(lo ^ hi)); // leading bits lo and hi share: that many bits are emitted
+            if (d) {
+                const int b1 = (int)(hi >> 31);
+                lc_bw_put(bw, b1, 1, W.lane);
+                if (outstanding > 0) { lc_bw_put(bw, 1 - b1, outstanding, W.lane); outstanding = 0; }
+                if (d > 1) lc_bw_put_bits(bw, (hi << 1) >> (33 - d), d - 1, W.lane);
+                if (d == 32) { lo = 0u; hi = 0xffffffffu; }
+                else { lo <<= d; hi = (hi << d) | ((1u << d) - 1u); }
+            }
+            const int e = __clz((int)~((lo & ~hi) << 1)); // underflow steps: lo = 01.., hi = 10..
+            if (e) {
+                outstanding += e;
+                lo = (lo << e) & 0x7fffffffu;
+                hi = ((hi << e) & 0x7fffffffu) | 0x80000000u | ((1u << e) - 1u);
+            }
+            low = lo; high = hi;
+        } else {
+            while ((high & LC_HALF) == (low & LC_HALF)) {
+                const long long bit = high >> 31;
+                if (bit < 0 || bit > 1 || (outstanding > 0 && (1 - bit) < 0)) { W.status = LC_ENC_BIT_OVERFLOW; break; }
+                lc_bw_put(bw, (int)bit, 1, W.lane);
+                if (outstanding > 0) lc_bw_put(bw, (int)(1 - bit), outstanding, W.lane);
+                outstanding = 0;
+                low = (low << 1) & (LC_FULL - 1);
+                high = ((high << 1) & (LC_FULL - 1)) | 1;
+            }
+            if (W.status != LC_OK) break;
+            while ((low & LC_QUARTER) != 0 && (high & LC_QUARTER) == 0) {
+                outstanding += 1;
+                low = (low << 1) & (LC_HALF - 1);
+                high = ((high << 1) & (LC_HALF - 1)) | fix | 1;
+            }
         }
         if (bw.ovf) { W.status = LC_OUT_OVERFLOW; break; }
     }

@@ -11,7 +11,8 @@ SO = os.path.join(HERE, "_build", "libhostsim.so")
 SRCS = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "cuda_emul.h"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_coder.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_common.cuh"),
-        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_par.cuh")]
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_par.cuh"),
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_fast.cuh")]
 _lib = None
 
 
@@ -58,8 +59,9 @@ def encode(codes, n, mode=1, rate=0.05, slot_bytes=None, grid=None):
     return out, nbits, status, fault
 
 
-def decode(streams, n, shape, mode=1, rate=0.05, grid=None, codebook=None):
-    """streams: list of bytes objects, one per stream; shape: per-batch shape as for encode()."""
+def decode(streams, n, shape, mode=1, rate=0.05, grid=None, codebook=None, fast=False):
+    """streams: list of bytes objects, one per stream; shape: per-batch shape as for encode().
+    fast=True: the fast decoder kernel + generic redo pass (repaired mode, 3-D shapes only)."""
     B, imgs, R, C, has_ctx = _shape(shape)
     assert len(streams) == B
     total = imgs * R * C
@@ -83,6 +85,15 @@ def decode(streams, n, shape, mode=1, rate=0.05, grid=None, codebook=None):
         cbp, deqp = _p(cb, ctypes.c_float), _p(deq, ctypes.c_float)
     else:
         deq, cbp, deqp = None, None, None
+    if fast:
+        assert mode == 1 and has_ctx
+        redone = ctypes.c_int(0)
+        rc = lib().hostsim_decode_fast(_p(blob, ctypes.c_ubyte), _p(offs, ctypes.c_longlong), _p(nbits, ctypes.c_int), B,
+                                       imgs, R, C, int(n), ctypes.c_double(rate), _p(out, ctypes.c_int), cbp, deqp,
+                                       _p(status, ctypes.c_int), _p(fault, ctypes.c_int), grid, ctypes.byref(redone))
+        assert rc == 0, rc
+        decode.last_redone = redone.value
+        return out.reshape(shape), status, fault, deq
     rc = lib().hostsim_decode(_p(blob, ctypes.c_ubyte), _p(offs, ctypes.c_longlong), _p(nbits, ctypes.c_int), B, imgs, R, C, int(n),
                               ctypes.c_double(rate), int(mode), has_ctx, _p(out, ctypes.c_int), cbp, deqp,
                               _p(status, ctypes.c_int), _p(fault, ctypes.c_int), grid)

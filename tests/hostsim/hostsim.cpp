@@ -10,6 +10,7 @@
 
 #include "../../image_compression_2_b200/csrc/lc_coder.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_par.cuh"
+#include "../../image_compression_2_b200/csrc/lc_decoder_fast.cuh"
 #include <algorithm>
 #include <numeric>
 
@@ -96,13 +97,19 @@ static void enc_body(void *p)
 }
 struct DecArgs {
     LcCoderCfg cfg; const unsigned char *bytes; const long long *offsets; const int *nbits; int B; int *out; const float *deq_table;
-    float *deq_out; int *status, *fault; char *scratch; char *smem;
+    float *deq_out; int *status, *fault; char *scratch; char *smem; int only_flagged;
 };
 static void dec_body(void *p)
 {
     DecArgs *a = (DecArgs *)p;
     lc_decode_block(a->cfg, a->bytes, a->offsets, a->nbits, a->B, a->out, a->deq_table, a->deq_out, a->status, a->fault,
-                    a->scratch, a->smem);
+                    a->scratch, a->smem, a->only_flagged);
+}
+static void decfast_body(void *p)
+{
+    DecArgs *a = (DecArgs *)p;
+    lc_fast_decode_block(a->cfg, a->bytes, a->offsets, a->nbits, a->B, a->out, a->deq_table, a->deq_out, a->status,
+                         a->fault, a->scratch, a->smem);
 }
 
 static int make_cfg(LcCoderCfg &cfg, int imgs, int R, int C, int n, double rate, int mode, int has_ctx)
@@ -138,8 +145,30 @@ extern "C" int hostsim_decode(const unsigned char *bytes, const long long *offse
     std::vector<char> scratch((size_t)grid * a.cfg.scratch_stride + 256);
     std::vector<char> smem(a.cfg.sm_bytes + 64);
     a.bytes = bytes; a.offsets = offsets; a.nbits = nbits; a.B = B; a.out = out; a.deq_table = deq_table; a.deq_out = deq_out;
-    a.status = status; a.fault = fault; a.scratch = scratch.data();
+    a.status = status; a.fault = fault; a.scratch = scratch.data(); a.only_flagged = 0;
     a.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a, (unsigned)b, (unsigned)grid);
+    return 0;
+}
+
+// fast decoder (repaired mode, (left,up) contexts) followed by the generic redo pass, as the host does
+extern "C" int hostsim_decode_fast(const unsigned char *bytes, const long long *offsets, const int *nbits, int B,
+                                   int imgs, int R, int C, int n, double rate, int *out, const float *deq_table,
+                                   float *deq_out, int *status, int *fault, int grid, int *n_redone)
+{
+    DecArgs a;
+    int rc = make_cfg(a.cfg, imgs, R, C, n, rate, LC_MODE_REPAIRED, 1);
+    if (rc) return rc;
+    std::vector<char> scratch((size_t)grid * a.cfg.scratch_stride + 256);
+    std::vector<char> smem(a.cfg.sm_bytes + 64);
+    a.bytes = bytes; a.offsets = offsets; a.nbits = nbits; a.B = B; a.out = out; a.deq_table = deq_table; a.deq_out = deq_out;
+    a.status = status; a.fault = fault; a.scratch = scratch.data(); a.only_flagged = 0;
+    a.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    for (int b = 0; b < grid; b++) emu::run_warp(decfast_body, &a, (unsigned)b, (unsigned)grid);
+    int redo = 0;
+    for (int b = 0; b < B; b++) redo += status[b] == LC_NEEDS_GENERIC;
+    *n_redone = redo;
+    a.only_flagged = LC_NEEDS_GENERIC;
     for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a, (unsigned)b, (unsigned)grid);
     return 0;
 }

@@ -152,3 +152,42 @@ def test_parallel_encoder_batches_and_faults():
     # tiny output slot
     out, nbits, status, fault = H.encode_par(rng.integers(0, 256, (1, 4, 64)).astype(np.int32), 256, 1, slot_bytes=64)
     assert status[0] == 5
+
+
+# ---- fast decoder (lazy states, register-resident model, closed-form renormalisation) ----------------
+
+def test_fast_decoder_matches_reference_vectors():
+    ran = 0
+    for fixture in ("kat.npz", "coder_small.npz", "coder_full.npz"):
+        for name, rec in coder_cases(golden(fixture), mode="repaired").items():
+            n, codes = int(rec["n"]), rec["codes"]
+            if not _pow2(n) or codes.ndim != 3 or "enc_error" in rec:
+                continue
+            batch = codes[None]
+            dec, st, fi, _ = H.decode([rec["packed"].tobytes()], n, batch.shape, 1, fast=True)
+            ref = rec["decoded"].reshape(batch.shape)
+            if "dec_error" in rec:
+                k = int(rec["dec_fault_index"])
+                assert st[0] == ERR_TO_STATUS[str(rec["dec_error"][0])] and fi[0] == k, name
+                assert np.array_equal(dec.ravel()[:k], ref.ravel()[:k]) and not dec.ravel()[k:].any(), name
+            elif st[0] == 4:
+                assert ref.ravel()[fi[0]] == -1, name
+            else:
+                assert st[0] == 0 and np.array_equal(dec, ref), name
+            ran += 1
+    assert ran > 100
+
+
+def test_fast_decoder_hands_wide_contexts_to_generic_kernel():
+    """A context with more than 32 distinct symbols: the fast kernel flags the stream, the generic kernel redoes it."""
+    rng = np.random.default_rng(31)
+    n = 256
+    codes = np.zeros((2, 4, 400), np.int32)
+    codes[0, :, 0::2] = 7                              # (left=7, up=7|-1) contexts recur ...
+    codes[0, :, 1::2] = rng.integers(0, n, (4, 200))   # ... with many different symbols
+    codes[1] = np.clip(np.round(rng.normal(128, 9, (4, 400))), 0, n - 1)
+    streams = [O.encode_stream(codes[b:b + 1], n)["packed"] for b in range(2)]
+    cb = np.linspace(-1, 1, n).astype(np.float32)
+    dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast=True, grid=1, codebook=cb)
+    assert H.decode.last_redone == 1
+    assert not st.any() and np.array_equal(dec, codes) and np.array_equal(deq.reshape(codes.shape), cb[codes])
