@@ -163,6 +163,30 @@ __device__ __forceinline__ void lc_dense_fresh(LcWarp &W)
     W.dense_ready = 1;
 }
 
+// one accumulator chain of NumPy's pairwise sum: r = a[0]; r += a[8]; r += a[16]; ...  The trip count
+// is 16 for every n >= 128; compile-time unrolling lets the shared-memory loads issue up front so
+// only the dependent float64 adds remain on the critical path.
+template <int STEPS> __device__ __forceinline__ double lc_chain_fixed(const double *p)
+{
+    double v[STEPS];
+#pragma unroll
+    for (int t = 0; t < STEPS; t++) v[t] = p[8 * t];
+    double r = v[0];
+#pragma unroll
+    for (int t = 1; t < STEPS; t++) r = LC_DADD(r, v[t]);
+    return r;
+}
+__device__ __forceinline__ double lc_chain(const double *p, int steps)
+{
+    switch (steps) {
+    case 16: return lc_chain_fixed<16>(p);
+    case 8: return lc_chain_fixed<8>(p);
+    case 4: return lc_chain_fixed<4>(p);
+    case 2: return lc_chain_fixed<2>(p);
+    default: return p[0];
+    }
+}
+
 // ---- NumPy pairwise float64 sum of the dense image (call site cabac_compression.py:135)
 __device__ __forceinline__ double lc_pairwise_total(const LcWarp &W)
 {
@@ -174,13 +198,8 @@ __device__ __forceinline__ double lc_pairwise_total(const LcWarp &W)
     const int chains = W.pw_chains;
     const int c = W.lane & (chains - 1) & 31;
     const double *p = W.dense + (c >> 3) * W.pw_len + (c & 7);
-    double r = p[0], r2 = 0.0;
-    for (int t = 1; t < W.pw_steps; t++) r = LC_DADD(r, p[8 * t]);
-    if (chains == 64) {
-        const double *q = p + 4 * 128;
-        r2 = q[0];
-        for (int t = 1; t < W.pw_steps; t++) r2 = LC_DADD(r2, q[8 * t]);
-    }
+    double r = lc_chain(p, W.pw_steps), r2 = 0.0;
+    if (chains == 64) r2 = lc_chain(p + 4 * 128, W.pw_steps);
     // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) per block, then the binary tree over blocks
     for (int off = 1; off < chains && off < 32; off <<= 1) {
         r = LC_DADD(r, __shfl_xor_sync(LC_FULL_MASK, r, off));

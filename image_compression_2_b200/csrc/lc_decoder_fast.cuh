@@ -64,13 +64,8 @@ __device__ __forceinline__ double lcf_pairwise_total(const LcFast &F)
     const int chains = F.pw_chains;
     const int c = F.lane & (chains - 1) & 31;
     const double *p = F.dense + (c >> 3) * F.pw_len + (c & 7);
-    double r = p[0], r2 = 0.0;
-    for (int t = 1; t < F.pw_steps; t++) r = LC_DADD(r, p[8 * t]);
-    if (chains == 64) {
-        const double *q = p + 4 * 128;
-        r2 = q[0];
-        for (int t = 1; t < F.pw_steps; t++) r2 = LC_DADD(r2, q[8 * t]);
-    }
+    double r = lc_chain(p, F.pw_steps), r2 = 0.0;
+    if (chains == 64) r2 = lc_chain(p + 4 * 128, F.pw_steps);
     for (int off = 1; off < chains && off < 32; off <<= 1) {
         r = LC_DADD(r, __shfl_xor_sync(LC_FULL_MASK, r, off));
         if (chains == 64) r2 = LC_DADD(r2, __shfl_xor_sync(LC_FULL_MASK, r2, off));
@@ -199,6 +194,17 @@ __device__ __forceinline__ bool lcf_gap_search(const LcFast &F, double v, double
     if (!(v - lo > F.delta) || !(hi - v >= F.delta)) return false;
     out.sym = gfirst + m; out.clo = lo; out.chi = hi; out.exact = 0;
     return true;
+}
+
+// second visit: the model is (u, {s1: P1}) and every lane knows all of it -- no shuffles needed
+__device__ __forceinline__ bool lcf_search_first(const LcFast &F, int s1, double v, LcInterval &out)
+{
+    const double A0 = (double)s1 * F.u; // ~cum[s1]
+    const double B0 = A0 + F.P1;        // ~cum[s1+1]
+    if (A0 - v >= F.delta) return lcf_gap_search(F, v, 0.0, 0, s1, out);
+    if (v - B0 > F.delta) return lcf_gap_search(F, v, B0, s1 + 1, F.n - s1 - 1, out);
+    if (v - A0 > F.delta && B0 - v >= F.delta) { out.sym = s1; out.clo = A0; out.chi = B0; out.exact = 0; return true; }
+    return false;
 }
 
 // guarded approximate symbol search (see lc_search_fast); the whole list is in registers
@@ -351,11 +357,23 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
                 iv.sym = (t > (double)F.n) ? F.n : (int)(LC_D2LL(t) + ((double)LC_D2LL(t) < t ? 1 : 0)) - 1;
             }
             iv.clo = LC_DMUL((double)iv.sym, F.u0); iv.chi = LC_DMUL((double)(iv.sym + 1), F.u0);
-        } else if (!lcf_search(F, v, iv)) {
+        } else if (!(state == 1 ? lcf_search_first(F, LCF_S1(word), v, iv) : lcf_search(F, v, iv))) {
             lcf_exact_search(F, v, iv);
         }
         if (iv.sym >= F.n) { status = LC_DEC_SYMBOL_OOB; break; }
         if (iv.sym < 0) { status = LC_DEC_NEG_SYMBOL; break; }
+        const int s = iv.sym;
+        // ---- the symbol is known: request the table window of the NEXT position's context now, so
+        // its latency overlaps the interval update, renormalisation and write-back below
+        if (F.lane == 0) F.rows[(r & 1) * F.C + c] = (unsigned short)s;
+        int c2 = c + 1, r2 = r;
+        if (c2 == F.C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
+        int up2 = -1;
+        if (r2 > 0) up2 = (F.C == 1) ? s : (int)F.rows[((r2 - 1) & 1) * F.C + c2]; // C==1: the element just written
+        const uint32_t key2 = (uint32_t)((c2 > 0 ? s : -1) + 1) * (uint32_t)(F.n + 1) + (uint32_t)(up2 + 1);
+        const uint32_t start2 = ((key2 * 2654435761u) >> F.slot_shift) & ~15u;
+        unsigned long long w2 = __ldcg(&F.slots[(start2 + (uint32_t)F.lane) & mask]);
+
         long long low64 = lo, high64 = hi;
         if (!lc_interval_apply(iv, F.delta, low64, high64)) {
             LcInterval ex;
@@ -381,23 +399,13 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
                 code = ((code << e) ^ 0x80000000u) | bits;
             }
         }
-        const int s = iv.sym;
         // ---- output
         if (F.lane == (pos & 31)) my_out = s;
-        if (F.lane == 0) F.rows[(r & 1) * F.C + c] = (unsigned short)s;
         if ((pos & 31) == 31) {
             const int p = pos - 31 + F.lane;
             out[p] = my_out;
             if (deq_out) deq_out[p] = __ldg(deq_table + my_out);
         }
-        __syncwarp();
-        // ---- next position's context: request its table window now
-        int c2 = c + 1, r2 = r;
-        if (c2 == F.C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
-        const int up2 = r2 > 0 ? (int)F.rows[((r2 - 1) & 1) * F.C + c2] : -1;
-        const uint32_t key2 = (uint32_t)((c2 > 0 ? s : -1) + 1) * (uint32_t)(F.n + 1) + (uint32_t)(up2 + 1);
-        uint32_t start2 = ((key2 * 2654435761u) >> F.slot_shift) & ~15u;
-        unsigned long long w2 = __ldcg(&F.slots[(start2 + (uint32_t)F.lane) & mask]);
         // ---- write back this context
         unsigned long long new_word;
         if (state == 0) new_word = LCF_PACK_A(want, s);

@@ -167,6 +167,96 @@ __device__ __forceinline__ long long lc_enc_phase_b_stream(LcWarp &W, const doub
     return bw.nbits;
 }
 
+// Phase B, repaired mode: low/high stay below 2^32, so the state is two uint32, the
+// renormalisation/underflow loops are clz counts, and bits are appended many at a time to a 64-bit
+// accumulator.  Same arithmetic as lc_enc_phase_b_stream, ~4x fewer instructions on the serial chain.
+struct LcBits64 {
+    uint32_t *out;
+    uint32_t cap_words, wpos;
+    unsigned long long acc; // the low `nacc` bits are pending output, nacc < 32 between calls
+    int nacc, ovf;
+    long long nbits;
+};
+// append the low nb bits of v, nb in 1..32
+__device__ __forceinline__ void lc_b64_put(LcBits64 &b, uint32_t v, int nb, int lane)
+{
+    b.acc = (b.acc << nb) | v;
+    b.nacc += nb;
+    b.nbits += nb;
+    if (b.nacc >= 32) {
+        b.nacc -= 32;
+        const uint32_t word = (uint32_t)(b.acc >> b.nacc);
+        if (b.wpos < b.cap_words) { if (lane == 0) b.out[b.wpos] = __byte_perm(word, 0, 0x0123); }
+        else b.ovf = 1;
+        b.wpos++;
+    }
+}
+__device__ __forceinline__ void lc_b64_put_run(LcBits64 &b, int bit, long long count, int lane)
+{
+    while (count > 0) {
+        const int take = count > 32 ? 32 : (int)count;
+        lc_b64_put(b, bit ? (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) : 0u, take, lane);
+        count -= take;
+    }
+}
+
+__device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const double *__restrict__ clo,
+                                                             const double *__restrict__ chi, int limit, uint32_t *out,
+                                                             uint32_t cap_words, int *status, int *fault_index)
+{
+    LcBits64 bw;
+    bw.out = out; bw.cap_words = cap_words; bw.wpos = 0; bw.acc = 0ull; bw.nacc = 0; bw.ovf = 0; bw.nbits = 0;
+    uint32_t lo = 0u, hi = 0xffffffffu;
+    long long outstanding = 0;
+    int pos = 0;
+    double c_lo = 0.0, c_hi = 0.0;
+    if (limit > 0) { c_lo = __ldg(clo); c_hi = __ldg(chi); }
+    for (; pos < limit; pos++) {
+        // the next interval is independent of the coder state: request it before the dependent chain
+        const int pn = pos + 1 < limit ? pos + 1 : pos;
+        const double n_lo = __ldg(clo + pn), n_hi = __ldg(chi + pn);
+        // encode_symbol (:220-224): high = low + int(range*c_hi - 1), low = low + int(range*c_lo)
+        const double rd = LC_LL2D((long long)hi - (long long)lo + 1); // 0 when the interval has collapsed (hi = lo-1)
+        const long long ah = LC_D2LL(LC_DSUB(LC_DMUL(rd, c_hi), 1.0));
+        const long long al = LC_D2LL(LC_DMUL(rd, c_lo));
+        hi = lo + (uint32_t)ah;
+        lo = lo + (uint32_t)al;
+        const int d = __clz((int)(lo ^ hi));
+        if (d) {
+            if (outstanding == 0) lc_b64_put(bw, hi >> (32 - d), d, lane);
+            else {
+                const int b1 = (int)(hi >> 31);
+                lc_b64_put(bw, (uint32_t)b1, 1, lane);
+                lc_b64_put_run(bw, 1 - b1, outstanding, lane);
+                outstanding = 0;
+                if (d > 1) lc_b64_put(bw, (hi << 1) >> (33 - d), d - 1, lane);
+            }
+            if (d == 32) { lo = 0u; hi = 0xffffffffu; }
+            else { lo <<= d; hi = (hi << d) | ((1u << d) - 1u); }
+        }
+        const int e = __clz((int)~((lo & ~hi) << 1));
+        if (e) {
+            outstanding += e;
+            lo = (lo << e) & 0x7fffffffu;
+            hi = ((hi << e) & 0x7fffffffu) | 0x80000000u | ((1u << e) - 1u);
+        }
+        if (bw.ovf) break;
+        c_lo = n_lo; c_hi = n_hi;
+    }
+    *fault_index = pos;
+    if (bw.ovf) { *status = LC_OUT_OVERFLOW; return 0; }
+    // finish_encoding (:230-245)
+    outstanding += 1;
+    const int first = (lo & 0x40000000u) != 0 ? 1 : 0;
+    lc_b64_put(bw, (uint32_t)first, 1, lane);
+    lc_b64_put_run(bw, 1 - first, outstanding, lane);
+    const long long nbits = bw.nbits;
+    if (bw.nacc > 0) lc_b64_put(bw, 0u, 32 - bw.nacc, lane); // zero-pad the last word
+    if (bw.ovf) { *status = LC_OUT_OVERFLOW; return 0; }
+    *status = LC_OK;
+    return nbits;
+}
+
 // ---- block entry points --------------------------------------------------------------------------
 
 // Phase A: one block per stream, blockDim.x/32 warps share the stream's groups.  `smem` holds one
@@ -202,9 +292,16 @@ __device__ __forceinline__ void lc_enc_phase_b_block(const LcCoderCfg &cfg, int 
         const int fb = first_bad[sidx];
         const int limit = fb < cfg.total ? fb : cfg.total;
         int fi = 0;
-        long long nb = lc_enc_phase_b_stream(W, clo + o, chi + o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
-                                             slot_bytes / 4, &fi);
-        int st = W.status;
+        long long nb;
+        int st;
+        if (cfg.mode == LC_MODE_REPAIRED) {
+            nb = lc_enc_phase_b_repaired(W.lane, clo + o, chi + o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
+                                         slot_bytes / 4, &st, &fi);
+        } else {
+            nb = lc_enc_phase_b_stream(W, clo + o, chi + o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
+                                       slot_bytes / 4, &fi);
+            st = W.status;
+        }
         if (st == LC_OK && fb < cfg.total) { st = LC_BAD_SYMBOL; fi = fb; nb = 0; }
         if (W.lane == 0) { nbits[sidx] = (int)nb; status[sidx] = st; fault[sidx] = fi; }
         __syncwarp();
