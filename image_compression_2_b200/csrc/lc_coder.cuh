@@ -369,7 +369,7 @@ __device__ __forceinline__ bool lc_search_fast(const LcWarp &W, double v, LcInte
 __device__ __forceinline__ bool lc_interval_apply(const LcInterval &iv, double delta, long long &low, long long &high)
 {
     const long long range = high - low + 1;
-    const double rd = LC_LL2D(range);
+    const double rd = lc_ll2d_small(range); // |range| < 2^35 in both coder modes
     const double xh = LC_DSUB(LC_DMUL(rd, iv.chi), 1.0);
     const double xl = LC_DMUL(rd, iv.clo);
     const long long ah = LC_D2LL(xh), al = LC_D2LL(xl);

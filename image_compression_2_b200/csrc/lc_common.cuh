@@ -36,6 +36,40 @@ enum { LC_MODE_VERBATIM = 0, LC_MODE_REPAIRED = 1 };
 
 #define LC_FULL_MASK 0xffffffffu
 
+// Exact int64 -> float64 for |x| < 2^51 without I2F.F64.S64 (which measured ~150 cycles of latency on
+// B200): add x to the bit pattern of 2^52+2^51 and subtract that constant -- one integer add, one DADD.
+#ifdef LC_HOSTSIM
+static inline double lc_ll2d_small(long long x)
+{
+    long long b = 0x4338000000000000LL + x;
+    double d;
+    memcpy(&d, &b, 8);
+    return d - 6755399441055744.0;
+}
+// ~20-bit reciprocal seed refined by two Newton steps: relative error below 2^-49; NOT correctly
+// rounded, so only used where a guard band absorbs the error
+static inline double lc_rcp_fast(double x)
+{
+    double r = (double)(float)(1.0 / x);
+    r = std::fma(r, std::fma(-x, r, 1.0), r);
+    r = std::fma(r, std::fma(-x, r, 1.0), r);
+    return r;
+}
+#else
+static __device__ __forceinline__ double lc_ll2d_small(long long x)
+{
+    return __dadd_rn(__longlong_as_double(0x4338000000000000LL + x), -6755399441055744.0);
+}
+static __device__ __forceinline__ double lc_rcp_fast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+    return r;
+}
+#endif
+
 // Launch-time description of one coder launch.  All streams in a launch share it.
 struct LcCoderCfg {
     int n;       // alphabet size, power of two in [2,1024]

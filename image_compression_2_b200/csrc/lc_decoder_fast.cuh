@@ -35,7 +35,7 @@
 
 struct LcFast {
     int n, C, R, total, lane;
-    double rate, delta, u0, P1;
+    double rate, delta, delta_v, tmargin, u0, P1;
     uint32_t slot_cap, slot_shift, pool_bytes, pool_top;
     int pw_len, pw_steps, pw_chains;
     unsigned long long *slots;
@@ -185,13 +185,13 @@ __device__ __forceinline__ bool lcf_gap_search(const LcFast &F, double v, double
 {
     if (glen <= 0) return false;
     const double d = v - gbase;
-    if (!(d > F.delta)) return false;
-    const double t = d / F.u;
+    if (!(d > F.delta_v)) return false;
+    const double t = d * lc_rcp_fast(F.u); // any error only makes the margin tests below fail
     if (!(t < (double)glen)) return false;
     const int m = (int)t;
     const double lo = gbase + (double)m * F.u;
     const double hi = gbase + (double)(m + 1) * F.u;
-    if (!(v - lo > F.delta) || !(hi - v >= F.delta)) return false;
+    if (!(v - lo > F.delta_v) || !(hi - v >= F.delta_v)) return false;
     out.sym = gfirst + m; out.clo = lo; out.chi = hi; out.exact = 0;
     return true;
 }
@@ -201,9 +201,9 @@ __device__ __forceinline__ bool lcf_search_first(const LcFast &F, int s1, double
 {
     const double A0 = (double)s1 * F.u; // ~cum[s1]
     const double B0 = A0 + F.P1;        // ~cum[s1+1]
-    if (A0 - v >= F.delta) return lcf_gap_search(F, v, 0.0, 0, s1, out);
-    if (v - B0 > F.delta) return lcf_gap_search(F, v, B0, s1 + 1, F.n - s1 - 1, out);
-    if (v - A0 > F.delta && B0 - v >= F.delta) { out.sym = s1; out.clo = A0; out.chi = B0; out.exact = 0; return true; }
+    if (A0 - v >= F.delta_v) return lcf_gap_search(F, v, 0.0, 0, s1, out);
+    if (v - B0 > F.delta_v) return lcf_gap_search(F, v, B0, s1 + 1, F.n - s1 - 1, out);
+    if (v - A0 > F.delta_v && B0 - v >= F.delta_v) { out.sym = s1; out.clo = A0; out.chi = B0; out.exact = 0; return true; }
     return false;
 }
 
@@ -229,12 +229,12 @@ __device__ __forceinline__ bool lcf_search(const LcFast &F, double v, LcInterval
         const int sl = __shfl_sync(LC_FULL_MASK, sv, l);
         const double Bp = __shfl_sync(LC_FULL_MASK, Bv, lp);
         const int sp = __shfl_sync(LC_FULL_MASK, sv, lp);
-        if (v - Al > F.delta) {
-            if (!(Bl - v >= F.delta)) return false;
+        if (v - Al > F.delta_v) {
+            if (!(Bl - v >= F.delta_v)) return false;
             out.sym = sl; out.clo = Al; out.chi = Bl; out.exact = 0;
             return true;
         }
-        if (!(Al - v >= F.delta)) return false;
+        if (!(Al - v >= F.delta_v)) return false;
         const double gbase = l > 0 ? Bp : 0.0;
         const int gfirst = l > 0 ? sp + 1 : 0;
         return lcf_gap_search(F, v, gbase, gfirst, sl - gfirst, out);
@@ -346,20 +346,36 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         // ---- decode_symbol (:272-292)
         const long long range = (long long)hi - (long long)lo + 1;
         if (range == 0) { status = LC_DEC_ZERO_RANGE; break; }
-        double v = LC_DDIV(LC_DMUL(LC_LL2D((long long)code - (long long)lo + 1), 1.0), LC_LL2D(range));
-        v = LC_DSUB(v, 1e-10);
+        // scaled_value = (code-low+1)*1.0/range - 1e-10 (:285).  The IEEE quotient is only needed when
+        // a decision falls inside the guard band; the searches run on a fast quotient whose error
+        // (< 2^-46 absolute, v <= ~1) is part of F.delta_v.
+        const double num = lc_ll2d_small((long long)code - (long long)lo + 1);
+        const double rdv = lc_ll2d_small(range);
+        const double va = num * lc_rcp_fast(rdv) - 1e-10;
         LcInterval iv;
-        if (state == 0) {
+        bool decided;
+        if (state == 0) { // uniform context: first i with i/n >= v, i.e. ceil(v*n) - 1
             iv.exact = 1;
-            if (!(0.0 < v)) iv.sym = -1;
-            else {
-                const double t = LC_DMUL(v, (double)F.n);
-                iv.sym = (t > (double)F.n) ? F.n : (int)(LC_D2LL(t) + ((double)LC_D2LL(t) < t ? 1 : 0)) - 1;
-            }
-            iv.clo = LC_DMUL((double)iv.sym, F.u0); iv.chi = LC_DMUL((double)(iv.sym + 1), F.u0);
-        } else if (!(state == 1 ? lcf_search_first(F, LCF_S1(word), v, iv) : lcf_search(F, v, iv))) {
-            lcf_exact_search(F, v, iv);
+            const double t = va * (double)F.n;
+            const double tr = nearbyint(t);
+            decided = (t > F.tmargin) && (fabs(t - tr) > F.tmargin) && (t < (double)F.n);
+            if (decided) iv.sym = (int)ceil(t) - 1;
+        } else {
+            decided = state == 1 ? lcf_search_first(F, LCF_S1(word), va, iv) : lcf_search(F, va, iv);
         }
+        if (!decided) { // exact quotient, exact sums
+            double v = LC_DDIV(LC_DMUL(num, 1.0), rdv);
+            v = LC_DSUB(v, 1e-10);
+            if (state == 0) {
+                iv.exact = 1;
+                if (!(0.0 < v)) iv.sym = -1;
+                else {
+                    const double t = LC_DMUL(v, (double)F.n);
+                    iv.sym = (t > (double)F.n) ? F.n : (int)(LC_D2LL(t) + ((double)LC_D2LL(t) < t ? 1 : 0)) - 1;
+                }
+            } else lcf_exact_search(F, v, iv);
+        }
+        if (state == 0) { iv.clo = LC_DMUL((double)iv.sym, F.u0); iv.chi = LC_DMUL((double)(iv.sym + 1), F.u0); }
         if (iv.sym >= F.n) { status = LC_DEC_SYMBOL_OOB; break; }
         if (iv.sym < 0) { status = LC_DEC_NEG_SYMBOL; break; }
         const int s = iv.sym;
@@ -376,10 +392,14 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
 
         long long low64 = lo, high64 = hi;
         if (!lc_interval_apply(iv, F.delta, low64, high64)) {
-            LcInterval ex;
-            lcf_exact_at(F, iv.sym, ex);
-            if (!(ex.clo < v) || !(v <= ex.chi)) lcf_exact_search(F, v, ex); // cannot happen; keeps exactness unconditional
-            iv = ex;
+            // the symbol itself was decided with margin; only the exact bounds are missing
+            lcf_exact_at(F, iv.sym, iv);
+#ifdef LC_HOSTSIM
+            { // emulator-only check of the margin argument: the exact sums must bracket the exact v
+                const double vx = LC_DSUB(LC_DDIV(LC_DMUL(num, 1.0), rdv), 1e-10);
+                if (!(iv.clo < vx) || !(vx <= iv.chi)) { fprintf(stderr, "lc_decoder_fast: guard argument violated\n"); abort(); }
+            }
+#endif
             lc_interval_apply(iv, F.delta, low64, high64);
         }
         lo = (uint32_t)low64; hi = (uint32_t)high64;
@@ -456,6 +476,8 @@ __device__ __forceinline__ void lc_fast_decode_block(const LcCoderCfg &cfg, cons
     LcFast F;
     F.n = cfg.n; F.C = cfg.C; F.R = cfg.R; F.total = cfg.total; F.lane = (int)(threadIdx.x & 31);
     F.rate = cfg.rate; F.delta = cfg.delta; F.u0 = LC_DDIV(1.0, (double)cfg.n);
+    F.delta_v = cfg.delta + 1.5e-14;            // + error of the fast quotient (< 2^-46)
+    F.tmargin = (double)cfg.n * 1.5e-14;        // the same error scaled by n, for the uniform closed form
     F.slot_cap = cfg.slot_cap; F.slot_shift = cfg.slot_shift; F.pool_bytes = cfg.pool_bytes; F.pool_top = 0;
     F.pw_len = cfg.pw_len; F.pw_steps = cfg.pw_steps; F.pw_chains = cfg.pw_chains;
     char *sc = scratch + (size_t)blockIdx.x * cfg.scratch_stride;

@@ -216,7 +216,7 @@ __device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const dou
         const int pn = pos + 1 < limit ? pos + 1 : pos;
         const double n_lo = __ldg(clo + pn), n_hi = __ldg(chi + pn);
         // encode_symbol (:220-224): high = low + int(range*c_hi - 1), low = low + int(range*c_lo)
-        const double rd = LC_LL2D((long long)hi - (long long)lo + 1); // 0 when the interval has collapsed (hi = lo-1)
+        const double rd = lc_ll2d_small((long long)hi - (long long)lo + 1); // 0 when the interval has collapsed (hi = lo-1)
         const long long ah = LC_D2LL(LC_DSUB(LC_DMUL(rd, c_hi), 1.0));
         const long long al = LC_D2LL(LC_DMUL(rd, c_lo));
         hi = lo + (uint32_t)ah;
