@@ -169,3 +169,60 @@ def test_bad_symbol_raises_index_error():
     codes[0, 1, 3] = 16
     with pytest.raises(IndexError):
         coder.cabac_encode(codes, coder.ContextModel(16))
+
+
+# ---- BASELINE.json configurations at full size: size-independent properties + sampled oracle parity ----
+
+def _roundtrip_full(n, kind, B, seed, quantizer="codebook", sample=12):
+    from image_compression_2_b200 import LatentPipeline
+    lat = synth_latents(kind, B, seed)
+    pipe = LatentPipeline(n_symbols=n, quantizer=quantizer)
+    out = pipe.roundtrip_device(lat.cuda())
+    idx = out["idx"]
+    assert int(out["enc"].status.abs().sum()) == 0
+    streams, nbits, _, _ = out["enc"].to_host()
+    idx_h = idx.cpu().numpy()
+    dec_h = out["dec_idx"].cpu().numpy()
+    dst = out["dec_status"].cpu().numpy()
+    dfi = out["dec_fault"].cpu().numpy()
+    for b in np.random.default_rng(seed).choice(B, sample, replace=False):
+        ref = O.encode_stream(idx_h[b:b + 1], n, "repaired")
+        assert nbits[b] == ref["nbits"] and streams[b] == ref["packed"], "stream %d" % b
+        rd = O.decode_stream(ref["packed"], n, (1, 16, 512), "repaired")
+        assert dst[b] == rd["status"] and dfi[b] == rd["fault_index"]
+        assert np.array_equal(dec_h[b], rd["symbols"][0])
+    return out, pipe, nbits
+
+
+@pytest.mark.parametrize("bits,kind", [(4, "wide"), (8, "enc_like"), (10, "enc_like")])
+def test_cfg3_bits_sweep_4096_streams(bits, kind):
+    """Config 3: 4096 latents at 4/8/10 bits; the oracle round-trips these, so decode(encode(x)) == x everywhere."""
+    n = 1 << bits
+    out, pipe, nbits = _roundtrip_full(n, kind, 4096, 1000 + 3 * 100000 + bits)
+    assert int(out["dec_status"].abs().sum()) == 0
+    assert torch.equal(out["dec_idx"], out["idx"])
+    assert torch.equal(out["deq"], pipe.deq_table[out["idx"].long()])
+    bps = nbits.astype(np.float64).mean() / 8192
+    assert {4: 3.7 < bps < 4.3, 8: 7.9 < bps < 8.1, 10: 9.9 < bps < 10.1}[bits]  # SURVEY.md section 6
+
+
+def test_cfg3_4bit_enc_like_decoder_parity_up_to_fault():
+    """4-bit enc_like latents: the reference decoder itself mis-decodes these (hazard H1); the GPU decoder
+    must reproduce the oracle's symbols, fault class and fault index on every sampled stream."""
+    out, pipe, _ = _roundtrip_full(16, "enc_like", 1024, 777, sample=48)
+    mism = int((out["dec_idx"] != out["idx"]).any(dim=(1, 2)).sum())
+    assert mism > 0  # the hazard is real: some streams do not round-trip, exactly as in the reference
+
+
+def test_cfg5_hier_codes_roundtrip():
+    """Config 5: hierarchical multi-scale latents, quantiser B codes (GumbelSoftmaxCompressor.compress output)."""
+    out, pipe, _ = _roundtrip_full(256, "hier", 16384 // 8, 1000 + 5 * 100000)  # one GPU's share of 16,384 on 8
+    assert int(out["dec_status"].abs().sum()) == 0 and torch.equal(out["dec_idx"], out["idx"])
+
+
+def test_cfg4_large_batch_roundtrip():
+    """Config 4 on one GPU: 8192 streams (one GPU's share of 65,536 on 8), affine quantiser indices."""
+    out, pipe, _ = _roundtrip_full(256, "enc_like", 8192, 1000 + 4 * 100000, quantizer="affine", sample=8)
+    assert int(out["dec_status"].abs().sum()) == 0 and torch.equal(out["dec_idx"], out["idx"])
+    want = O.quantize_affine(synth_latents("enc_like", 8192, 1000 + 4 * 100000)[:8].numpy(), 8)[1]
+    assert np.array_equal(out["deq"][:8].cpu().numpy().view(np.uint32), want.view(np.uint32))
