@@ -142,12 +142,17 @@ def cpu_sample(args, n):
     threads = host_threads()
     S = args.cpu_sample_streams
     if S <= 0:
-        # one stream costs ~26 ms (n=256) / ~120 ms (n=1024) / ~3 ms (n=16) of one core
-        per = {16: 0.003, 256: 0.03, 1024: 0.13}.get(n, 0.03)
-        S = int(min(args.batch, max(2 * threads, 15.0 * threads / per)))
+        S = int(min(args.batch, 1024))
     lat = synth(args.kind, S, 1000 + 2 * 100000).numpy()
     cb = torch.linspace(-1, 1, n).float().numpy()
     return orc.quantize_codebook(lat, cb), threads
+
+
+def cpu_repeats(S, n, threads, target_s=12.0):
+    """How many passes over the S sample streams give about target_s seconds of wall clock."""
+    per = {16: 0.003, 256: 0.03, 1024: 0.13}.get(n, 0.03)  # core-seconds per stream (enc+dec), measured
+    one_pass = S * per / max(threads, 1)
+    return int(max(1, min(64, round(target_s / max(one_pass, 1e-3)))))
 
 
 def run_reference(args):
@@ -161,13 +166,14 @@ def run_reference(args):
     for _ in range(min(args.warmup, 1)):
         cpu_roundtrip_rate(codes[: max(2, threads)], n, threads)
     t_total, streams = 0.0, 0
+    reps = cpu_repeats(codes.shape[0], n, threads, target_s=max(2.0, 20.0 / max(args.steps, 1)))
     for _ in range(args.steps):
-        _, dt, s = cpu_roundtrip_rate(codes, n, threads)
+        _, dt, s = cpu_roundtrip_rate(codes, n, threads, repeats=reps)
         t_total += dt
         streams += s
     value = streams * SYMS / t_total
-    sample = "%d streams/step x %d steps of the bench workload (seeded %s latents), C port of the reference coder, %s" % (
-        codes.shape[0], args.steps, args.kind, cpu_model())
+    sample = "%d streams x %d passes per step x %d steps of the bench workload (seeded %s latents), C port of the reference coder, one process per core, %s" % (
+        codes.shape[0], reps, args.steps, args.kind, cpu_model())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
@@ -351,6 +357,12 @@ def run_b200(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         dec_ms = sum(t_dec) / len(t_dec)
+        facts = {}
+        try:
+            facts = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_facts.json"))).get("lc_fast_decode_kernel", {})
+        except Exception:
+            pass
+        same_cfg = facts.get("streams") == B and facts.get("n_symbols") == n
         bytes_per_launch = B * SYMS * (coded_bits / SYMS / 8.0 + 8.0)
         achieved = bytes_per_launch / (dec_ms * 1e-3) / 1e9
         line = {
@@ -363,17 +375,25 @@ def run_b200(args):
                        "parity": parity_note, "streams_per_s": value / SYMS},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(res["h2d_bytes"]),
                     "d2h_bytes_per_step": int(res["d2h_bytes"]), "ms_per_step": 1e3 * float(e_total) / args.steps},
-            "gpu_launches": 5 * args.steps,
-            "roofline": {"kernel": "lc_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+            "gpu_launches": 8 * args.steps,
+            "roofline": {"kernel": "lc_fast_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": facts.get("dram_bytes_per_launch") if same_cfg else None,
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
                          "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms_total / args.steps),
-                         "note": "latency/issue-bound serial coder, not HBM-bound; see DESIGN.md section 5"},
+                         "warp_inst_per_symbol": facts.get("warp_inst_per_symbol") if same_cfg else None,
+                         "issue_slot_utilisation": facts.get("issue_slot_utilisation") if same_cfg else None,
+                         "ncu": "profiles/r01_ncu_all_kernels_v5.md",
+                         "note": "decode = dependent chain per stream: latency/issue-bound, not HBM-bound "
+                                 "(DESIGN.md section 5); traffic above the algorithmic bytes is the per-stream "
+                                 "context table + record pool"},
             "clocks": clocks,
             "rank_bytes": [int(x) for x in sizes.tolist()],
         }
         if not args.no_cpu_baseline:
             codes, threads = cpu_sample(args, n)
-            cv, cdt, cs = cpu_roundtrip_rate(codes, n, threads)
+            cv, cdt, cs = cpu_roundtrip_rate(codes, n, threads, repeats=cpu_repeats(codes.shape[0], n, threads))
             line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d streams of the same workload in %.1f s, C port of the reference coder "
                                               "(oracle/latent_oracle.c), %s" % (cs, cdt, cpu_model())}
