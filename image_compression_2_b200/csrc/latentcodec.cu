@@ -3,6 +3,7 @@
 // --fmad=false -lineinfo).  No tensor cores: nothing on this path is a dense contraction.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <cub/block/block_radix_sort.cuh>
 
@@ -273,18 +274,26 @@ __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const 
 __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
                                                              const uint32_t *__restrict__ skeys,
                                                              const unsigned short *__restrict__ spos,
-                                                             const int *__restrict__ first_bad, double *clo, double *chi)
+                                                             const int *__restrict__ first_bad, double *ivs)
 {
     extern __shared__ __align__(16) char lc_smem[];
-    lc_enc_phase_a_block(cfg, codes, B, skeys, spos, first_bad, clo, chi, lc_smem);
+    lc_enc_phase_a_block(cfg, codes, B, skeys, spos, first_bad, ivs, lc_smem);
+}
+
+__global__ void __launch_bounds__(32) lc_enc_phase_a_lanes_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
+                                                                  const uint32_t *__restrict__ skeys,
+                                                                  const unsigned short *__restrict__ spos,
+                                                                  const int *__restrict__ first_bad, double *ivs)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lc_enc_phase_a_lanes_block(cfg, codes, B, skeys, spos, first_bad, ivs, lc_smem);
 }
 
 __global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
-                                                            const double *__restrict__ clo, const double *__restrict__ chi,
-                                                            unsigned char *slots, uint32_t slot_bytes, int *nbits,
-                                                            int *status, int *fault)
+                                                            const double *__restrict__ ivs, unsigned char *slots,
+                                                            uint32_t slot_bytes, int *nbits, int *status, int *fault)
 {
-    lc_enc_phase_b_block(cfg, B, first_bad, clo, chi, slots, slot_bytes, nbits, status, fault);
+    lc_enc_phase_b_block(cfg, B, first_bad, ivs, slots, slot_bytes, nbits, status, fault);
 }
 
 // =================================================================================================
@@ -484,25 +493,37 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
         const size_t sort_smem = sizeof(LcBlockSort::TempStorage);
         const size_t a_smem = (size_t)8 * cfg.n * 8;
         static bool attr_done = false;
+        static int phase_a_choice = 0; // 0 auto, 1 warp-per-group, 2 lane-per-group (LC_PHASE_A=warp|lanes)
         if (!attr_done) {
             cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
             cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
+            cudaFuncSetAttribute(lc_enc_phase_a_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 256 * 32 * 8 + 256 + LC_PAR_MAX_SYMBOLS);
+            const char *e = getenv("LC_PHASE_A");
+            if (e && e[0] == 'w') phase_a_choice = 1;
+            if (e && e[0] == 'l') phase_a_choice = 2;
             attr_done = true;
         }
+        // lane-per-group needs a [n][32] float64 tile per warp: n <= 256
+        const bool lanes_variant = cfg.n <= 256 && phase_a_choice != 1;
         for (int b0 = 0; b0 < B; b0 += LC_PAR_TILE) {
             const int nb = (B - b0) < LC_PAR_TILE ? (B - b0) : LC_PAR_TILE;
             char *ws = (char *)scratch;
             uint32_t *skeys = (uint32_t *)ws;                 ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 4;
-            double *clo = (double *)ws;                       ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 8;
-            double *chi = (double *)ws;                       ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 8;
+            double *ivs = (double *)ws;                       ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 16;
             unsigned short *spos = (unsigned short *)ws;      ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 2;
             int *first_bad = (int *)ws;
             const int *codes = idx + (size_t)b0 * cfg.total;
             lc_enc_sort_kernel<<<nb, 256, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad);
             LC_CUDA_RET();
-            lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, clo, chi);
+            if (lanes_variant) {
+                const size_t la_smem = (size_t)cfg.n * 32 * 8 + 256 + LC_PAR_MAX_SYMBOLS;
+                lc_enc_phase_a_lanes_kernel<<<nb, 32, la_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
+            } else {
+                lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
+            }
             LC_CUDA_RET();
-            lc_enc_phase_b_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, clo, chi, slots + (size_t)b0 * slot_bytes,
+            lc_enc_phase_b_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, ivs, slots + (size_t)b0 * slot_bytes,
                                                     (uint32_t)slot_bytes, out_nbits + b0, status + b0, fault_index + b0);
             LC_CUDA_RET();
         }

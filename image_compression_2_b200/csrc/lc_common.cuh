@@ -70,6 +70,13 @@ static __device__ __forceinline__ double lc_rcp_fast(double x)
 }
 #endif
 
+// pull the 128-byte line holding p into L1 ahead of a later load (no-op in the CPU emulator)
+#ifdef LC_HOSTSIM
+static inline void lc_prefetch_l1(const void *) {}
+#else
+static __device__ __forceinline__ void lc_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
+
 // Launch-time description of one coder launch.  All streams in a launch share it.
 struct LcCoderCfg {
     int n;       // alphabet size, power of two in [2,1024]

@@ -52,10 +52,10 @@ __device__ __forceinline__ void lc_dense_update(LcWarp &W, int s)
 }
 
 // Phase A for one warp.  skeys/spos: this stream's positions sorted by (key, position); entries at
-// index >= total are padding.  clo/chi: float64 [total], indexed by position.
+// index >= total are padding.  iv: float64 [2*total], iv[2p] = cum[s_p], iv[2p+1] = cum[s_p+1].
 __device__ __forceinline__ void lc_enc_phase_a_warp(LcWarp &W, const int *__restrict__ codes,
                                                     const uint32_t *__restrict__ skeys,
-                                                    const unsigned short *__restrict__ spos, double *clo, double *chi,
+                                                    const unsigned short *__restrict__ spos, double *iv,
                                                     int total, int warp_id, int n_warps)
 {
     for (int chunk = warp_id; chunk * 32 < total; chunk += n_warps) {
@@ -66,8 +66,8 @@ __device__ __forceinline__ void lc_enc_phase_a_warp(LcWarp &W, const int *__rest
         if (head) { // first visit of a context: uniform model, cum[i] = i/n exactly
             const int p = spos[j];
             const int s = codes[p];
-            clo[p] = LC_DMUL((double)s, W.u0);
-            chi[p] = LC_DMUL((double)(s + 1), W.u0);
+            iv[2 * p] = LC_DMUL((double)s, W.u0);
+            iv[2 * p + 1] = LC_DMUL((double)(s + 1), W.u0);
         }
         const bool multi = head && (j + 1 < total) && (skeys[j + 1] == kj);
         unsigned m = __ballot_sync(LC_FULL_MASK, multi);
@@ -84,7 +84,7 @@ __device__ __forceinline__ void lc_enc_phase_a_warp(LcWarp &W, const int *__rest
                 const bool last = (t + 1 >= total) || (skeys[t + 1] != key);
                 if (t != chunk * 32 + l) {
                     const double T = lc_dense_prefix(W.dense, s);
-                    if (W.lane == 0) { clo[p] = T; chi[p] = LC_DADD(T, W.dense[s]); }
+                    if (W.lane == 0) { iv[2 * p] = T; iv[2 * p + 1] = LC_DADD(T, W.dense[s]); }
                 }
                 if (last) break;
                 lc_dense_update(W, s);
@@ -96,9 +96,8 @@ __device__ __forceinline__ void lc_enc_phase_a_warp(LcWarp &W, const int *__rest
 }
 
 // Phase B for one stream (one warp): the range coder over precomputed exact intervals.
-__device__ __forceinline__ long long lc_enc_phase_b_stream(LcWarp &W, const double *__restrict__ clo,
-                                                           const double *__restrict__ chi, int limit, uint32_t *out,
-                                                           uint32_t cap_words, int *fault_index)
+__device__ __forceinline__ long long lc_enc_phase_b_stream(LcWarp &W, const double *__restrict__ ivs, int limit,
+                                                           uint32_t *out, uint32_t cap_words, int *fault_index)
 {
     LcBitWriter bw; lc_bw_init(bw, out, cap_words);
     long long low = 0, high = LC_FULL - 1, outstanding = 0;
@@ -110,7 +109,7 @@ __device__ __forceinline__ long long lc_enc_phase_b_stream(LcWarp &W, const doub
         const int l = pos & 31;
         if (l == 0) {
             const int p = pos + W.lane;
-            if (p < limit) { my_lo = clo[p]; my_hi = chi[p]; }
+            if (p < limit) { my_lo = ivs[2 * p]; my_hi = ivs[2 * p + 1]; }
         }
         LcInterval iv;
         iv.clo = __shfl_sync(LC_FULL_MASK, my_lo, l);
@@ -200,9 +199,9 @@ __device__ __forceinline__ void lc_b64_put_run(LcBits64 &b, int bit, long long c
     }
 }
 
-__device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const double *__restrict__ clo,
-                                                             const double *__restrict__ chi, int limit, uint32_t *out,
-                                                             uint32_t cap_words, int *status, int *fault_index)
+__device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const double *__restrict__ ivs, int limit,
+                                                             uint32_t *out, uint32_t cap_words, int *status,
+                                                             int *fault_index)
 {
     LcBits64 bw;
     bw.out = out; bw.cap_words = cap_words; bw.wpos = 0; bw.acc = 0ull; bw.nacc = 0; bw.ovf = 0; bw.nbits = 0;
@@ -210,11 +209,14 @@ __device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const dou
     long long outstanding = 0;
     int pos = 0;
     double c_lo = 0.0, c_hi = 0.0;
-    if (limit > 0) { c_lo = __ldg(clo); c_hi = __ldg(chi); }
+    if (limit > 0) { c_lo = __ldg(ivs); c_hi = __ldg(ivs + 1); }
+    // the intervals come from DRAM (phase A wrote them); they do not depend on the coder state, so
+    // their lines are pulled into L1 half a KiB ahead and the next pair is loaded one symbol early
+    for (int q = lane * 8; q < 64 && q < limit; q += 256) lc_prefetch_l1(ivs + 2 * q);
     for (; pos < limit; pos++) {
-        // the next interval is independent of the coder state: request it before the dependent chain
+        if ((pos & 7) == 0 && pos + 64 < limit) lc_prefetch_l1(ivs + 2 * (pos + 64));
         const int pn = pos + 1 < limit ? pos + 1 : pos;
-        const double n_lo = __ldg(clo + pn), n_hi = __ldg(chi + pn);
+        const double n_lo = __ldg(ivs + 2 * pn), n_hi = __ldg(ivs + 2 * pn + 1);
         // encode_symbol (:220-224): high = low + int(range*c_hi - 1), low = low + int(range*c_lo)
         const double rd = lc_ll2d_small((long long)hi - (long long)lo + 1); // 0 when the interval has collapsed (hi = lo-1)
         const long long ah = LC_D2LL(LC_DSUB(LC_DMUL(rd, c_hi), 1.0));
@@ -266,7 +268,7 @@ __device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const dou
 // the serial encoder stops.
 __device__ __forceinline__ void lc_enc_phase_a_block(const LcCoderCfg &cfg, const int *codes, int B,
                                                      const uint32_t *skeys, const unsigned short *spos,
-                                                     const int *first_bad, double *clo, double *chi, char *smem)
+                                                     const int *first_bad, double *ivs, char *smem)
 {
     const int warp_id = (int)(threadIdx.x >> 5), n_warps = (int)(blockDim.x >> 5);
     LcWarp W;
@@ -275,14 +277,14 @@ __device__ __forceinline__ void lc_enc_phase_a_block(const LcCoderCfg &cfg, cons
     for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
         const size_t o = (size_t)sidx * LC_PAR_MAX_SYMBOLS;
         const int fb = first_bad[sidx];
-        lc_enc_phase_a_warp(W, codes + (size_t)sidx * cfg.total, skeys + o, spos + o, clo + o, chi + o,
+        lc_enc_phase_a_warp(W, codes + (size_t)sidx * cfg.total, skeys + o, spos + o, ivs + 2 * o,
                             fb < cfg.total ? fb : cfg.total, warp_id, n_warps);
     }
 }
 
 // Phase B: one warp per stream (blockDim.x = 32).
 __device__ __forceinline__ void lc_enc_phase_b_block(const LcCoderCfg &cfg, int B, const int *first_bad,
-                                                     const double *clo, const double *chi, unsigned char *out_slots,
+                                                     const double *ivs, unsigned char *out_slots,
                                                      uint32_t slot_bytes, int *nbits, int *status, int *fault)
 {
     LcWarp W;
@@ -295,15 +297,158 @@ __device__ __forceinline__ void lc_enc_phase_b_block(const LcCoderCfg &cfg, int 
         long long nb;
         int st;
         if (cfg.mode == LC_MODE_REPAIRED) {
-            nb = lc_enc_phase_b_repaired(W.lane, clo + o, chi + o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
+            nb = lc_enc_phase_b_repaired(W.lane, ivs + 2 * o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
                                          slot_bytes / 4, &st, &fi);
         } else {
-            nb = lc_enc_phase_b_stream(W, clo + o, chi + o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
+            nb = lc_enc_phase_b_stream(W, ivs + 2 * o, limit, (uint32_t *)(out_slots + (size_t)sidx * slot_bytes),
                                        slot_bytes / 4, &fi);
             st = W.status;
         }
         if (st == LC_OK && fb < cfg.total) { st = LC_BAD_SYMBOL; fi = fb; nb = 0; }
         if (W.lane == 0) { nbits[sidx] = (int)nb; status[sidx] = st; fault[sidx] = fi; }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// Phase A, lane-per-group variant (n <= 256).
+//
+// In the warp-per-group kernel above all 32 lanes execute the same strictly sequential np.cumsum
+// walk, so 31/32 of the issued work is redundant.  Here every LANE owns one context group: its
+// dense model is a column of a [n][32] float64 tile in shared memory (element i of lane L at
+// tile[i*32+L]: conflict-free for 64-bit accesses), and the lane runs the reference's arithmetic
+// as plain scalar code -- NumPy's 8-accumulator pairwise sum, the sequential prefix, the scaling
+// loop.  Lanes advance one visit per step in lock step and pick up the next group of the stream
+// when theirs ends.  One warp (block) per stream; groups with a single visit never reach a lane.
+// =================================================================================================
+
+// NumPy pairwise sum of one lane's column (n >= 8: blocks of min(n,128), 8 accumulators, binary tree)
+__device__ __forceinline__ double lc_col_pairwise(const double *col, int n, int pw_len, int pw_steps)
+{
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; i++) r = LC_DADD(r, col[i * 32]);
+        return r;
+    }
+    double bs[8];
+    const int nblk = n / pw_len;
+    for (int b = 0; b < nblk; b++) {
+        const double *p = col + (size_t)b * pw_len * 32;
+        double r0 = p[0], r1 = p[32], r2 = p[64], r3 = p[96], r4 = p[128], r5 = p[160], r6 = p[192], r7 = p[224];
+        for (int t = 1; t < pw_steps; t++) {
+            const double *q = p + t * 256;
+            r0 = LC_DADD(r0, q[0]);   r1 = LC_DADD(r1, q[32]);  r2 = LC_DADD(r2, q[64]);  r3 = LC_DADD(r3, q[96]);
+            r4 = LC_DADD(r4, q[128]); r5 = LC_DADD(r5, q[160]); r6 = LC_DADD(r6, q[192]); r7 = LC_DADD(r7, q[224]);
+        }
+        bs[b] = LC_DADD(LC_DADD(LC_DADD(r0, r1), LC_DADD(r2, r3)), LC_DADD(LC_DADD(r4, r5), LC_DADD(r6, r7)));
+    }
+    // recursive halving over the blocks (n2 = n/2 is a multiple of 128 for n >= 256)
+    for (int w = 1; w < nblk; w <<= 1)
+        for (int b = 0; b + w < nblk; b += 2 * w) bs[b] = LC_DADD(bs[b], bs[b + w]);
+    return bs[0];
+}
+
+// ContextModel.update_model (:119-144) on one lane's column
+__device__ __forceinline__ void lc_col_update(double *col, int n, int pw_len, int pw_steps, double rate, int s)
+{
+    const double p_old = col[s * 32];
+    const double p_new = LC_DADD(p_old, LC_DMUL(rate, LC_DSUB(1.0, p_old)));
+    col[s * 32] = p_new;
+    const double total = lc_col_pairwise(col, n, pw_len, pw_steps);
+    const double others = LC_DSUB(total, p_new);
+    const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, p_new), others) : 0.0;
+    for (int i = 0; i < n; i++) col[i * 32] = LC_DMUL(col[i * 32], f);
+    col[s * 32] = p_new;
+}
+
+// smem: tile[n*32] doubles | u1tab[32] doubles | glist[LC_PAR_MAX_SYMBOLS/2] u16
+__device__ __forceinline__ void lc_enc_phase_a_lanes_block(const LcCoderCfg &cfg, const int *codes_all, int B,
+                                                           const uint32_t *skeys_all, const unsigned short *spos_all,
+                                                           const int *first_bad, double *ivs_all, char *smem)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    const int n = cfg.n, pw_len = cfg.pw_len, pw_steps = cfg.pw_steps;
+    const double rate = cfg.rate;
+    const double u0 = LC_DDIV(1.0, (double)n);
+    const double P1 = LC_DADD(u0, LC_DMUL(rate, LC_DSUB(1.0, u0)));
+    double *tile = (double *)smem;
+    double *col = tile + lane;
+    double *u1tab = tile + (size_t)n * 32;
+    unsigned short *glist = (unsigned short *)(u1tab + 32);
+    // u after the first update, by chain step of the symbol (by symbol when n < 8): each lane computes one entry
+    {
+        const int entries = cfg.pw_chains == 0 ? n : pw_steps;
+        if (lane < entries) {
+            const int s = cfg.pw_chains == 0 ? lane : 8 * lane;
+            for (int i = 0; i < n; i++) col[i * 32] = u0;
+            lc_col_update(col, n, pw_len, pw_steps, rate, s);
+            u1tab[lane] = col[(s == 0 ? 1 : 0) * 32]; // any other symbol: u0 * f
+        }
+        __syncwarp();
+    }
+    for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
+        const size_t o = (size_t)sidx * LC_PAR_MAX_SYMBOLS;
+        const int *codes = codes_all + (size_t)sidx * cfg.total;
+        const uint32_t *skeys = skeys_all + o;
+        const unsigned short *spos = spos_all + o;
+        double *ivs = ivs_all + 2 * o;
+        const int fb = first_bad[sidx];
+        const int total = fb < cfg.total ? fb : cfg.total;
+        // pass 1: first visits are closed form; list the groups that have a second visit
+        int ngroups = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int j = base + lane;
+            const bool valid = j < total;
+            const uint32_t kj = valid ? skeys[j] : 0u;
+            const bool head = valid && (j == 0 || skeys[j - 1] != kj);
+            if (head) {
+                const int p = spos[j];
+                const int s = codes[p];
+                ivs[2 * p] = LC_DMUL((double)s, u0);
+                ivs[2 * p + 1] = LC_DMUL((double)(s + 1), u0);
+            }
+            const bool multi = head && (j + 1 < total) && (skeys[j + 1] == kj);
+            const unsigned m = __ballot_sync(LC_FULL_MASK, multi);
+            if (multi) glist[ngroups + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+            ngroups += __popc(m);
+        }
+        __syncwarp();
+        // pass 2: every lane walks one group at a time, one visit per step
+        int next = 0;      // next unassigned entry of glist (warp-uniform)
+        int t = -1;        // sorted index of the visit this lane handles in the current step, -1 = idle
+        uint32_t key = 0u;
+        for (;;) {
+            // lanes without a group take the next ones from the list
+            const unsigned need = __ballot_sync(LC_FULL_MASK, t < 0);
+            if (need) {
+                const int g = next + __popc(need & ((1u << lane) - 1u));
+                if (t < 0 && g < ngroups) {
+                    const int j0 = glist[g];
+                    key = skeys[j0];
+                    const int s1 = codes[spos[j0]];
+                    // model after the first visit: P1 at s1, u1 elsewhere
+                    const double u1 = u1tab[cfg.pw_chains == 0 ? s1 : ((s1 & (pw_len - 1)) >> 3)];
+                    for (int i = 0; i < n; i++) col[i * 32] = u1;
+                    col[s1 * 32] = P1;
+                    t = j0 + 1; // its second visit
+                }
+                next += __popc(need);
+                if (next > ngroups) next = ngroups;
+            }
+            if (__ballot_sync(LC_FULL_MASK, t >= 0) == 0u) break;
+            if (t >= 0) {
+                const int p = spos[t];
+                const int s = codes[p];
+                // exact np.cumsum prefix (:346-347)
+                double T = 0.0;
+                for (int i = 0; i < s; i++) T = LC_DADD(T, col[i * 32]);
+                ivs[2 * p] = T;
+                ivs[2 * p + 1] = LC_DADD(T, col[s * 32]);
+                const bool last = (t + 1 >= total) || (skeys[t + 1] != key);
+                if (last) t = -1; // the update after the last visit is never read
+                else { lc_col_update(col, n, pw_len, pw_steps, rate, s); t++; }
+            }
+        }
         __syncwarp();
     }
 }

@@ -183,18 +183,23 @@ extern "C" void hostsim_stats(long long *out, int reset)
 // ---- parallel encoder: phase S restated on the host (the real kernel uses a CUB block sort and is
 // checked on the GPU), phases A and B run through the emulator
 struct ParAArgs { LcCoderCfg cfg; const int *codes; int B; const uint32_t *skeys; const unsigned short *spos;
-                  const int *first_bad; double *clo, *chi; char *smem; };
+                  const int *first_bad; double *ivs; char *smem; };
 static void para_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
-    lc_enc_phase_a_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->clo, a->chi, a->smem);
+    lc_enc_phase_a_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->ivs, a->smem);
 }
-struct ParBArgs { LcCoderCfg cfg; int B; const int *first_bad; const double *clo, *chi; unsigned char *out_slots;
+struct ParBArgs { LcCoderCfg cfg; int B; const int *first_bad; const double *ivs; unsigned char *out_slots;
                   uint32_t slot_bytes; int *nbits, *status, *fault; };
+static void para_lanes_body(void *p)
+{
+    ParAArgs *a = (ParAArgs *)p;
+    lc_enc_phase_a_lanes_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->ivs, a->smem);
+}
 static void parb_body(void *p)
 {
     ParBArgs *a = (ParBArgs *)p;
-    lc_enc_phase_b_block(a->cfg, a->B, a->first_bad, a->clo, a->chi, a->out_slots, a->slot_bytes, a->nbits, a->status,
+    lc_enc_phase_b_block(a->cfg, a->B, a->first_bad, a->ivs, a->out_slots, a->slot_bytes, a->nbits, a->status,
                          a->fault);
 }
 
@@ -229,13 +234,16 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
             spos[(size_t)b * LC_PAR_MAX_SYMBOLS + j] = (unsigned short)order[j];
         }
     }
-    std::vector<double> clo((size_t)B * LC_PAR_MAX_SYMBOLS, -1.0), chi((size_t)B * LC_PAR_MAX_SYMBOLS, -1.0);
-    std::vector<char> smem((size_t)nwarps * n * 8 + 64);
-    ParAArgs a{cfg, codes, B, skeys.data(), spos.data(), first_bad.data(), clo.data(), chi.data(),
+    std::vector<double> ivs((size_t)B * LC_PAR_MAX_SYMBOLS * 2, -1.0);
+    std::vector<char> smem(std::max((size_t)nwarps * n * 8, (size_t)n * 32 * 8 + 256 + LC_PAR_MAX_SYMBOLS) + 64);
+    ParAArgs a{cfg, codes, B, skeys.data(), spos.data(), first_bad.data(), ivs.data(),
                (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15)};
+    if (nwarps == 0) { // lane-per-group variant: one warp per block
+        for (int b = 0; b < grid; b++) emu::run_warp(para_lanes_body, &a, (unsigned)b, (unsigned)grid);
+    } else
     for (int b = 0; b < grid; b++)
         for (int w = 0; w < nwarps; w++) emu::run_warp(para_body, &a, (unsigned)b, (unsigned)grid, (unsigned)w, (unsigned)nwarps);
-    ParBArgs bb{cfg, B, first_bad.data(), clo.data(), chi.data(), out_slots, slot_bytes, nbits, status, fault};
+    ParBArgs bb{cfg, B, first_bad.data(), ivs.data(), out_slots, slot_bytes, nbits, status, fault};
     for (int b = 0; b < grid; b++) emu::run_warp(parb_body, &bb, (unsigned)b, (unsigned)grid);
     return 0;
 }

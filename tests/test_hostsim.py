@@ -191,3 +191,23 @@ def test_fast_decoder_hands_wide_contexts_to_generic_kernel():
     dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast=True, grid=1, codebook=cb)
     assert H.decode.last_redone == 1
     assert not st.any() and np.array_equal(dec, codes) and np.array_equal(deq.reshape(codes.shape), cb[codes])
+
+
+def test_lane_per_group_phase_a():
+    """nwarps=0 selects the lane-per-group phase A (n <= 256): same bitstreams as the oracle."""
+    rng = np.random.default_rng(41)
+    c = golden("config1.npz")
+    out, nbits, status, _ = H.encode_par(c["coder_repaired__codes"][None], 256, 1, nwarps=0)
+    packed = c["coder_repaired__packed"].tobytes()
+    assert status[0] == 0 and out[0, : len(packed)].tobytes() == packed
+    for n, shape in ((2, (2, 3, 40)), (4, (2, 4, 64)), (16, (3, 16, 512)), (64, (4, 5, 100)), (128, (2, 8, 200)), (256, (2, 16, 512))):
+        codes = np.clip(np.round(rng.normal(n / 2, max(0.8, n / 14), shape)), 0, n - 1).astype(np.int32)
+        codes[0, 0, :8] = n - 1
+        out, nbits, status, fault = H.encode_par(codes, n, 1, grid=2, nwarps=0)
+        for b in range(shape[0]):
+            ref = O.encode_stream(codes[b:b + 1], n, "repaired")
+            assert status[b] == 0 and nbits[b] == ref["nbits"] and out[b, : len(ref["packed"])].tobytes() == ref["packed"]
+    codes = rng.integers(0, 16, (2, 4, 64)).astype(np.int32)
+    codes[1, 2, 7] = 99
+    out, nbits, status, fault = H.encode_par(codes, 16, 1, nwarps=0)
+    assert status.tolist() == [0, 6] and fault[1] == 2 * 64 + 7
