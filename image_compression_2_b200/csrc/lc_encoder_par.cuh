@@ -208,15 +208,21 @@ __device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const dou
     uint32_t lo = 0u, hi = 0xffffffffu;
     long long outstanding = 0;
     int pos = 0;
-    double c_lo = 0.0, c_hi = 0.0;
-    if (limit > 0) { c_lo = __ldg(ivs); c_hi = __ldg(ivs + 1); }
-    // the intervals come from DRAM (phase A wrote them); they do not depend on the coder state, so
-    // their lines are pulled into L1 half a KiB ahead and the next pair is loaded one symbol early
-    for (int q = lane * 8; q < 64 && q < limit; q += 256) lc_prefetch_l1(ivs + 2 * q);
+    // The intervals come from DRAM (phase A wrote them) and do not depend on the coder state: each lane
+    // holds one symbol's pair of the current and of the next 32-symbol chunk (coalesced 16-byte loads
+    // issued a whole chunk ahead), and the pair of symbol pos+1 is broadcast while symbol pos is coded.
+    double cur_lo = 0.0, cur_hi = 0.0, nx_lo = 0.0, nx_hi = 0.0;
+    if (lane < limit) { cur_lo = __ldg(ivs + 2 * lane); cur_hi = __ldg(ivs + 2 * lane + 1); }
+    if (32 + lane < limit) { nx_lo = __ldg(ivs + 2 * (32 + lane)); nx_hi = __ldg(ivs + 2 * (32 + lane) + 1); }
+    double c_lo = __shfl_sync(LC_FULL_MASK, cur_lo, 0), c_hi = __shfl_sync(LC_FULL_MASK, cur_hi, 0);
     for (; pos < limit; pos++) {
-        if ((pos & 7) == 0 && pos + 64 < limit) lc_prefetch_l1(ivs + 2 * (pos + 64));
-        const int pn = pos + 1 < limit ? pos + 1 : pos;
-        const double n_lo = __ldg(ivs + 2 * pn), n_hi = __ldg(ivs + 2 * pn + 1);
+        const int pn = pos + 1;
+        if ((pn & 31) == 0) { // entering the next chunk: rotate and request the one after it
+            cur_lo = nx_lo; cur_hi = nx_hi;
+            const int q = pn + 32 + lane;
+            if (q < limit) { nx_lo = __ldg(ivs + 2 * q); nx_hi = __ldg(ivs + 2 * q + 1); }
+        }
+        const double n_lo = __shfl_sync(LC_FULL_MASK, cur_lo, pn & 31), n_hi = __shfl_sync(LC_FULL_MASK, cur_hi, pn & 31);
         // encode_symbol (:220-224): high = low + int(range*c_hi - 1), low = low + int(range*c_lo)
         const double rd = lc_ll2d_small((long long)hi - (long long)lo + 1); // 0 when the interval has collapsed (hi = lo-1)
         const long long ah = LC_D2LL(LC_DSUB(LC_DMUL(rd, c_hi), 1.0));
@@ -357,8 +363,32 @@ __device__ __forceinline__ void lc_col_update(double *col, int n, int pw_len, in
     const double total = lc_col_pairwise(col, n, pw_len, pw_steps);
     const double others = LC_DSUB(total, p_new);
     const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, p_new), others) : 0.0;
-    for (int i = 0; i < n; i++) col[i * 32] = LC_DMUL(col[i * 32], f);
+    // in-place scaling, eight elements at a time: loads first, then the multiplies, then the stores
+    // (the compiler cannot reorder shared-memory loads across the stores of a rolled loop)
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double *q = col + i * 32;
+        const double a0 = q[0], a1 = q[32], a2 = q[64], a3 = q[96], a4 = q[128], a5 = q[160], a6 = q[192], a7 = q[224];
+        q[0] = LC_DMUL(a0, f);   q[32] = LC_DMUL(a1, f);  q[64] = LC_DMUL(a2, f);  q[96] = LC_DMUL(a3, f);
+        q[128] = LC_DMUL(a4, f); q[160] = LC_DMUL(a5, f); q[192] = LC_DMUL(a6, f); q[224] = LC_DMUL(a7, f);
+    }
+    for (; i < n; i++) col[i * 32] = LC_DMUL(col[i * 32], f);
     col[s * 32] = p_new;
+}
+
+// exact np.cumsum prefix of one lane's column: loads in batches of eight ahead of the dependent adds
+__device__ __forceinline__ double lc_col_prefix(const double *col, int s)
+{
+    double T = 0.0;
+    int i = 0;
+    for (; i + 8 <= s; i += 8) {
+        const double *q = col + i * 32;
+        const double a0 = q[0], a1 = q[32], a2 = q[64], a3 = q[96], a4 = q[128], a5 = q[160], a6 = q[192], a7 = q[224];
+        T = LC_DADD(T, a0); T = LC_DADD(T, a1); T = LC_DADD(T, a2); T = LC_DADD(T, a3);
+        T = LC_DADD(T, a4); T = LC_DADD(T, a5); T = LC_DADD(T, a6); T = LC_DADD(T, a7);
+    }
+    for (; i < s; i++) T = LC_DADD(T, col[i * 32]);
+    return T;
 }
 
 // smem: tile[n*32] doubles | u1tab[32] doubles | glist[LC_PAR_MAX_SYMBOLS/2] u16
@@ -440,8 +470,7 @@ __device__ __forceinline__ void lc_enc_phase_a_lanes_block(const LcCoderCfg &cfg
                 const int p = spos[t];
                 const int s = codes[p];
                 // exact np.cumsum prefix (:346-347)
-                double T = 0.0;
-                for (int i = 0; i < s; i++) T = LC_DADD(T, col[i * 32]);
+                const double T = lc_col_prefix(col, s);
                 ivs[2 * p] = T;
                 ivs[2 * p + 1] = LC_DADD(T, col[s * 32]);
                 const bool last = (t + 1 >= total) || (skeys[t + 1] != key);
