@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 
 #include "../../include/latentcodec.h"
 #include "lc_coder.cuh"
@@ -229,10 +230,14 @@ __global__ void __launch_bounds__(32) lc_fast_decode_kernel(LcCoderCfg cfg, cons
 //   phase B: the serial range coder over those intervals, one warp per stream
 // =================================================================================================
 typedef cub::BlockRadixSort<uint32_t, 256, LC_PAR_MAX_SYMBOLS / 256, unsigned short> LcBlockSort;
+typedef cub::BlockScan<int, 256> LcBlockScan;
 
+// Also emits, per stream, the list of contexts visited at least twice (glist/ngroups: the work items of
+// phase A) and the closed-form interval of every first visit (uniform model: cum[i] = i/n).
 __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const int *__restrict__ codes,
                                                           uint32_t *__restrict__ skeys, unsigned short *__restrict__ spos,
-                                                          int *__restrict__ first_bad)
+                                                          int *__restrict__ first_bad, unsigned short *__restrict__ glist,
+                                                          int *__restrict__ ngroups, double *__restrict__ ivs)
 {
     extern __shared__ __align__(16) char lc_smem[];
     LcBlockSort::TempStorage &temp = *reinterpret_cast<LcBlockSort::TempStorage *>(lc_smem);
@@ -269,6 +274,43 @@ __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const 
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) { ok[i] = keys[i]; ov[i] = vals[i]; }
     if (threadIdx.x == 0) first_bad[blockIdx.x] = fb;
+
+    // group heads: sorted index j = tid*ITEMS + i starts a context when its key differs from j-1
+    __shared__ uint32_t s_edge_last[256], s_edge_first[256];
+    __shared__ LcBlockScan::TempStorage scan_temp;
+    s_edge_last[threadIdx.x] = keys[ITEMS - 1];
+    s_edge_first[threadIdx.x] = keys[0];
+    __syncthreads();
+    const uint32_t prev_edge = threadIdx.x > 0 ? s_edge_last[threadIdx.x - 1] : 0u;
+    const uint32_t next_edge = threadIdx.x < 255 ? s_edge_first[threadIdx.x + 1] : LC_PAR_KEY_PAD;
+    const double u0 = LC_DDIV(1.0, (double)n);
+    unsigned multi_mask = 0u;
+    int n_multi = 0;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const int j = (int)threadIdx.x * ITEMS + i;
+        const uint32_t kprev = i > 0 ? keys[i - 1] : prev_edge;
+        const uint32_t knext = i < ITEMS - 1 ? keys[i + 1] : next_edge;
+        const bool valid = j < fb; // positions before the first bad symbol; padding keys sort behind them
+        const bool head = valid && (j == 0 || kprev != keys[i]);
+        if (head) {
+            const int p = vals[i];
+            const int sy = c[p];
+            double *o = ivs + (size_t)blockIdx.x * 2 * LC_PAR_MAX_SYMBOLS + 2 * p;
+            o[0] = LC_DMUL((double)sy, u0);
+            o[1] = LC_DMUL((double)(sy + 1), u0);
+        }
+        if (head && (j + 1 < fb) && knext == keys[i]) { multi_mask |= 1u << i; n_multi++; }
+    }
+    int g_off = 0, g_total = 0;
+    LcBlockScan(scan_temp).ExclusiveSum(n_multi, g_off, g_total);
+    unsigned short *gl = glist + (size_t)blockIdx.x * LC_PAR_MAX_GROUPS;
+    while (multi_mask) {
+        const int i = __ffs((int)multi_mask) - 1;
+        multi_mask &= multi_mask - 1;
+        gl[g_off++] = (unsigned short)((int)threadIdx.x * ITEMS + i);
+    }
+    if (threadIdx.x == 0) ngroups[blockIdx.x] = g_total;
 }
 
 __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
@@ -283,10 +325,13 @@ __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, con
 __global__ void __launch_bounds__(32) lc_enc_phase_a_lanes_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
                                                                   const uint32_t *__restrict__ skeys,
                                                                   const unsigned short *__restrict__ spos,
-                                                                  const int *__restrict__ first_bad, double *ivs)
+                                                                  const int *__restrict__ first_bad,
+                                                                  const unsigned short *__restrict__ glist,
+                                                                  const int *__restrict__ ngroups, double *ivs,
+                                                                  unsigned int *task_counter)
 {
     extern __shared__ __align__(16) char lc_smem[];
-    lc_enc_phase_a_lanes_block(cfg, codes, B, skeys, spos, first_bad, ivs, lc_smem);
+    lc_enc_phase_a_lanes_block(cfg, codes, B, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, lc_smem);
 }
 
 __global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
@@ -376,7 +421,7 @@ static int lc_grid_for(const LcCoderCfg &cfg, int B)
 }
 
 // parallel-encoder workspace per stream: sorted keys (4 B) + positions (2 B) + two float64 bounds
-#define LC_PAR_STREAM_BYTES ((int64_t)LC_PAR_MAX_SYMBOLS * (4 + 2 + 8 + 8) + 16)
+#define LC_PAR_STREAM_BYTES ((int64_t)LC_PAR_MAX_SYMBOLS * (4 + 2 + 8 + 8) + LC_PAR_MAX_GROUPS * 2 + 32)
 #define LC_PAR_TILE 2048
 
 static bool lc_use_parallel_encoder(const LcCoderCfg &cfg) { return cfg.has_ctx && cfg.total <= LC_PAR_MAX_SYMBOLS; }
@@ -498,7 +543,7 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
             cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
             cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
             cudaFuncSetAttribute(lc_enc_phase_a_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 256 * 32 * 8 + 256 + LC_PAR_MAX_SYMBOLS);
+                                 256 * 32 * 8 + 256);
             const char *e = getenv("LC_PHASE_A");
             if (e && e[0] == 'w') phase_a_choice = 1;
             if (e && e[0] == 'l') phase_a_choice = 2;
@@ -512,13 +557,21 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
             uint32_t *skeys = (uint32_t *)ws;                 ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 4;
             double *ivs = (double *)ws;                       ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 16;
             unsigned short *spos = (unsigned short *)ws;      ws += (size_t)nb * LC_PAR_MAX_SYMBOLS * 2;
-            int *first_bad = (int *)ws;
+            unsigned short *glist = (unsigned short *)ws;     ws += (size_t)nb * LC_PAR_MAX_GROUPS * 2;
+            int *first_bad = (int *)ws;                       ws += (size_t)nb * 4;
+            int *ngroups = (int *)ws;                         ws += (size_t)nb * 4;
+            unsigned int *task_counter = (unsigned int *)ws;
             const int *codes = idx + (size_t)b0 * cfg.total;
-            lc_enc_sort_kernel<<<nb, 256, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad);
+            lc_enc_sort_kernel<<<nb, 256, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs);
             LC_CUDA_RET();
             if (lanes_variant) {
-                const size_t la_smem = (size_t)cfg.n * 32 * 8 + 256 + LC_PAR_MAX_SYMBOLS;
-                lc_enc_phase_a_lanes_kernel<<<nb, 32, la_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
+                const size_t la_smem = (size_t)cfg.n * 32 * 8 + 256;
+                int per_sm = (int)((227u * 1024u) / (la_smem + 1024u));
+                if (per_sm > 16) per_sm = 16;
+                const int la_grid = lc_num_sms() * per_sm;
+                cudaMemsetAsync(task_counter, 0, 4, st);
+                lc_enc_phase_a_lanes_kernel<<<la_grid, 32, la_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, glist,
+                                                                          ngroups, ivs, task_counter);
             } else {
                 lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
             }

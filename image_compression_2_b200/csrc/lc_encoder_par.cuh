@@ -391,10 +391,43 @@ __device__ __forceinline__ double lc_col_prefix(const double *col, int s)
     return T;
 }
 
-// smem: tile[n*32] doubles | u1tab[32] doubles | glist[LC_PAR_MAX_SYMBOLS/2] u16
+// Group list of one stream, produced by phase S (lc_enc_sort_kernel) or, for the emulator, by
+// lc_enc_group_list_warp below: glist[g] = sorted index of the first visit of the g-th context that is
+// visited at least twice; first visits get their closed-form interval (uniform model: cum[i] = i/n).
+#define LC_PAR_MAX_GROUPS (LC_PAR_MAX_SYMBOLS / 2)
+#define LC_PAR_TASK_GROUPS 64
+
+__device__ __forceinline__ int lc_enc_group_list_warp(int lane, const int *codes, const uint32_t *skeys,
+                                                      const unsigned short *spos, int total, double u0, double *ivs,
+                                                      unsigned short *glist)
+{
+    int ngroups = 0;
+    for (int base = 0; base < total; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < total;
+        const uint32_t kj = valid ? skeys[j] : 0u;
+        const bool head = valid && (j == 0 || skeys[j - 1] != kj);
+        if (head) {
+            const int p = spos[j];
+            const int s = codes[p];
+            ivs[2 * p] = LC_DMUL((double)s, u0);
+            ivs[2 * p + 1] = LC_DMUL((double)(s + 1), u0);
+        }
+        const bool multi = head && (j + 1 < total) && (skeys[j + 1] == kj);
+        const unsigned m = __ballot_sync(LC_FULL_MASK, multi);
+        if (multi) glist[ngroups + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+        ngroups += __popc(m);
+    }
+    return ngroups;
+}
+
+// smem: tile[n*32] doubles | u1tab[32] doubles.
+// Persistent warps pull tasks (stream, chunk of LC_PAR_TASK_GROUPS groups) from *task_counter.
 __device__ __forceinline__ void lc_enc_phase_a_lanes_block(const LcCoderCfg &cfg, const int *codes_all, int B,
                                                            const uint32_t *skeys_all, const unsigned short *spos_all,
-                                                           const int *first_bad, double *ivs_all, char *smem)
+                                                           const int *first_bad, const unsigned short *glist_all,
+                                                           const int *ngroups_all, double *ivs_all,
+                                                           unsigned int *task_counter, char *smem)
 {
     const int lane = (int)(threadIdx.x & 31);
     const int n = cfg.n, pw_len = cfg.pw_len, pw_steps = cfg.pw_steps;
@@ -404,7 +437,6 @@ __device__ __forceinline__ void lc_enc_phase_a_lanes_block(const LcCoderCfg &cfg
     double *tile = (double *)smem;
     double *col = tile + lane;
     double *u1tab = tile + (size_t)n * 32;
-    unsigned short *glist = (unsigned short *)(u1tab + 32);
     // u after the first update, by chain step of the symbol (by symbol when n < 8): each lane computes one entry
     {
         const int entries = cfg.pw_chains == 0 ? n : pw_steps;
@@ -416,66 +448,91 @@ __device__ __forceinline__ void lc_enc_phase_a_lanes_block(const LcCoderCfg &cfg
         }
         __syncwarp();
     }
-    for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
+    const unsigned chunks_per_stream = LC_PAR_MAX_GROUPS / LC_PAR_TASK_GROUPS;
+    const unsigned n_tasks = (unsigned)B * chunks_per_stream;
+    for (;;) {
+        unsigned task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1u);
+        task = __shfl_sync(LC_FULL_MASK, task, 0);
+        if (task >= n_tasks) break;
+        const int sidx = (int)(task / chunks_per_stream);
+        const int g_lo = (int)(task % chunks_per_stream) * LC_PAR_TASK_GROUPS;
+        const int ngroups = ngroups_all[sidx];
+        if (g_lo >= ngroups) continue;
+        const int g_hi = (g_lo + LC_PAR_TASK_GROUPS < ngroups) ? g_lo + LC_PAR_TASK_GROUPS : ngroups;
         const size_t o = (size_t)sidx * LC_PAR_MAX_SYMBOLS;
         const int *codes = codes_all + (size_t)sidx * cfg.total;
         const uint32_t *skeys = skeys_all + o;
         const unsigned short *spos = spos_all + o;
+        const unsigned short *glist = glist_all + (size_t)sidx * LC_PAR_MAX_GROUPS;
         double *ivs = ivs_all + 2 * o;
         const int fb = first_bad[sidx];
         const int total = fb < cfg.total ? fb : cfg.total;
-        // pass 1: first visits are closed form; list the groups that have a second visit
-        int ngroups = 0;
-        for (int base = 0; base < total; base += 32) {
-            const int j = base + lane;
-            const bool valid = j < total;
-            const uint32_t kj = valid ? skeys[j] : 0u;
-            const bool head = valid && (j == 0 || skeys[j - 1] != kj);
-            if (head) {
-                const int p = spos[j];
-                const int s = codes[p];
-                ivs[2 * p] = LC_DMUL((double)s, u0);
-                ivs[2 * p + 1] = LC_DMUL((double)(s + 1), u0);
-            }
-            const bool multi = head && (j + 1 < total) && (skeys[j + 1] == kj);
-            const unsigned m = __ballot_sync(LC_FULL_MASK, multi);
-            if (multi) glist[ngroups + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
-            ngroups += __popc(m);
-        }
-        __syncwarp();
-        // pass 2: every lane walks one group at a time, one visit per step
-        int next = 0;      // next unassigned entry of glist (warp-uniform)
-        int t = -1;        // sorted index of the visit this lane handles in the current step, -1 = idle
+
+        // every lane walks one group at a time, one visit per step
+        int next = g_lo;   // next unassigned group of this task (warp-uniform)
+        int t = -1;        // sorted index of the visit handled in this step, -1 = idle
+        int visit = 0;     // 2 = second visit of the group (model still implicit), >= 3 = column is live
+        int s1 = 0, p = 0, s = 0;
+        bool last = false;
+        double u1 = 0.0;
         uint32_t key = 0u;
         for (;;) {
-            // lanes without a group take the next ones from the list
             const unsigned need = __ballot_sync(LC_FULL_MASK, t < 0);
             if (need) {
                 const int g = next + __popc(need & ((1u << lane) - 1u));
-                if (t < 0 && g < ngroups) {
+                if (t < 0 && g < g_hi) {
                     const int j0 = glist[g];
                     key = skeys[j0];
-                    const int s1 = codes[spos[j0]];
-                    // model after the first visit: P1 at s1, u1 elsewhere
-                    const double u1 = u1tab[cfg.pw_chains == 0 ? s1 : ((s1 & (pw_len - 1)) >> 3)];
-                    for (int i = 0; i < n; i++) col[i * 32] = u1;
-                    col[s1 * 32] = P1;
+                    s1 = codes[spos[j0]];
+                    u1 = u1tab[cfg.pw_chains == 0 ? s1 : ((s1 & (pw_len - 1)) >> 3)];
                     t = j0 + 1; // its second visit
+                    visit = 2;
+                    p = spos[t]; s = codes[p];
+                    last = (t + 1 >= total) || (skeys[t + 1] != key);
                 }
                 next += __popc(need);
-                if (next > ngroups) next = ngroups;
+                if (next > g_hi) next = g_hi;
             }
             if (__ballot_sync(LC_FULL_MASK, t >= 0) == 0u) break;
             if (t >= 0) {
-                const int p = spos[t];
-                const int s = codes[p];
-                // exact np.cumsum prefix (:346-347)
-                const double T = lc_col_prefix(col, s);
+                // data of the following visit (if any): requested now, used in the next step
+                const bool more = !last;
+                int p_n = 0, s_n = 0;
+                bool last_n = true;
+                if (more) {
+                    p_n = spos[t + 1];
+                    last_n = (t + 2 >= total) || (skeys[t + 2] != key);
+                }
+                double T;
+                double ps;
+                if (visit == 2) {
+                    // model after one update: u1 everywhere, P1 at s1 -- the exact np.cumsum prefix needs no column
+                    T = 0.0;
+                    const int run1 = s < s1 ? s : s1;
+                    for (int i = 0; i < run1; i++) T = LC_DADD(T, u1);
+                    if (s > s1) {
+                        T = LC_DADD(T, P1);
+                        for (int i = s1 + 1; i < s; i++) T = LC_DADD(T, u1);
+                    }
+                    ps = (s == s1) ? P1 : u1;
+                } else {
+                    T = lc_col_prefix(col, s);
+                    ps = col[s * 32];
+                }
                 ivs[2 * p] = T;
-                ivs[2 * p + 1] = LC_DADD(T, col[s * 32]);
-                const bool last = (t + 1 >= total) || (skeys[t + 1] != key);
+                ivs[2 * p + 1] = LC_DADD(T, ps);
+                if (more) s_n = codes[p_n];
                 if (last) t = -1; // the update after the last visit is never read
-                else { lc_col_update(col, n, pw_len, pw_steps, rate, s); t++; }
+                else {
+                    if (visit == 2) { // the group goes on: materialise the column now
+                        for (int i = 0; i < n; i++) col[i * 32] = u1;
+                        col[s1 * 32] = P1;
+                    }
+                    lc_col_update(col, n, pw_len, pw_steps, rate, s);
+                    t++; visit = 3;
+                    p = p_n; s = s_n; last = last_n;
+                }
             }
         }
         __syncwarp();

@@ -171,6 +171,7 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline long long __double2ll_rz(double a) { return (long long)a; }
 static inline double __ll2double_rn(long long a) { return (double)a; }
 static inline double __int2double_rn(int a) { return (double)a; }
+static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p = o + v; return o; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }
 template <typename T> static inline void __stcg(T *p, T v) { *p = v; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }

@@ -183,7 +183,7 @@ extern "C" void hostsim_stats(long long *out, int reset)
 // ---- parallel encoder: phase S restated on the host (the real kernel uses a CUB block sort and is
 // checked on the GPU), phases A and B run through the emulator
 struct ParAArgs { LcCoderCfg cfg; const int *codes; int B; const uint32_t *skeys; const unsigned short *spos;
-                  const int *first_bad; double *ivs; char *smem; };
+                  const int *first_bad; double *ivs; char *smem; unsigned short *glist; int *ngroups; unsigned int *task_counter; };
 static void para_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
@@ -194,7 +194,22 @@ struct ParBArgs { LcCoderCfg cfg; int B; const int *first_bad; const double *ivs
 static void para_lanes_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
-    lc_enc_phase_a_lanes_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->ivs, a->smem);
+    lc_enc_phase_a_lanes_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->glist, a->ngroups, a->ivs,
+                               a->task_counter, a->smem);
+}
+static void glist_body(void *p)
+{   // phase S part: group list + first-visit intervals (on the GPU this is done by lc_enc_sort_kernel)
+    ParAArgs *a = (ParAArgs *)p;
+    const int lane = (int)(threadIdx.x & 31);
+    const double u0 = 1.0 / (double)a->cfg.n;
+    for (int b = (int)blockIdx.x; b < a->B; b += (int)gridDim.x) {
+        const size_t o = (size_t)b * LC_PAR_MAX_SYMBOLS;
+        const int fb = a->first_bad[b];
+        const int total = fb < a->cfg.total ? fb : a->cfg.total;
+        const int ng = lc_enc_group_list_warp(lane, a->codes + (size_t)b * a->cfg.total, a->skeys + o, a->spos + o, total, u0,
+                                              a->ivs + 2 * o, a->glist + (size_t)b * LC_PAR_MAX_GROUPS);
+        if (lane == 0) a->ngroups[b] = ng;
+    }
 }
 static void parb_body(void *p)
 {
@@ -236,9 +251,13 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
     }
     std::vector<double> ivs((size_t)B * LC_PAR_MAX_SYMBOLS * 2, -1.0);
     std::vector<char> smem(std::max((size_t)nwarps * n * 8, (size_t)n * 32 * 8 + 256 + LC_PAR_MAX_SYMBOLS) + 64);
+    std::vector<unsigned short> glist((size_t)B * LC_PAR_MAX_GROUPS, 0);
+    std::vector<int> ngroups(B, 0);
+    unsigned int task_counter = 0;
     ParAArgs a{cfg, codes, B, skeys.data(), spos.data(), first_bad.data(), ivs.data(),
-               (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15)};
-    if (nwarps == 0) { // lane-per-group variant: one warp per block
+               (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15), glist.data(), ngroups.data(), &task_counter};
+    if (nwarps == 0) { // lane-per-group variant: one warp per block, tasks from a shared counter
+        for (int b = 0; b < grid; b++) emu::run_warp(glist_body, &a, (unsigned)b, (unsigned)grid);
         for (int b = 0; b < grid; b++) emu::run_warp(para_lanes_body, &a, (unsigned)b, (unsigned)grid);
     } else
     for (int b = 0; b < grid; b++)
