@@ -42,6 +42,9 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.LIB
+    override = os.environ.get("LATENTCODEC_LIB")  # debug builds (tools/dec_profile.py); same ABI
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing and _build.needs_build():
         if _build.nvcc_path() is not None:
             _build.build_library()

@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblatentcodec.so")
 SOURCES = [os.path.join(CSRC, "latentcodec.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "lc_coder.cuh"), os.path.join(CSRC, "lc_common.cuh"),
-                  os.path.join(os.path.dirname(HERE), "include", "latentcodec.h")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", "latentcodec.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -33,17 +33,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build_library(force=False, verbose=False):
-    """Compile the CUDA library if it is missing or stale. Returns its path."""
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """Compile the CUDA library if it is missing or stale. Returns its path.
+    `out`/`defines` build a debug variant elsewhere (tools/dec_profile.py)."""
+    target = out or LIB
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build liblatentcodec.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + SOURCES
+    cmd = ([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", target + ".tmp"] + SOURCES)
     subprocess.check_call(cmd)
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
+    os.replace(target + ".tmp", target)
+    return target
 
 
 if __name__ == "__main__":

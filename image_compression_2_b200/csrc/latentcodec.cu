@@ -634,4 +634,15 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
     return 0;
 }
 
+#ifdef LC_DEC_PROFILE
+// debug builds only (tools/dec_profile.py): read and clear the decoder's cycle counters
+int lc_debug_profile(unsigned long long *out64)
+{
+    static unsigned long long zero[64];
+    if (cudaMemcpyFromSymbol(out64, lc_prof_global, sizeof(zero)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(lc_prof_global, zero, sizeof(zero)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
+
 } // extern "C"

@@ -22,6 +22,28 @@
 
 #define LC_NEEDS_GENERIC 100 // internal status: more than 32 distinct symbols in one context
 
+// Optional per-state cycle accounting (build with -DLC_DEC_PROFILE; tools/dec_profile.py).  Row = context
+// state 0..3 (+4: symbols that needed the exact search, +5: symbols that needed exact_at), columns =
+// count, then cycles spent in probe / model load / search / interval / renorm+output / write-back.
+#ifdef LC_DEC_PROFILE
+__device__ unsigned long long lc_prof_global[8 * 8];
+#define LCP_DECL __shared__ unsigned long long lcp_sm[8 * 8]; long long lcp_t = 0; int lcp_row = 0;
+#define LCP_INIT() do { for (int i_ = F.lane; i_ < 64; i_ += 32) lcp_sm[i_] = 0ull; __syncwarp(); } while (0)
+#define LCP_START() do { lcp_t = clock64(); } while (0)
+#define LCP_ROW(r_) do { lcp_row = (r_); } while (0)
+#define LCP_MARK(col_) do { const long long n_ = clock64(); if (F.lane == 0) lcp_sm[lcp_row * 8 + (col_)] += (unsigned long long)(n_ - lcp_t); lcp_t = n_; } while (0)
+#define LCP_COUNT(r_, col_) do { if (F.lane == 0) lcp_sm[(r_) * 8 + (col_)] += 1ull; } while (0)
+#define LCP_FLUSH() do { __syncwarp(); for (int i_ = F.lane; i_ < 64; i_ += 32) atomicAdd(&lc_prof_global[i_], lcp_sm[i_]); } while (0)
+#else
+#define LCP_DECL
+#define LCP_INIT()
+#define LCP_START()
+#define LCP_ROW(r_)
+#define LCP_MARK(col_)
+#define LCP_COUNT(r_, col_)
+#define LCP_FLUSH()
+#endif
+
 #define LCF_STATE(w) ((int)(((w) >> 22) & 3ull))
 #define LCF_S1(w) ((int)(((w) >> 24) & 0x3FFull))
 #define LCF_S2(w) ((int)(((w) >> 34) & 0x3FFull))
@@ -301,6 +323,8 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
                                                       int *fault_index)
 {
     const uint32_t mask = F.slot_cap - 1;
+    LCP_DECL
+    LCP_INIT();
     for (uint32_t i = F.lane; i < F.slot_cap; i += 32) __stcg(&F.slots[i], 0ull);
     F.pool_top = 0;
     __syncwarp();
@@ -316,6 +340,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
     unsigned long long w = __ldcg(&F.slots[(start + (uint32_t)F.lane) & mask]);
     for (; pos < F.total; pos++) {
         // ---- resolve the probe
+        LCP_START();
         const uint32_t want = key + 1u;
         uint32_t slot_idx;
         unsigned long long word = 0ull;
@@ -329,6 +354,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
             w = __ldcg(&F.slots[(start + (uint32_t)F.lane) & mask]);
         }
         const int state = LCF_STATE(word);
+        LCP_ROW(state); LCP_COUNT(state, 0); LCP_MARK(1);
         // ---- bring the model of this context into registers
         if (state == 1) lcf_state_first(F, LCF_S1(word));
         else if (state == 2) {
@@ -343,6 +369,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
             F.my_val = valid ? __ldcg((const double *)(rec + 8) + F.lane) : 0.0;
             F.my_sym = valid ? (int)__ldcg((const unsigned short *)(rec + 8 + (8 << cl)) + F.lane) : 0x7fffffff;
         }
+        LCP_MARK(2);
         // ---- decode_symbol (:272-292)
         const long long range = (long long)hi - (long long)lo + 1;
         if (range == 0) { status = LC_DEC_ZERO_RANGE; break; }
@@ -364,6 +391,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
             decided = state == 1 ? lcf_search_first(F, LCF_S1(word), va, iv) : lcf_search(F, va, iv);
         }
         if (!decided) { // exact quotient, exact sums
+            LCP_COUNT(4, state);
             double v = LC_DDIV(LC_DMUL(num, 1.0), rdv);
             v = LC_DSUB(v, 1e-10);
             if (state == 0) {
@@ -379,6 +407,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         if (iv.sym >= F.n) { status = LC_DEC_SYMBOL_OOB; break; }
         if (iv.sym < 0) { status = LC_DEC_NEG_SYMBOL; break; }
         const int s = iv.sym;
+        LCP_MARK(3);
         // ---- the symbol is known: request the table window of the NEXT position's context now, so
         // its latency overlaps the interval update, renormalisation and write-back below
         if (F.lane == 0) F.rows[(r & 1) * F.C + c] = (unsigned short)s;
@@ -393,6 +422,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         long long low64 = lo, high64 = hi;
         if (!lc_interval_apply(iv, F.delta, low64, high64)) {
             // the symbol itself was decided with margin; only the exact bounds are missing
+            LCP_COUNT(5, state);
             lcf_exact_at(F, iv.sym, iv);
 #ifdef LC_HOSTSIM
             { // emulator-only check of the margin argument: the exact sums must bracket the exact v
@@ -403,6 +433,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
             lc_interval_apply(iv, F.delta, low64, high64);
         }
         lo = (uint32_t)low64; hi = (uint32_t)high64;
+        LCP_MARK(4);
         // ---- renormalise (:295-303) and underflow (:306-309), closed form
         {
             const int d = __clz((int)(lo ^ hi));
@@ -426,6 +457,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
             out[p] = my_out;
             if (deq_out) deq_out[p] = __ldg(deq_table + my_out);
         }
+        LCP_MARK(5);
         // ---- write back this context
         unsigned long long new_word;
         if (state == 0) new_word = LCF_PACK_A(want, s);
@@ -455,7 +487,9 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         __syncwarp();
         key = key2; start = start2; w = w2;
         left = s; c = c2; r = r2;
+        LCP_MARK(6);
     }
+    LCP_FLUSH();
     *fault_index = pos;
     *status_out = status;
     {
