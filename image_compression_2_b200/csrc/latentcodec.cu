@@ -12,6 +12,7 @@
 #include "lc_coder.cuh"
 #include "lc_encoder_par.cuh"
 #include "lc_decoder_fast.cuh"
+#include "lc_decoder_v2.cuh"
 
 #define LC_CUDA_RET()                                                     \
     do {                                                                  \
@@ -223,6 +224,26 @@ __global__ void __launch_bounds__(32) lc_fast_decode_kernel(LcCoderCfg cfg, cons
     lc_fast_decode_block(cfg, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, lc_smem);
 }
 
+// Decoder v2 (lc_decoder_v2.cuh): one block per stream = one decoder warp + LCV_NU updater warps; a
+// one-block kernel first fills the per-launch tables (u after the first update, exact cumsum rows).
+__global__ void __launch_bounds__(256) lc_v2_tables_kernel(LcCoderCfg cfg, double *tables)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lcv_tables_block(cfg, tables, lc_smem);
+}
+
+__global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_kernel(LcCoderCfg cfg, LcV2Cfg vc,
+                                                                          const unsigned char *__restrict__ bytes,
+                                                                          const long long *__restrict__ offsets,
+                                                                          const int *__restrict__ nbits, int B, int *out,
+                                                                          const float *__restrict__ deq_table,
+                                                                          float *deq_out, int *status, int *fault,
+                                                                          char *scratch, const double *tables)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lcv_decode_block(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables, lc_smem);
+}
+
 // =================================================================================================
 // K3-parallel: the encoder split by context group (lc_encoder_par.cuh)
 //   phase S: keys + stable sort by key (one 256-thread block per stream, CUB block radix sort)
@@ -426,9 +447,36 @@ static int lc_grid_for(const LcCoderCfg &cfg, int B)
 
 static bool lc_use_parallel_encoder(const LcCoderCfg &cfg) { return cfg.has_ctx && cfg.total <= LC_PAR_MAX_SYMBOLS; }
 
+// decoder v2: which kernel decodes (LC_DECODER=fast keeps the previous kernel, for A/B runs), grid, scratch
+static bool lc_use_decoder_v2(const LcCoderCfg &cfg)
+{
+    static int choice = -1;
+    if (choice < 0) { const char *e = getenv("LC_DECODER"); choice = (e && e[0] == 'f') ? 0 : 1; }
+    return choice == 1 && lcv_eligible(cfg);
+}
+static int lc_v2_grid(const LcV2Cfg &vc, int B)
+{
+    int per_sm = (int)((227u * 1024u) / (vc.sm_bytes + 1024u));
+    if (per_sm > 7) per_sm = 7;
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)lc_num_sms() * per_sm;
+    if (g > B) g = B;
+    return g < 1 ? 1 : (int)g;
+}
+static int64_t lc_v2_scratch_need(const LcCoderCfg &cfg, int B)
+{
+    LcV2Cfg vc;
+    lcv_cfg_make(cfg, &vc);
+    return (int64_t)lc_v2_grid(vc, B) * (int64_t)vc.g_stride + (int64_t)lcv_tables_bytes(cfg.n) + 256;
+}
+
 static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
 {
     int64_t need = (int64_t)lc_grid_for(cfg, B) * (int64_t)cfg.scratch_stride;
+    if (lc_use_decoder_v2(cfg)) {
+        const int64_t v2 = lc_v2_scratch_need(cfg, B);
+        if (v2 > need) need = v2;
+    }
     if (lc_use_parallel_encoder(cfg)) {
         const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES;
         if (par > need) need = par;
@@ -614,6 +662,31 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg.sm_bytes > 48 * 1024)
         cudaFuncSetAttribute(lc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+    if (lc_use_decoder_v2(cfg)) {
+        // decoder/updater warps; streams with a context of more than 32 distinct symbols are flagged
+        // and redone from scratch by the generic kernel
+        LcV2Cfg vc;
+        lcv_cfg_make(cfg, &vc);
+        const int g2 = lc_v2_grid(vc, B);
+        double *tables = (double *)((char *)scratch + (((size_t)g2 * vc.g_stride + 255) & ~(size_t)255));
+        static bool v2_attr = false;
+        if (!v2_attr) {
+            cudaFuncSetAttribute(lc_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            v2_attr = true;
+        }
+        if (vc.sm_bytes > 64 * 1024) return -22;
+        lc_v2_tables_kernel<<<1, 256, (size_t)(cfg.n + 64) * 8, st>>>(cfg, tables);
+        LC_CUDA_RET();
+        lc_decode_v2_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits, B,
+                                                                     idx_out, deq_table, deq_out, status, fault_index,
+                                                                     (char *)scratch, tables);
+        LC_CUDA_RET();
+        lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
+                                                         deq_table, deq_out, status, fault_index, (char *)scratch,
+                                                         LC_NEEDS_GENERIC);
+        LC_CUDA_RET();
+        return 0;
+    }
     if (cfg.mode == LC_MODE_REPAIRED && cfg.has_ctx) {
         // fast kernel; streams it cannot finish (a context with more than 32 distinct symbols) are
         // flagged and redone from scratch by the generic kernel

@@ -317,6 +317,71 @@ __device__ __forceinline__ uint32_t lcf_br_bits(LcBitReader64 &b, int nb, int la
     return v;
 }
 
+
+// decode_symbol (:272-292), search part: the symbol of the open context's model held in F (state 0: uniform
+// vector, 1: one update with s1, >= 2: register record) for the coder state (lo, hi, code).
+// Returns LC_OK (| 0x100 when the exact path was needed) or the fault status; num/rdv are (code-low+1) and range.
+__device__ __forceinline__ int lcf_find_symbol(const LcFast &F, int state, int s1, uint32_t lo, uint32_t hi, uint32_t code,
+                                               LcInterval &iv, double &num, double &rdv)
+{
+    const long long range = (long long)hi - (long long)lo + 1;
+    if (range == 0) return LC_DEC_ZERO_RANGE;
+    // scaled_value = (code-low+1)*1.0/range - 1e-10 (:285).  The IEEE quotient is only needed when
+    // a decision falls inside the guard band; the searches run on a fast quotient whose error
+    // (< 2^-46 absolute, v <= ~1) is part of F.delta_v.
+    num = lc_ll2d_small((long long)code - (long long)lo + 1);
+    rdv = lc_ll2d_small(range);
+    const double va = num * lc_rcp_fast(rdv) - 1e-10;
+    bool decided;
+    int flags = 0;
+    if (state == 0) { // uniform context: first i with i/n >= v, i.e. ceil(v*n) - 1
+        iv.exact = 1;
+        const double t = va * (double)F.n;
+        const double tr = nearbyint(t);
+        decided = (t > F.tmargin) && (fabs(t - tr) > F.tmargin) && (t < (double)F.n);
+        if (decided) iv.sym = (int)ceil(t) - 1;
+    } else {
+        decided = state == 1 ? lcf_search_first(F, s1, va, iv) : lcf_search(F, va, iv);
+    }
+    if (!decided) { // exact quotient, exact sums
+        flags = 0x100;
+        double v = LC_DDIV(LC_DMUL(num, 1.0), rdv);
+        v = LC_DSUB(v, 1e-10);
+        if (state == 0) {
+            iv.exact = 1;
+            if (!(0.0 < v)) iv.sym = -1;
+            else {
+                const double t = LC_DMUL(v, (double)F.n);
+                iv.sym = (t > (double)F.n) ? F.n : (int)(LC_D2LL(t) + ((double)LC_D2LL(t) < t ? 1 : 0)) - 1;
+            }
+        } else lcf_exact_search(F, v, iv);
+    }
+    if (state == 0) { iv.clo = LC_DMUL((double)iv.sym, F.u0); iv.chi = LC_DMUL((double)(iv.sym + 1), F.u0); }
+    if (iv.sym >= F.n) return LC_DEC_SYMBOL_OOB;
+    if (iv.sym < 0) return LC_DEC_NEG_SYMBOL;
+    return LC_OK | flags;
+}
+
+// decode_symbol (:291-292), interval part: high/low from the symbol's cumulative bounds
+__device__ __forceinline__ void lcf_apply_symbol(const LcFast &F, LcInterval &iv, double num, double rdv, uint32_t &lo,
+                                                 uint32_t &hi)
+{
+    long long low64 = lo, high64 = hi;
+    if (!lc_interval_apply(iv, F.delta, low64, high64)) {
+        // the symbol itself was decided with margin; only the exact bounds are missing
+        lcf_exact_at(F, iv.sym, iv);
+#ifdef LC_HOSTSIM
+        { // emulator-only check of the margin argument: the exact sums must bracket the exact v
+            const double vx = LC_DSUB(LC_DDIV(LC_DMUL(num, 1.0), rdv), 1e-10);
+            if (!(iv.clo < vx) || !(vx <= iv.chi)) { fprintf(stderr, "lc_decoder_fast: guard argument violated\n"); abort(); }
+        }
+#endif
+        lc_interval_apply(iv, F.delta, low64, high64);
+    }
+    (void)num; (void)rdv;
+    lo = (uint32_t)low64; hi = (uint32_t)high64;
+}
+
 // =================================================================================================
 __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned char *src, long long nbytes, int *out,
                                                       const float *deq_table, float *deq_out, int *status_out,
@@ -371,41 +436,15 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         }
         LCP_MARK(2);
         // ---- decode_symbol (:272-292)
-        const long long range = (long long)hi - (long long)lo + 1;
-        if (range == 0) { status = LC_DEC_ZERO_RANGE; break; }
-        // scaled_value = (code-low+1)*1.0/range - 1e-10 (:285).  The IEEE quotient is only needed when
-        // a decision falls inside the guard band; the searches run on a fast quotient whose error
-        // (< 2^-46 absolute, v <= ~1) is part of F.delta_v.
-        const double num = lc_ll2d_small((long long)code - (long long)lo + 1);
-        const double rdv = lc_ll2d_small(range);
-        const double va = num * lc_rcp_fast(rdv) - 1e-10;
         LcInterval iv;
-        bool decided;
-        if (state == 0) { // uniform context: first i with i/n >= v, i.e. ceil(v*n) - 1
-            iv.exact = 1;
-            const double t = va * (double)F.n;
-            const double tr = nearbyint(t);
-            decided = (t > F.tmargin) && (fabs(t - tr) > F.tmargin) && (t < (double)F.n);
-            if (decided) iv.sym = (int)ceil(t) - 1;
-        } else {
-            decided = state == 1 ? lcf_search_first(F, LCF_S1(word), va, iv) : lcf_search(F, va, iv);
+        double num, rdv;
+        {
+            const int fs = lcf_find_symbol(F, state, LCF_S1(word), lo, hi, code, iv, num, rdv);
+#ifdef LC_DEC_PROFILE
+            if (fs & 0x100) LCP_COUNT(4, state);
+#endif
+            if ((fs & 0xff) != LC_OK) { status = fs & 0xff; break; }
         }
-        if (!decided) { // exact quotient, exact sums
-            LCP_COUNT(4, state);
-            double v = LC_DDIV(LC_DMUL(num, 1.0), rdv);
-            v = LC_DSUB(v, 1e-10);
-            if (state == 0) {
-                iv.exact = 1;
-                if (!(0.0 < v)) iv.sym = -1;
-                else {
-                    const double t = LC_DMUL(v, (double)F.n);
-                    iv.sym = (t > (double)F.n) ? F.n : (int)(LC_D2LL(t) + ((double)LC_D2LL(t) < t ? 1 : 0)) - 1;
-                }
-            } else lcf_exact_search(F, v, iv);
-        }
-        if (state == 0) { iv.clo = LC_DMUL((double)iv.sym, F.u0); iv.chi = LC_DMUL((double)(iv.sym + 1), F.u0); }
-        if (iv.sym >= F.n) { status = LC_DEC_SYMBOL_OOB; break; }
-        if (iv.sym < 0) { status = LC_DEC_NEG_SYMBOL; break; }
         const int s = iv.sym;
         LCP_MARK(3);
         // ---- the symbol is known: request the table window of the NEXT position's context now, so
@@ -419,20 +458,10 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         const uint32_t start2 = ((key2 * 2654435761u) >> F.slot_shift) & ~15u;
         unsigned long long w2 = __ldcg(&F.slots[(start2 + (uint32_t)F.lane) & mask]);
 
-        long long low64 = lo, high64 = hi;
-        if (!lc_interval_apply(iv, F.delta, low64, high64)) {
-            // the symbol itself was decided with margin; only the exact bounds are missing
-            LCP_COUNT(5, state);
-            lcf_exact_at(F, iv.sym, iv);
-#ifdef LC_HOSTSIM
-            { // emulator-only check of the margin argument: the exact sums must bracket the exact v
-                const double vx = LC_DSUB(LC_DDIV(LC_DMUL(num, 1.0), rdv), 1e-10);
-                if (!(iv.clo < vx) || !(vx <= iv.chi)) { fprintf(stderr, "lc_decoder_fast: guard argument violated\n"); abort(); }
-            }
+#ifdef LC_DEC_PROFILE
+        { long long l_ = lo, h_ = hi; if (!lc_interval_apply(iv, F.delta, l_, h_)) LCP_COUNT(5, state); }
 #endif
-            lc_interval_apply(iv, F.delta, low64, high64);
-        }
-        lo = (uint32_t)low64; hi = (uint32_t)high64;
+        lcf_apply_symbol(F, iv, num, rdv, lo, hi);
         LCP_MARK(4);
         // ---- renormalise (:295-303) and underflow (:306-309), closed form
         {

@@ -1,0 +1,644 @@
+// Decoder v2: cabac_decode (cabac_compression.py:363-406), repaired coder mode, (left,up) contexts,
+// alphabets of at most 256 symbols.  Same results as lc_decoder_fast.cuh / lc_coder.cuh; restructured
+// around the measured per-state cycle budget of the first two versions (profiles/r01_decoder_state_cycles_*):
+// the serial chain per symbol was ~2800 cycles, spread evenly over table probe, search, interval and
+// -- for contexts seen three times or more -- the model update (pairwise sum, IEEE division).
+//
+//  * Role-specialised warps.  A block is one stream: warp 0 (the DECODER warp) runs the strictly serial
+//    part -- context lookup, symbol search, interval, renormalisation -- and never does model arithmetic;
+//    warps 1..LCV_NU (UPDATER warps) run ContextModel.update_model (:119-144) behind it.  The decoder
+//    posts (context, symbol) jobs into a shared-memory ring and goes on; a model is only needed again
+//    when its context recurs, which the decoder detects from the keys of its last LCV_RING jobs (held
+//    one per lane) and then waits for.  No cross-warp flag is read on the common path.
+//  * Direct-mapped context table.  key = (left+1)*(n+1)+(up+1) < (n+1)^2 indexes a 2-bit state array in
+//    SHARED memory (0 never seen, 1 seen once, 2 record inline, 3 record in the pool), a 4-byte word and
+//    a 64-byte record in global memory.  48 % of the symbols of the benchmark open a fresh context and
+//    are resolved from shared memory alone; the global arrays are never cleared (the state bits say what
+//    is valid).
+//  * Fresh contexts (state 0) are decoded in integer arithmetic: the uniform model's bounds i/n are
+//    exact, so symbol and new low/high are 64-bit integer products, verified with integer margins.
+//  * Contexts seen once (state 1) use a per-launch table of the EXACT np.cumsum values of the model
+//    after one update (it depends only on the first symbol): no guard band, no sequential re-summation
+//    (the truncation guard of the previous version tripped on a third of these symbols).
+//  * Records of at most LCV_INLINE_K entries (94 % of the deeper visits) are searched as scalar code
+//    from registers; larger ones use the lane-parallel search of lc_decoder_fast.cuh.
+//  * The bit reader is warp-uniform (every lane loads the same word, one refill ahead).
+// Whenever a fast path cannot decide with its margins it falls back to lcf_find_symbol /
+// lcf_apply_symbol, the same exact evaluation the other kernels use.
+#pragma once
+#include "lc_decoder_fast.cuh"
+
+#define LCV_NU 2
+#define LCV_WARPS (1 + LCV_NU)
+#define LCV_RING 32
+#define LCV_INLINE_K 6
+#define LCV_SENTINEL 0xFFFFFFFFu
+#define LCV_MAX_N 256
+#define LCV_MAX_C 4096
+
+// launch description (host fills it: lcv_cfg_make)
+struct LcV2Cfg {
+    uint32_t nkeys;       // (n+1)^2
+    uint32_t lg_n;        // log2 n
+    uint32_t eps_k;       // floor(1e-10 * n * 2^40): the -1e-10 of decode_symbol in units of range/2^40
+    uint32_t pool_bytes;  // overflow-record pool per block
+    // shared memory carve-up
+    uint32_t sm_bits, sm_rows, sm_ring, sm_tab, sm_dense, sm_misc, sm_bytes;
+    // per-block global scratch carve-up
+    uint64_t g_word, g_rec, g_pool, g_stride;
+};
+
+static inline int lcv_eligible(const LcCoderCfg &c)
+{
+    return c.mode == LC_MODE_REPAIRED && c.has_ctx && c.n >= 8 && c.n <= LCV_MAX_N && c.C >= 4 && c.C <= LCV_MAX_C;
+}
+
+static inline void lcv_cfg_make(const LcCoderCfg &c, LcV2Cfg *v)
+{
+    v->nkeys = (uint32_t)(c.n + 1) * (uint32_t)(c.n + 1);
+    v->lg_n = 0;
+    while ((1 << v->lg_n) < c.n) v->lg_n++;
+    v->eps_k = (uint32_t)(1e-10 * (double)c.n * 1099511627776.0);
+    v->pool_bytes = c.pool_bytes;
+    uint32_t off = 0;
+    v->sm_bits = off;  off += lc_round_up((v->nkeys + 15) / 16 * 4, 16);
+    v->sm_rows = off;  off += lc_round_up((uint32_t)c.C * 2, 16);
+    v->sm_ring = off;  off += LCV_RING * 8 + LCV_RING * 12; // posted-barriers[32] (8 B) | key[32] | payload[32] | done[32]
+    v->sm_tab = off;   off += 2 * 32 * 8;              // u1tab[32] | ru1tab[32]
+    v->sm_dense = off; off += LCV_NU * (uint32_t)c.n * 8;
+    v->sm_misc = off;  off += 16;                      // pool_top | abort
+    v->sm_bytes = lc_round_up(off, 16);
+    uint64_t g = 0;
+    v->g_word = g; g += ((uint64_t)v->nkeys * 4 + 255) & ~(uint64_t)255;
+    v->g_rec = g;  g += (uint64_t)v->nkeys * 64;
+    v->g_pool = g; g += ((uint64_t)v->pool_bytes + 255) & ~(uint64_t)255;
+    v->g_stride = g;
+}
+
+// per-launch tables (global): u1tab[32] | ru1tab[32] | cum1[n][n+1]
+static inline uint64_t lcv_tables_bytes(int n) { return (uint64_t)(64 + (uint64_t)n * (n + 1)) * 8; }
+
+// "Job posted" signalling: one shared-memory mbarrier per ring slot, one arrival per use of the slot.  A waiting
+// updater warp is suspended by the hardware (mbarrier.try_wait) instead of polling -- in the first version of
+// this kernel the updaters' poll loops were half of all issued instructions and competed with the decoder warps.
+// Use m of a slot (m = job / LCV_RING) completes phase m; waiting for it is a parity wait on (m & 1).  A slot is
+// not reused before its job is finished, so the barrier is never more than one phase ahead of its waiter.
+#ifdef LC_HOSTSIM
+#define LCV_SPIN() emu::spin_yield()
+#define LCV_FENCE() ((void)0)
+static inline uint32_t lcv_ld_vol(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+static inline void lcv_st_vol(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+static inline void lcv_bar_init(unsigned long long *b) { *(volatile unsigned long long *)b = 0ull; } // completed phases
+static inline void lcv_bar_arrive(unsigned long long *b) { *(volatile unsigned long long *)b += 1ull; }
+static inline void lcv_bar_wait(unsigned long long *b, uint32_t parity)
+{
+    while (((uint32_t)*(volatile unsigned long long *)b & 1u) == parity) emu::spin_yield();
+}
+#else
+#define LCV_SPIN() __nanosleep(32)
+#define LCV_FENCE() __threadfence_block()
+static __device__ __forceinline__ uint32_t lcv_ld_vol(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+static __device__ __forceinline__ void lcv_st_vol(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+static __device__ __forceinline__ void lcv_bar_init(unsigned long long *b)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+static __device__ __forceinline__ void lcv_bar_arrive(unsigned long long *b) // release.cta
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+static __device__ __forceinline__ void lcv_bar_wait(unsigned long long *b, uint32_t parity) // acquire.cta
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LCV_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LCV_DONE;\n"
+        "bra LCV_WAIT;\n"
+        "LCV_DONE:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+}
+#endif
+
+// ---- tables kernel body: u after the first update per chain step, its reciprocal, and the exact
+// np.cumsum (:346-347) of the model after one update with s1, for every s1.  One block.
+__device__ __forceinline__ void lcv_tables_block(const LcCoderCfg &cfg, double *tables, char *smem)
+{
+    double *u1g = tables, *ru1g = tables + 32, *cum1 = tables + 64;
+    const int n = cfg.n;
+    if (threadIdx.x < 32) {
+        LcFast F;
+        F.n = n; F.lane = (int)threadIdx.x; F.rate = cfg.rate; F.u0 = LC_DDIV(1.0, (double)n);
+        F.pw_len = cfg.pw_len; F.pw_steps = cfg.pw_steps; F.pw_chains = cfg.pw_chains;
+        F.dense = (double *)smem; F.u1tab = (double *)smem + n;
+        lcf_tables_init(F);
+        const int entries = F.pw_chains == 0 ? n : F.pw_steps;
+        if (F.lane < entries) { u1g[F.lane] = F.u1tab[F.lane]; ru1g[F.lane] = lc_rcp_fast(F.u1tab[F.lane]); }
+    }
+    __syncthreads();
+    const double u0 = LC_DDIV(1.0, (double)n);
+    const double P1 = LC_DADD(u0, LC_DMUL(cfg.rate, LC_DSUB(1.0, u0)));
+    const double *u1s = (const double *)smem + n;
+    for (int s1 = (int)threadIdx.x; s1 < n; s1 += (int)blockDim.x) {
+        const double u = u1s[cfg.pw_chains == 0 ? s1 : ((s1 & (cfg.pw_len - 1)) >> 3)];
+        double *row = cum1 + (size_t)s1 * (n + 1);
+        double T = 0.0;
+        row[0] = 0.0;
+        for (int i = 0; i < n; i++) { T = LC_DADD(T, i == s1 ? P1 : u); row[i + 1] = T; }
+    }
+}
+
+// ---- warp-uniform bit reader: 64-bit window, the next word always already loaded
+struct LcvBits {
+    const uint32_t *w;
+    uint32_t nbytes; // a stream is at most 2^22 symbols of at most ~80 bits
+    unsigned long long win;
+    int nwin;
+    uint32_t widx;
+    uint32_t nextw;
+};
+__device__ __forceinline__ uint32_t lcv_br_word(const LcvBits &b, uint32_t wi)
+{
+    const uint32_t byte0 = wi * 4u;
+    if (byte0 >= b.nbytes) return 0u; // the reference reads zeros past the end (:260-270)
+    uint32_t w = __byte_perm(__ldg(b.w + wi), 0, 0x0123);
+    const uint32_t rem = b.nbytes - byte0;
+    if (rem < 4u) w &= 0xffffffffu << (8u * (4u - rem));
+    return w;
+}
+__device__ __forceinline__ void lcv_br_init(LcvBits &b, const unsigned char *src, long long nbytes)
+{
+    b.w = (const uint32_t *)src; b.nbytes = (uint32_t)(nbytes > 0x7fffffffll ? 0x7fffffffll : nbytes);
+    b.win = ((unsigned long long)lcv_br_word(b, 0) << 32) | lcv_br_word(b, 1);
+    b.nwin = 64; b.widx = 2; b.nextw = lcv_br_word(b, 2);
+}
+// next nb bits (1..32), MSB first
+__device__ __forceinline__ uint32_t lcv_br_take(LcvBits &b, int nb)
+{
+    const uint32_t v = (uint32_t)(b.win >> (64 - nb));
+    b.win <<= nb;
+    b.nwin -= nb;
+    if (b.nwin <= 32) {
+        b.win |= (unsigned long long)b.nextw << (32 - b.nwin);
+        b.nwin += 32;
+        b.widx++;
+        b.nextw = lcv_br_word(b, b.widx);
+    }
+    return v;
+}
+
+// ---- shared/global views of one block
+struct LcV2 {
+    uint32_t *sbits;          // 2-bit context states
+    unsigned char *rows;      // previous/current row of decoded symbols
+    unsigned long long *ring_bar; // "job posted" barrier per ring slot
+    uint32_t *ring_key, *ring_pay, *ring_done;
+    double *u1tab, *ru1tab;
+    uint32_t *pool_top, *abort_code;
+    uint32_t *gword;          // per context: first symbol (state 1) or K|offset of the pool record (state 3)
+    char *grec;               // per context: 64-byte inline record  u | val[6] | sym[6] k pad
+    char *pool;
+    const double *cum1;
+    uint32_t pool_bytes, eps_k, lg_n;
+};
+
+#define LCV_PAY(s, st, s1) ((uint32_t)(s) | ((uint32_t)(st) << 10) | ((uint32_t)(s1) << 12))
+#define LCV_PAY_S(w) ((int)((w) & 0x3FFu))
+#define LCV_PAY_ST(w) ((int)(((w) >> 10) & 3u))
+#define LCV_PAY_S1(w) ((int)(((w) >> 12) & 0x3FFu))
+#define LCV_WORD_C(k, off16) ((uint32_t)(k) | ((uint32_t)(off16) << 6))
+#define LCV_WORD_K(w) ((int)((w) & 0x3Fu))
+#define LCV_WORD_OFF(w) ((uint32_t)(w) >> 6)
+
+// lane-distributed register model (LcFast) from a pool record
+__device__ __forceinline__ void lcv_load_pool(LcFast &F, const LcV2 &V, uint32_t word)
+{
+    F.k = LCV_WORD_K(word);
+    if (F.k > 32) F.k = 32; // only reachable on a stream already flagged for the generic kernel
+    const char *rec = V.pool + (size_t)LCV_WORD_OFF(word) * 16;
+    int cl = 1; while ((1 << cl) < F.k) cl++;
+    F.u = __ldcg((const double *)rec);
+    const bool valid = F.lane < F.k;
+    F.my_val = valid ? __ldcg((const double *)(rec + 8) + F.lane) : 0.0;
+    F.my_sym = valid ? (int)__ldcg((const unsigned short *)(rec + 8 + (8 << cl)) + F.lane) : 0x7fffffff;
+}
+
+// lane-distributed register model from an inline record
+__device__ __forceinline__ void lcv_load_inline(LcFast &F, const LcV2 &V, uint32_t key)
+{
+    const char *rec = V.grec + (size_t)key * 64;
+    int k = (int)__ldcg((const unsigned char *)rec + 62);
+    if (k > LCV_INLINE_K) k = LCV_INLINE_K;
+    F.k = k;
+    F.u = __ldcg((const double *)rec);
+    const bool valid = F.lane < k;
+    F.my_val = valid ? __ldcg((const double *)(rec + 8) + F.lane) : 0.0;
+    F.my_sym = valid ? (int)__ldcg((const unsigned char *)rec + 56 + F.lane) : 0x7fffffff;
+}
+
+// =================================================================================================
+// UPDATER warps
+// =================================================================================================
+// j: this warp's next job (jobs are numbered through all streams of the block; warp u takes j = u mod LCV_NU)
+__device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &j)
+{
+    for (;; j += LCV_NU) {
+        const uint32_t slot = j & (LCV_RING - 1);
+        lcv_bar_wait(V.ring_bar + slot, (j / LCV_RING) & 1u);
+        const uint32_t key = lcv_ld_vol(V.ring_key + slot);
+        const uint32_t pay = lcv_ld_vol(V.ring_pay + slot);
+        if (key == LCV_SENTINEL) {
+            __syncwarp();
+            if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+            j += LCV_NU;
+            break;
+        }
+        if (lcv_ld_vol(V.abort_code) == 0u) {
+            const int s = LCV_PAY_S(pay), st = LCV_PAY_ST(pay);
+            const uint32_t shift = (key & 15u) * 2u;
+            uint32_t word = 0u;
+            if (st == 1) lcf_state_first(F, LCV_PAY_S1(pay));
+            else if (st == 2) lcv_load_inline(F, V, key);
+            else { word = __ldcg(V.gword + key); lcv_load_pool(F, V, word); }
+            const int k_old = F.k;
+            if (!lcf_update(F, s)) {
+                if (F.lane == 0) atomicCAS(V.abort_code, 0u, (uint32_t)LC_NEEDS_GENERIC);
+            } else if (F.k <= LCV_INLINE_K) {
+                char *rec = V.grec + (size_t)key * 64;
+                if (F.lane == 0) { __stcg((double *)rec, F.u); __stcg((unsigned char *)rec + 62, (unsigned char)F.k); }
+                if (F.lane < F.k) {
+                    __stcg((double *)(rec + 8) + F.lane, F.my_val);
+                    __stcg((unsigned char *)rec + 56 + F.lane, (unsigned char)F.my_sym);
+                }
+                LCV_FENCE();
+                if (st == 1 && F.lane == 0) atomicXor(V.sbits + (key >> 4), 3u << shift); // 01 -> 10
+            } else {
+                int cl = 1; while ((1 << cl) < F.k) cl++;
+                uint32_t off16 = LCV_WORD_OFF(word);
+                bool alloc = st != 3;
+                if (st == 3) { int clo_ = 1; while ((1 << clo_) < k_old) clo_++; alloc = cl != clo_; }
+                bool ok = true;
+                if (alloc) {
+                    const uint32_t bytes = (8u + (10u << cl) + 15u) & ~15u;
+                    uint32_t top = 0u;
+                    if (F.lane == 0) top = atomicAdd(V.pool_top, bytes);
+                    top = __shfl_sync(LC_FULL_MASK, top, 0);
+                    if (top + bytes > V.pool_bytes) {
+                        ok = false;
+                        if (F.lane == 0) atomicCAS(V.abort_code, 0u, (uint32_t)LC_POOL_OVERFLOW);
+                    }
+                    off16 = top >> 4;
+                }
+                if (ok) {
+                    char *rec = V.pool + (size_t)off16 * 16;
+                    if (F.lane == 0) __stcg((double *)rec, F.u);
+                    if (F.lane < F.k) {
+                        __stcg((double *)(rec + 8) + F.lane, F.my_val);
+                        __stcg((unsigned short *)(rec + 8 + (8 << cl)) + F.lane, (unsigned short)F.my_sym);
+                    }
+                    if (F.lane == 0) __stcg(V.gword + key, LCV_WORD_C(F.k, off16));
+                    LCV_FENCE();
+                    if (st != 3 && F.lane == 0) atomicXor(V.sbits + (key >> 4), (uint32_t)(st ^ 3) << shift);
+                }
+            }
+        }
+        __syncwarp();
+        LCV_FENCE();
+        if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+    }
+}
+
+// =================================================================================================
+// DECODER warp
+// =================================================================================================
+struct LcvPost {
+    uint32_t njobs;      // jobs posted so far in this stream
+    uint32_t my_key;     // lane l: key of the last job posted into ring slot l
+    uint32_t my_job;     // ... and its index
+};
+
+__device__ __forceinline__ void lcv_post(const LcV2 &V, LcvPost &P, int lane, uint32_t key, uint32_t pay)
+{
+    const uint32_t j = P.njobs, slot = j & (LCV_RING - 1);
+    if (j >= LCV_RING) { // the job that used this slot must be finished before the slot is reused
+        while (lcv_ld_vol(V.ring_done + slot) != j - LCV_RING + 1u) LCV_SPIN();
+        LCV_FENCE();
+    }
+    if (lane == 0) {
+        lcv_st_vol(V.ring_key + slot, key); lcv_st_vol(V.ring_pay + slot, pay);
+        lcv_bar_arrive(V.ring_bar + slot);
+    }
+    if ((uint32_t)lane == slot) { P.my_key = key; P.my_job = j; }
+    P.njobs = j + 1u;
+}
+
+// approximate symbol search in a gap of never-observed symbols (see lcf_gap_search), reciprocal supplied
+__device__ __forceinline__ bool lcv_gap_search(double u, double ru, double dv, double v, double gbase, int gfirst,
+                                               int glen, LcInterval &out)
+{
+    if (glen <= 0) return false;
+    const double d = v - gbase;
+    if (!(d > dv)) return false;
+    const double t = d * ru; // any error only makes the margin tests below fail
+    if (!(t < (double)glen)) return false;
+    const int m = (int)t;
+    const double lo = gbase + (double)m * u;
+    const double hi = gbase + (double)(m + 1) * u;
+    if (!(v - lo > dv) || !(hi - v >= dv)) return false;
+    out.sym = gfirst + m; out.clo = lo; out.chi = hi; out.exact = 0;
+    return true;
+}
+
+// issue the global loads the next visit of context `key` needs (state st): the 4-byte word (states 1, 3) or the
+// inline record (state 2).  Only called when no job on that context can still be running.
+#define LCV_PREFETCH(st_, key_, gw_, q0_, q1_, q2_, q3_)                                   \
+    do {                                                                                    \
+        if ((st_) == 2) {                                                                   \
+            const double2 *q_ = (const double2 *)(V.grec + (size_t)(key_) * 64);            \
+            q0_ = __ldcg(q_); q1_ = __ldcg(q_ + 1); q2_ = __ldcg(q_ + 2); q3_ = __ldcg(q_ + 3); \
+        } else if ((st_) != 0) gw_ = __ldcg(V.gword + (key_));                              \
+    } while (0)
+
+// write decoded symbols [first, first+count) of the row held in shared memory (and their dequantised values)
+__device__ __forceinline__ void lcv_flush_row(const unsigned char *row, int first_col, int count, int *out,
+                                              const float *deq_table, float *deq_out, int lane)
+{
+    for (int i = lane; i < count; i += 32) {
+        const int sy = (int)row[first_col + i];
+        out[i] = sy;
+        if (deq_out) deq_out[i] = __ldg(deq_table + sy);
+    }
+}
+
+__device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvPost &P, const unsigned char *src,
+                                                  long long nbytes, int *out, const float *deq_table, float *deq_out,
+                                                  int *status_out, int *fault_index)
+{
+    const int lane = F.lane, n = F.n, C = F.C;
+    LcvBits br; lcv_br_init(br, src, nbytes);
+    uint32_t lo = 0u, hi = 0xffffffffu;
+    uint32_t code = lcv_br_take(br, 32); // start_decoding (:247-258)
+    int status = LC_OK;
+    int pos = 0, r = 0, c = 0;
+    uint32_t key = 0u; // (left=-1, up=-1)
+    int st = 0;        // its state; the data the state needs is requested one symbol ahead:
+    uint32_t gw = 0u;  //   states 1, 3: the context's 4-byte word
+    double2 q0 = {0.0, 0.0}, q1 = q0, q2 = q0, q3 = q0; // state 2: the inline record  u | val[6] | sym[6] k
+    P.my_key = LCV_SENTINEL; // contexts of the previous stream are not this stream's
+    const double cfix = 1e-10;
+    LCP_DECL
+    LCP_INIT();
+    for (; pos < F.total; pos++) {
+        LCP_START();
+        LCP_ROW(st); LCP_COUNT(st, 0);
+        const uint32_t shift = (key & 15u) * 2u;
+        // ---- decode_symbol (:272-292)
+        const uint32_t rng1 = hi - lo, off = code - lo; // range-1, (code-low+1)-1
+        const bool pre_ok = hi >= lo && off <= rng1 && rng1 >= 0xffffu;
+        int s = 0, s1 = 0;
+        uint32_t nlo = 0u, nhi = 0u;
+        bool done = false;
+        if (st == 0) {
+            if (pre_ok) {
+                // uniform model: cum[i] = i/n exactly, so range*cum is exact and everything is integer work.
+                // With a = (code-low+1)*n and E = 1e-10*n*range, the symbol is the s with
+                // s*range < a - E (+- 3e-4) <= (s+1)*range; candidate from a float quotient, checked with margins.
+                const int cand = (int)(__fdividef((float)off, (float)rng1) * (float)n);
+                const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
+                const unsigned long long above = below + rng1 + 1ull;
+                const unsigned long long a = ((unsigned long long)off + 1ull) << V.lg_n;
+                const unsigned long long e_lo = (unsigned long long)(__umulhi(rng1, V.eps_k) >> 8); // <= E < e_lo + 3
+                if (cand >= 0 && cand < n && below + e_lo + 4ull <= a && a + 1ull <= above + e_lo) {
+                    s = cand; done = true;
+                    nlo = lo + (uint32_t)(below >> V.lg_n);
+                    nhi = lo + (uint32_t)(above >> V.lg_n) - 1u;
+                }
+            }
+        } else if (st == 1) {
+            s1 = (int)(gw & 0x3FFu);
+            if (s1 >= n) s1 = n - 1; // only on a stream already flagged for the generic kernel
+            if (pre_ok) { // model after one update: exact np.cumsum values from the per-launch table
+                const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
+                const int t = lcf_tab_index(F, s1);
+                const double u = V.u1tab[t], ru = V.ru1tab[t];
+                const double va = nd * lc_rcp_fast(rd) - cfix;
+                const double A0 = (double)s1 * u, B0 = A0 + F.P1;
+                int sc;
+                if (va < A0) sc = (int)(va * ru);
+                else if (va <= B0) sc = s1;
+                else sc = s1 + 1 + (int)((va - B0) * ru);
+                sc = sc < 0 ? 0 : (sc > n - 1 ? n - 1 : sc);
+                const double *row = V.cum1 + (size_t)s1 * (n + 1);
+                const double clo = __ldg(row + sc), chi = __ldg(row + sc + 1);
+                const double xl = LC_DMUL(rd, clo), xh1 = LC_DMUL(rd, chi);
+                const double tgt = nd - cfix * rd; // ~ v*range; |error| < 3e-6 for range <= 2^32
+                if (tgt - xl > 1e-5 && xh1 - tgt >= 1e-5) { // cum[sc] < v <= cum[sc+1], decided with margin
+                    s = sc; done = true;
+                    nlo = lo + (uint32_t)LC_D2LL(xl);
+                    nhi = lo + (uint32_t)LC_D2LL(LC_DSUB(xh1, 1.0));
+                }
+            }
+        } else if (st == 2) {
+            const double u = q0.x;
+            const unsigned long long sb = (unsigned long long)__double_as_longlong(q3.y);
+            int k = (int)((sb >> 48) & 0xffu);
+            if (k > LCV_INLINE_K) k = LCV_INLINE_K;
+            double val[LCV_INLINE_K] = {q0.y, q1.x, q1.y, q2.x, q2.y, q3.x};
+            int sym[LCV_INLINE_K];
+#pragma unroll
+            for (int j = 0; j < LCV_INLINE_K; j++) sym[j] = (int)((sb >> (8 * j)) & 0xffu);
+            bool decided = false;
+            LcInterval iv; iv.sym = 0; iv.clo = 0.0; iv.chi = 0.0; iv.exact = 0;
+            const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
+            if (pre_ok) {
+                const double ru = lc_rcp_fast(u);
+                const double va = nd * lc_rcp_fast(rd) - cfix;
+                // approximate cum before (A) and after (Bv) every entry
+                double A[LCV_INLINE_K], Bv[LCV_INLINE_K];
+                double S = 0.0, Bk = 0.0; // Bk/g0: end of the last valid entry (start of the tail gap)
+                int g0 = 0;
+#pragma unroll
+                for (int j = 0; j < LCV_INLINE_K; j++) {
+                    A[j] = (double)(sym[j] - j) * u + S;
+                    S += val[j];
+                    Bv[j] = A[j] + val[j];
+                    if (j < k) { Bk = Bv[j]; g0 = sym[j] + 1; }
+                }
+                // first entry whose upper bound reaches v (descending scan: the last assignment wins)
+                int l = k;
+                double Al = 0.0, Bl = 0.0, Bp = 0.0;
+                int sl = 0, gf = 0;
+#pragma unroll
+                for (int j = LCV_INLINE_K - 1; j >= 0; j--) {
+                    if (j < k && Bv[j] >= va) {
+                        l = j; Al = A[j]; Bl = Bv[j]; sl = sym[j];
+                        Bp = j > 0 ? Bv[j > 0 ? j - 1 : 0] : 0.0;
+                        gf = j > 0 ? sym[j > 0 ? j - 1 : 0] + 1 : 0;
+                    }
+                }
+                if (l < k) {
+                    if (va - Al > F.delta_v) {
+                        if (Bl - va >= F.delta_v) { iv.sym = sl; iv.clo = Al; iv.chi = Bl; decided = true; }
+                    } else if (Al - va >= F.delta_v) {
+                        decided = lcv_gap_search(u, ru, F.delta_v, va, Bp, gf, sl - gf, iv);
+                    }
+                } else {
+                    decided = lcv_gap_search(u, ru, F.delta_v, va, Bk, g0, n - g0, iv);
+                }
+            }
+            // lane-distributed copy of the record for the exact paths
+            F.k = k; F.u = u; F.my_sym = 0x7fffffff; F.my_val = 0.0;
+#pragma unroll
+            for (int j = 0; j < LCV_INLINE_K; j++) if (lane == j && j < k) { F.my_sym = sym[j]; F.my_val = val[j]; }
+            if (decided) {
+                lcf_apply_symbol(F, iv, nd, rd, lo, hi);
+                nlo = lo; nhi = hi; s = iv.sym; done = true;
+            }
+        } else {
+            lcv_load_pool(F, V, gw);
+        }
+        if (!done) { // exact evaluation shared with the other kernels
+            LCP_COUNT(4, st);
+            if (st == 1) lcf_state_first(F, s1);
+            LcInterval iv;
+            double num, rdv;
+            const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
+            if (fs != LC_OK) { status = fs; break; }
+            lcf_apply_symbol(F, iv, num, rdv, lo, hi);
+            nlo = lo; nhi = hi; s = iv.sym;
+        }
+        lo = nlo; hi = nhi;
+        LCP_MARK(1);
+        // ---- next position's context (get_context :78-117): its state, and the data that state needs
+        if (lane == 0) V.rows[(r & 1) * C + c] = (unsigned char)s;
+        int c2 = c + 1, r2 = r;
+        if (c2 == C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
+        // (the row above was written at least C-1 >= 3 symbols ago and ordered by the __syncwarp() below)
+        const int up2 = r2 > 0 ? (int)V.rows[((r2 - 1) & 1) * C + c2] : -1;
+        const uint32_t key2 = (uint32_t)((c2 > 0 ? s : -1) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);
+        const uint32_t shift2 = (key2 & 15u) * 2u;
+        int st2 = (int)((lcv_ld_vol(V.sbits + (key2 >> 4)) >> shift2) & 3u);
+        uint32_t gw2 = 0u;
+        double2 p0 = {0.0, 0.0}, p1 = p0, p2 = p0, p3 = p0;
+        bool pend2 = key2 == key; // this symbol's own update of the same context comes first
+        if (st2 != 0 && !pend2) {
+            // a job on that context among the last LCV_RING posted ones may still be running
+            pend2 = __ballot_sync(LC_FULL_MASK, P.my_key == key2) != 0u;
+            if (!pend2) LCV_PREFETCH(st2, key2, gw2, p0, p1, p2, p3);
+        }
+        // ---- renormalise (:295-303) and underflow (:306-309): closed form, one read of d+e bits
+        {
+            const int d = __clz((int)(lo ^ hi)); // leading bits low and high share
+            const uint32_t lo_d = (uint32_t)((unsigned long long)lo << d);
+            const uint32_t hi_d = ~(uint32_t)((unsigned long long)(~hi) << d);
+            const int e = __clz((int)~((lo_d & ~hi_d) << 1)); // underflow steps: low = 01.., high = 10..
+            const int t = d + e;
+            if (t) {
+                if (t <= 32) {
+                    const uint32_t bits = lcv_br_take(br, t);
+                    code = (uint32_t)((unsigned long long)code << t) | bits;
+                } else {
+                    const uint32_t b1 = lcv_br_take(br, d);
+                    code = (uint32_t)((unsigned long long)code << d) | b1;
+                    const uint32_t b2 = lcv_br_take(br, e);
+                    code = (code << e) | b2;
+                }
+                lo = (uint32_t)((unsigned long long)lo_d << e);
+                hi = ~(uint32_t)((unsigned long long)(~hi_d) << e);
+                if (e) { lo &= 0x7fffffffu; hi |= 0x80000000u; code ^= 0x80000000u; }
+            }
+        }
+        LCP_MARK(2);
+        // ---- this context's model moves on
+        if (st == 0) {
+            if (lane == 0) { __stcg(V.gword + key, (uint32_t)s); atomicOr(V.sbits + (key >> 4), 1u << shift); }
+        } else {
+            lcv_post(V, P, lane, key, LCV_PAY(s, st, s1));
+        }
+        __syncwarp(); // lane 0's writes (row, word, state bits) are ordered before the other lanes' next reads
+        if (c2 == 0) { // a row is complete: write it out
+            lcv_flush_row(V.rows + (r & 1) * C, 0, C, out + (pos - (C - 1)), deq_table,
+                          deq_out ? deq_out + (pos - (C - 1)) : (float *)0, lane);
+            const uint32_t ab = lcv_ld_vol(V.abort_code);
+            if (ab) { status = (int)ab; pos++; c = C; break; }
+        }
+        if (pend2) {
+            LCP_COUNT(6, st2);
+            const bool mine = P.my_key == key2;
+            if (mine) while (lcv_ld_vol(V.ring_done + lane) != P.my_job + 1u) LCV_SPIN();
+            __syncwarp();
+            LCV_FENCE();
+            st2 = (int)((lcv_ld_vol(V.sbits + (key2 >> 4)) >> shift2) & 3u);
+            LCV_PREFETCH(st2, key2, gw2, p0, p1, p2, p3);
+        }
+        key = key2; c = c2; r = r2; st = st2; gw = gw2; q0 = p0; q1 = p1; q2 = p2; q3 = p3;
+        LCP_MARK(3);
+    }
+    LCP_FLUSH();
+    // release the updaters
+    for (int u = 0; u < LCV_NU; u++) lcv_post(V, P, lane, LCV_SENTINEL, 0u);
+    *fault_index = pos;
+    *status_out = status;
+    __syncwarp();
+    {
+        // symbols of the unfinished row (c of them; none when the stream ended on a row boundary), zeros after a fault
+        const int done = pos;
+        const int part = (c < C) ? c : 0;
+        if (part > 0) lcv_flush_row(V.rows + (r & 1) * C, 0, part, out + (done - part), deq_table,
+                                    deq_out ? deq_out + (done - part) : (float *)0, lane);
+        for (int z = done + lane; z < F.total; z += 32) { out[z] = 0; if (deq_out) deq_out[z] = 0.0f; }
+    }
+}
+
+// Block entry: LCV_WARPS warps, persistent over streams.
+__device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const LcV2Cfg &vc, const unsigned char *bytes,
+                                                 const long long *offsets, const int *nbits, int B, int *out,
+                                                 const float *deq_table, float *deq_out, int *status, int *fault,
+                                                 char *scratch, const double *tables, char *smem)
+{
+    const int warp = (int)(threadIdx.x >> 5);
+    LcV2 V;
+    V.sbits = (uint32_t *)(smem + vc.sm_bits);
+    V.rows = (unsigned char *)(smem + vc.sm_rows);
+    V.ring_bar = (unsigned long long *)(smem + vc.sm_ring);
+    V.ring_key = (uint32_t *)(V.ring_bar + LCV_RING);
+    V.ring_pay = V.ring_key + LCV_RING; V.ring_done = V.ring_pay + LCV_RING;
+    V.u1tab = (double *)(smem + vc.sm_tab); V.ru1tab = V.u1tab + 32;
+    V.pool_top = (uint32_t *)(smem + vc.sm_misc); V.abort_code = V.pool_top + 1;
+    char *sc = scratch + (size_t)blockIdx.x * vc.g_stride;
+    V.gword = (uint32_t *)(sc + vc.g_word); V.grec = sc + vc.g_rec; V.pool = sc + vc.g_pool;
+    V.cum1 = tables + 64;
+    V.pool_bytes = vc.pool_bytes; V.eps_k = vc.eps_k; V.lg_n = vc.lg_n;
+    LcFast F;
+    F.n = cfg.n; F.C = cfg.C; F.R = cfg.R; F.total = cfg.total; F.lane = (int)(threadIdx.x & 31);
+    F.rate = cfg.rate; F.delta = cfg.delta; F.u0 = LC_DDIV(1.0, (double)cfg.n);
+    F.delta_v = cfg.delta + 1.5e-14; F.tmargin = (double)cfg.n * 1.5e-14;
+    F.P1 = LC_DADD(F.u0, LC_DMUL(F.rate, LC_DSUB(1.0, F.u0)));
+    F.slot_cap = 0; F.slot_shift = 0; F.pool_bytes = vc.pool_bytes; F.pool_top = 0;
+    F.pw_len = cfg.pw_len; F.pw_steps = cfg.pw_steps; F.pw_chains = cfg.pw_chains;
+    F.slots = (unsigned long long *)0; F.pool = V.pool;
+    F.dense = (double *)(smem + vc.sm_dense) + (size_t)(warp > 0 ? warp - 1 : 0) * cfg.n;
+    F.u1tab = V.u1tab; F.rows = (unsigned short *)0;
+    F.k = 0; F.u = F.u0; F.my_sym = 0x7fffffff; F.my_val = 0.0;
+    if (threadIdx.x < 64) V.u1tab[threadIdx.x] = tables[threadIdx.x];
+    if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = 0u; }
+    LcvPost P; P.njobs = 0u; P.my_key = LCV_SENTINEL; P.my_job = 0u;
+    uint32_t ujob = (uint32_t)(warp > 0 ? warp - 1 : 0);
+    const uint32_t nwords = (vc.nkeys + 15u) / 16u;
+    for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
+        __syncthreads(); // the previous stream is finished by every warp
+        for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) V.sbits[i] = 0u;
+        if (threadIdx.x == 0) { *V.pool_top = 0u; *V.abort_code = 0u; }
+        __syncthreads();
+        if (warp == 0) {
+            int fi = 0, st = 0;
+            const long long nby = ((long long)nbits[sidx] + 7) >> 3;
+            lcv_decode_stream(F, V, P, bytes + offsets[sidx], nby, out + (size_t)sidx * cfg.total, deq_table,
+                              deq_out ? deq_out + (size_t)sidx * cfg.total : (float *)0, &st, &fi);
+            if (F.lane == 0) { status[sidx] = st; fault[sidx] = fi; }
+        } else {
+            lcv_updater(F, V, ujob);
+        }
+    }
+}

@@ -12,7 +12,8 @@ SRCS = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "cuda_emul.h"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_coder.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_common.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_par.cuh"),
-        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_fast.cuh")]
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_fast.cuh"),
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v2.cuh")]
 _lib = None
 
 
@@ -61,7 +62,8 @@ def encode(codes, n, mode=1, rate=0.05, slot_bytes=None, grid=None):
 
 def decode(streams, n, shape, mode=1, rate=0.05, grid=None, codebook=None, fast=False):
     """streams: list of bytes objects, one per stream; shape: per-batch shape as for encode().
-    fast=True: the fast decoder kernel + generic redo pass (repaired mode, 3-D shapes only)."""
+    fast=True: the fast decoder kernel + generic redo pass (repaired mode, 3-D shapes only);
+    fast="v2": decoder v2 (decoder warp + updater warps) + generic redo pass."""
     B, imgs, R, C, has_ctx = _shape(shape)
     assert len(streams) == B
     total = imgs * R * C
@@ -88,7 +90,8 @@ def decode(streams, n, shape, mode=1, rate=0.05, grid=None, codebook=None, fast=
     if fast:
         assert mode == 1 and has_ctx
         redone = ctypes.c_int(0)
-        rc = lib().hostsim_decode_fast(_p(blob, ctypes.c_ubyte), _p(offs, ctypes.c_longlong), _p(nbits, ctypes.c_int), B,
+        fn = lib().hostsim_decode_v2 if fast == "v2" else lib().hostsim_decode_fast
+        rc = fn(_p(blob, ctypes.c_ubyte), _p(offs, ctypes.c_longlong), _p(nbits, ctypes.c_int), B,
                                        imgs, R, C, int(n), ctypes.c_double(rate), _p(out, ctypes.c_int), cbp, deqp,
                                        _p(status, ctypes.c_int), _p(fault, ctypes.c_int), grid, ctypes.byref(redone))
         assert rc == 0, rc

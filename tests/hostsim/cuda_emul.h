@@ -6,8 +6,10 @@
  * One warp = 32 coroutines (hand-rolled x86-64 stack switch) scheduled round-robin on one OS
  * thread.  Warp collectives (__shfl*_sync, __ballot_sync, __syncwarp) are rendezvous points; the
  * emulator aborts if the 32 lanes do not all reach the SAME collective call site (divergence bug)
- * or if a lane exits while others wait.  Blocks may have several warps as long as the warps do
- * not synchronise with one another (they are then run one after the other).
+ * or if a lane exits while others wait.  run_warp() runs one warp to completion (blocks whose warps
+ * do not synchronise with one another are run warp after warp); run_block() schedules all warps of
+ * a block round-robin so that they can hand work to one another through shared memory: spin loops
+ * call spin_yield(), __syncthreads() is a real block barrier there.
  */
 #pragma once
 #include <cmath>
@@ -49,6 +51,9 @@ struct Warp {
 
 extern Warp *g_warp;
 
+struct Block { int nwarps; int arrived; uint64_t gen; uint64_t events; };
+extern Block *g_block; /* non-null while run_block() is scheduling cooperating warps */
+
 extern "C" void emu_switch(void **save_sp, void *load_sp);
 
 inline Dim tid() { return Dim{g_warp->warp * 32u + (unsigned)g_warp->cur, 0, 0}; }
@@ -86,6 +91,19 @@ inline uint64_t rendezvous(int site) {
         while (w->gen == g) yield_to_main();
     }
     return g;
+}
+
+/* a lane waiting in a spin loop for another warp: give the other lanes and warps a turn */
+inline void spin_yield() { yield_to_main(); }
+
+/* __syncthreads(): a block barrier under run_block(), a warp rendezvous under run_warp() */
+inline void block_barrier(int site) {
+    Block *b = g_block;
+    if (!b) { (void)rendezvous(site); return; }
+    const uint64_t g = b->gen;
+    b->events++;
+    if (++b->arrived == 32 * b->nwarps) { b->arrived = 0; b->gen = g + 1; }
+    else while (b->gen == g) yield_to_main();
 }
 
 template <typename T> inline uint64_t to_bits(T v) {
@@ -134,6 +152,7 @@ inline unsigned ballot(int pred, int site) {
 }
 
 void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned warp = 0, unsigned nwarps = 1);
+void run_block(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned nwarps);
 
 } // namespace emu
 
@@ -148,7 +167,7 @@ void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsi
 #define __shfl_down_sync(mask, v, delta) emu::shfl_down((v), (delta), __LINE__)
 #define __ballot_sync(mask, pred) emu::ballot((pred), __LINE__)
 #define __syncwarp() ((void)emu::rendezvous(__LINE__))
-#define __syncthreads() ((void)emu::rendezvous(__LINE__))
+#define __syncthreads() (emu::block_barrier(__LINE__))
 
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
@@ -172,6 +191,13 @@ static inline long long __double2ll_rz(double a) { return (long long)a; }
 static inline double __ll2double_rn(long long a) { return (double)a; }
 static inline double __int2double_rn(int a) { return (double)a; }
 static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p = o + v; return o; }
+static inline unsigned int atomicOr(unsigned int *p, unsigned int v) { unsigned int o = *p; *p = o | v; return o; }
+static inline unsigned int atomicXor(unsigned int *p, unsigned int v) { unsigned int o = *p; *p = o ^ v; return o; }
+static inline unsigned int atomicCAS(unsigned int *p, unsigned int c, unsigned int v) { unsigned int o = *p; if (o == c) *p = v; return o; }
+struct double2 { double x, y; };
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((uint64_t)a * b) >> 32); }
+static inline long long __double_as_longlong(double d) { long long b; memcpy(&b, &d, 8); return b; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }
 template <typename T> static inline void __stcg(T *p, T v) { *p = v; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }

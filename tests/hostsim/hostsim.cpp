@@ -11,11 +11,13 @@
 #include "../../image_compression_2_b200/csrc/lc_coder.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_par.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_fast.cuh"
+#include "../../image_compression_2_b200/csrc/lc_decoder_v2.cuh"
 #include <algorithm>
 #include <numeric>
 
 namespace emu {
 Warp *g_warp = nullptr;
+Block *g_block = nullptr;
 
 asm(R"(
 .text
@@ -49,10 +51,9 @@ static void lane_entry()
     abort(); // a finished lane is never resumed
 }
 
-void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned warp, unsigned nwarps)
+static void warp_setup(Warp &w, void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned warp, unsigned nwarps)
 {
     static const size_t STACK = 256 * 1024;
-    Warp w;
     memset(&w, 0, sizeof(w));
     w.fn = fn; w.arg = arg; w.block = block; w.grid = grid; w.warp = warp; w.nwarps = nwarps;
     for (int i = 0; i < 32; i++) {
@@ -64,6 +65,47 @@ void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsi
         for (int r = 0; r < 6; r++) *--sp = 0;
         w.lane_sp[i] = sp;
     }
+}
+
+// all warps of one block, scheduled round-robin (one turn per lane) so that warps can wait for one another
+void run_block(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned nwarps)
+{
+    std::vector<Warp> ws(nwarps);
+    for (unsigned w = 0; w < nwarps; w++) warp_setup(ws[w], fn, arg, block, grid, w, nwarps);
+    Block blk{(int)nwarps, 0, 0, 0};
+    Warp *saved = g_warp;
+    Block *saved_b = g_block;
+    g_block = &blk;
+    int alive = 32 * (int)nwarps;
+    uint64_t idle = 0;
+    while (alive > 0) {
+        uint64_t sig0 = blk.events + blk.gen;
+        for (unsigned w = 0; w < nwarps; w++) sig0 += ws[w].gen * 64 + (uint64_t)ws[w].arrived;
+        const int alive0 = alive;
+        for (unsigned w = 0; w < nwarps; w++) {
+            g_warp = &ws[w];
+            for (int i = 0; i < 32; i++) {
+                if (ws[w].done[i]) continue;
+                ws[w].cur = i;
+                emu_switch(&ws[w].main_sp, ws[w].lane_sp[i]);
+                if (ws[w].done[i]) alive--;
+            }
+        }
+        uint64_t sig1 = blk.events + blk.gen;
+        for (unsigned w = 0; w < nwarps; w++) sig1 += ws[w].gen * 64 + (uint64_t)ws[w].arrived;
+        if (sig1 == sig0 && alive == alive0) { if (++idle > 200000) die("run_block: no progress (deadlock between warps?)", -1); }
+        else idle = 0;
+    }
+    g_warp = saved;
+    g_block = saved_b;
+    for (unsigned w = 0; w < nwarps; w++)
+        for (int i = 0; i < 32; i++) free(ws[w].lane_stack[i]);
+}
+
+void run_warp(void (*fn)(void *), void *arg, unsigned block, unsigned grid, unsigned warp, unsigned nwarps)
+{
+    Warp w;
+    warp_setup(w, fn, arg, block, grid, warp, nwarps);
     Warp *saved = g_warp;
     g_warp = &w;
     int alive = 32;
@@ -170,6 +212,47 @@ extern "C" int hostsim_decode_fast(const unsigned char *bytes, const long long *
     *n_redone = redo;
     a.only_flagged = LC_NEEDS_GENERIC;
     for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a, (unsigned)b, (unsigned)grid);
+    return 0;
+}
+
+// decoder v2 (decoder warp + updater warps per block) followed by the generic redo pass, as the host does
+struct DecV2Args { DecArgs d; LcV2Cfg vc; double *tables; char *scratch2; };
+static void decv2_tables_body(void *p)
+{
+    DecV2Args *a = (DecV2Args *)p;
+    lcv_tables_block(a->d.cfg, a->tables, a->d.smem);
+}
+static void decv2_body(void *p)
+{
+    DecV2Args *a = (DecV2Args *)p;
+    lcv_decode_block(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table, a->d.deq_out,
+                     a->d.status, a->d.fault, a->scratch2, a->tables, a->d.smem);
+}
+extern "C" int hostsim_decode_v2(const unsigned char *bytes, const long long *offsets, const int *nbits, int B,
+                                 int imgs, int R, int C, int n, double rate, int *out, const float *deq_table,
+                                 float *deq_out, int *status, int *fault, int grid, int *n_redone)
+{
+    DecV2Args a;
+    int rc = make_cfg(a.d.cfg, imgs, R, C, n, rate, LC_MODE_REPAIRED, 1);
+    if (rc) return rc;
+    if (!lcv_eligible(a.d.cfg)) return -22;
+    lcv_cfg_make(a.d.cfg, &a.vc);
+    std::vector<char> scratch((size_t)grid * a.d.cfg.scratch_stride + 256);
+    std::vector<char> scratch2((size_t)grid * a.vc.g_stride + 256, (char)0xAB); // never cleared on the GPU either
+    std::vector<double> tables(lcv_tables_bytes(n) / 8 + 8, -777.0);
+    std::vector<char> smem(std::max((size_t)a.vc.sm_bytes, std::max((size_t)a.d.cfg.sm_bytes, (size_t)(n + 64) * 8)) + 64);
+    a.d.bytes = bytes; a.d.offsets = offsets; a.d.nbits = nbits; a.d.B = B; a.d.out = out; a.d.deq_table = deq_table;
+    a.d.deq_out = deq_out; a.d.status = status; a.d.fault = fault; a.d.scratch = scratch.data(); a.d.only_flagged = 0;
+    a.d.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    a.tables = tables.data();
+    a.scratch2 = (char *)(((uintptr_t)scratch2.data() + 255) & ~(uintptr_t)255);
+    emu::run_block(decv2_tables_body, &a, 0u, 1u, 8u);
+    for (int b = 0; b < grid; b++) emu::run_block(decv2_body, &a, (unsigned)b, (unsigned)grid, LCV_WARPS);
+    int redo = 0;
+    for (int b = 0; b < B; b++) redo += status[b] == LC_NEEDS_GENERIC;
+    *n_redone = redo;
+    a.d.only_flagged = LC_NEEDS_GENERIC;
+    for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a.d, (unsigned)b, (unsigned)grid);
     return 0;
 }
 

@@ -211,3 +211,83 @@ def test_lane_per_group_phase_a():
     codes[1, 2, 7] = 99
     out, nbits, status, fault = H.encode_par(codes, 16, 1, nwarps=0)
     assert status.tolist() == [0, 6] and fault[1] == 2 * 64 + 7
+
+
+# ---- decoder v2 (decoder warp + updater warps, direct-mapped contexts, integer / table fast paths) ----
+
+def _v2_ok(n, shape):
+    return 8 <= n <= 256 and len(shape) == 3 and 4 <= shape[2] <= 4096
+
+
+def test_decoder_v2_matches_reference_vectors():
+    ran = 0
+    for fixture in ("kat.npz", "coder_small.npz", "coder_full.npz"):
+        for name, rec in coder_cases(golden(fixture), mode="repaired").items():
+            n, codes = int(rec["n"]), rec["codes"]
+            if not _pow2(n) or codes.ndim != 3 or "enc_error" in rec or not _v2_ok(n, codes.shape):
+                continue
+            batch = codes[None]
+            dec, st, fi, _ = H.decode([rec["packed"].tobytes()], n, batch.shape, 1, fast="v2")
+            ref = rec["decoded"].reshape(batch.shape)
+            if "dec_error" in rec:
+                k = int(rec["dec_fault_index"])
+                assert st[0] == ERR_TO_STATUS[str(rec["dec_error"][0])] and fi[0] == k, name
+                assert np.array_equal(dec.ravel()[:k], ref.ravel()[:k]) and not dec.ravel()[k:].any(), name
+            elif st[0] == 4:
+                assert ref.ravel()[fi[0]] == -1, name
+            else:
+                assert st[0] == 0 and np.array_equal(dec, ref), name
+            ran += 1
+    assert ran > 40
+
+
+def test_decoder_v2_against_oracle_decoder():
+    """Random streams over the alphabets v2 accepts, including narrow 4-bit data the reference itself cannot
+    round-trip (hazards H1-H3): same symbols, same fault class, same fault index as the oracle decoder."""
+    rng = np.random.default_rng(77)
+    cases = ((256, (3, 16, 512), 18.0), (256, (2, 16, 512), 2.5), (128, (2, 8, 200), 9.0), (64, (4, 5, 100), 4.5),
+             (16, (3, 16, 512), 1.14), (16, (2, 16, 512), 0.6), (8, (3, 6, 64), 1.0), (256, (2, 2, 2000), 30.0))
+    for n, shape, sd in cases:
+        codes = np.clip(np.round(rng.normal(n / 2, sd, shape)), 0, n - 1).astype(np.int32)
+        codes[0, 0, :8] = n - 1
+        streams = [O.encode_stream(codes[b:b + 1], n)["packed"] for b in range(shape[0])]
+        cb = np.linspace(-1, 1, n).astype(np.float32)
+        dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast="v2", grid=2, codebook=cb)
+        for b in range(shape[0]):
+            ref = O.decode_stream(streams[b], n, (1,) + shape[1:])
+            k = int(ref["fault_index"]) if ref["status"] else codes[b].size
+            assert st[b] == ref["status"] and (ref["status"] == 0 or fi[b] == k), (n, shape, b, st[b], ref["status"])
+            assert np.array_equal(dec[b].ravel()[:k], ref["symbols"].ravel()[:k]), (n, shape, b)
+            assert np.array_equal(deq[b][:k], cb[dec[b].ravel()[:k]])
+
+
+def test_decoder_v2_wide_contexts_and_images_sharing_a_model():
+    rng = np.random.default_rng(31)
+    n = 256
+    codes = np.zeros((2, 4, 400), np.int32)
+    codes[0, :, 0::2] = 7                              # (left=7, up=7|-1) contexts recur ...
+    codes[0, :, 1::2] = rng.integers(0, n, (4, 200))   # ... with many different symbols: > 32 entries
+    codes[1] = np.clip(np.round(rng.normal(128, 9, (4, 400))), 0, n - 1)
+    streams = [O.encode_stream(codes[b:b + 1], n)["packed"] for b in range(2)]
+    cb = np.linspace(-1, 1, n).astype(np.float32)
+    dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast="v2", grid=1, codebook=cb)
+    assert H.decode.last_redone == 1
+    assert not st.any() and np.array_equal(dec, codes) and np.array_equal(deq.reshape(codes.shape), cb[codes])
+    # records between 7 and 32 entries live in the pool
+    codes = np.zeros((1, 6, 300), np.int32)
+    codes[0, :, 0::2] = 5
+    codes[0, :, 1::2] = rng.integers(100, 120, (6, 150))
+    streams = [O.encode_stream(codes, n)["packed"]]
+    dec, st, fi, _ = H.decode(streams, n, codes.shape, 1, fast="v2", grid=1)
+    assert H.decode.last_redone == 0 and not st.any() and np.array_equal(dec, codes)
+    # the reference's batched call: several images share coder and model (cabac_compression.py:330-337)
+    imgs = np.clip(np.round(rng.normal(32, 3, (3, 4, 64))), 0, 63).astype(np.int32)
+    packed = O.encode_stream(imgs, 64)["packed"]
+    dec, st, fi, _ = H.decode([packed], 64, (1,) + imgs.shape, 1, fast="v2", grid=1)
+    assert not st.any() and np.array_equal(dec[0], imgs)
+    # corrupted stream: whatever the oracle decoder does, v2 does
+    bad = bytearray(packed); bad[len(bad) // 2] ^= 0x5a
+    ref = O.decode_stream(bytes(bad), 64, imgs.shape)
+    dec, st, fi, _ = H.decode([bytes(bad)], 64, (1,) + imgs.shape, 1, fast="v2", grid=1)
+    k = int(ref["fault_index"]) if ref["status"] else imgs.size
+    assert st[0] == ref["status"] and np.array_equal(dec.ravel()[:k], ref["symbols"].ravel()[:k])

@@ -43,7 +43,8 @@ assert lib.lc_debug_profile(buf.ctypes.data) == 0
 t = buf.reshape(8, 8).astype(np.float64)
 nsym = B * 16 * 512
 print("decode launch (instrumented): %.3f ms; %d symbols" % (ev0.elapsed_time(ev1), nsym))
-cols = ["probe", "load", "search", "interval", "renorm+out", "writeback"]
+v2 = os.environ.get("LC_DECODER", "v2")[0] != "f" and bits <= 8
+cols = ["state+wait", "symbol", "key+renorm+out", "post", "-", "-"] if v2 else ["probe", "load", "search", "interval", "renorm+out", "writeback"]
 print("%-8s %8s %8s | " % ("state", "share", "cyc/sym") + " ".join("%10s" % c for c in cols))
 tot = 0.0
 for st in range(4):
@@ -56,4 +57,5 @@ for st in range(4):
 print("mean cycles/symbol/warp: %.0f" % (tot / nsym))
 for st in range(4):
     cnt = max(t[st, 0], 1)
-    print("state %d: exact-search fallbacks %.2f%%, exact_at fallbacks %.2f%%" % (st, 100 * t[4, st] / cnt, 100 * t[5, st] / cnt))
+    print("state %d: exact-search fallbacks %.2f%%, exact_at fallbacks %.2f%%, waits for a recent job %.2f%%" % (
+        st, 100 * t[4, st] / cnt, 100 * t[5, st] / cnt, 100 * t[6, st] / cnt))
