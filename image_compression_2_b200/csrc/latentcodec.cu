@@ -13,6 +13,7 @@
 #include "lc_encoder_par.cuh"
 #include "lc_decoder_fast.cuh"
 #include "lc_decoder_v2.cuh"
+#include "lc_encoder_sparse.cuh"
 
 #define LC_CUDA_RET()                                                     \
     do {                                                                  \
@@ -253,12 +254,14 @@ __global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_kernel(LcCoder
 typedef cub::BlockRadixSort<uint32_t, 256, LC_PAR_MAX_SYMBOLS / 256, unsigned short> LcBlockSort;
 typedef cub::BlockScan<int, 256> LcBlockScan;
 
-// Also emits, per stream, the list of contexts visited at least twice (glist/ngroups: the work items of
-// phase A) and the closed-form interval of every first visit (uniform model: cum[i] = i/n).
+// Also emits what needs no model: the closed-form interval of every first visit (uniform model: cum[i] = i/n) and,
+// when `tables` is given, the interval of every second visit (table of exact cumsums of the model after one update,
+// lcv_tables_block), plus glist/ngroups = the contexts visited at least three times (the work items of phase A).
 __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const int *__restrict__ codes,
                                                           uint32_t *__restrict__ skeys, unsigned short *__restrict__ spos,
                                                           int *__restrict__ first_bad, unsigned short *__restrict__ glist,
-                                                          int *__restrict__ ngroups, double *__restrict__ ivs)
+                                                          int *__restrict__ ngroups, double *__restrict__ ivs,
+                                                          const double *__restrict__ tables)
 {
     extern __shared__ __align__(16) char lc_smem[];
     LcBlockSort::TempStorage &temp = *reinterpret_cast<LcBlockSort::TempStorage *>(lc_smem);
@@ -296,39 +299,60 @@ __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const 
     for (int i = 0; i < ITEMS; i++) { ok[i] = keys[i]; ov[i] = vals[i]; }
     if (threadIdx.x == 0) first_bad[blockIdx.x] = fb;
 
-    // group heads: sorted index j = tid*ITEMS + i starts a context when its key differs from j-1
-    __shared__ uint32_t s_edge_last[256], s_edge_first[256];
+    // neighbours across thread boundaries: sorted index j = tid*ITEMS + i
+    __shared__ uint32_t s_last[256], s_last2[256], s_first[256], s_first2[256];
+    __shared__ unsigned short s_last_val[256];
     __shared__ LcBlockScan::TempStorage scan_temp;
-    s_edge_last[threadIdx.x] = keys[ITEMS - 1];
-    s_edge_first[threadIdx.x] = keys[0];
+    s_last[threadIdx.x] = keys[ITEMS - 1];
+    s_last2[threadIdx.x] = keys[ITEMS - 2];
+    s_last_val[threadIdx.x] = vals[ITEMS - 1];
+    s_first[threadIdx.x] = keys[0];
+    s_first2[threadIdx.x] = keys[1];
     __syncthreads();
-    const uint32_t prev_edge = threadIdx.x > 0 ? s_edge_last[threadIdx.x - 1] : 0u;
-    const uint32_t next_edge = threadIdx.x < 255 ? s_edge_first[threadIdx.x + 1] : LC_PAR_KEY_PAD;
+    const bool has_prev = threadIdx.x > 0, has_next = threadIdx.x < 255;
+    const uint32_t prev1 = has_prev ? s_last[threadIdx.x - 1] : 0u, prev2 = has_prev ? s_last2[threadIdx.x - 1] : 0u;
+    const unsigned short prev_val = has_prev ? s_last_val[threadIdx.x - 1] : (unsigned short)0;
+    const uint32_t next1 = has_next ? s_first[threadIdx.x + 1] : LC_PAR_KEY_PAD;
+    const uint32_t next2 = has_next ? s_first2[threadIdx.x + 1] : LC_PAR_KEY_PAD;
     const double u0 = LC_DDIV(1.0, (double)n);
-    unsigned multi_mask = 0u;
-    int n_multi = 0;
+    const double *cum1 = tables ? tables + 64 : (const double *)0;
+    double *ivb = ivs + (size_t)blockIdx.x * 2 * LC_PAR_MAX_SYMBOLS;
+    unsigned list_mask = 0u;
+    int n_list = 0;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const int j = (int)threadIdx.x * ITEMS + i;
-        const uint32_t kprev = i > 0 ? keys[i - 1] : prev_edge;
-        const uint32_t knext = i < ITEMS - 1 ? keys[i + 1] : next_edge;
+        const uint32_t k0 = keys[i];
+        const uint32_t km1 = i > 0 ? keys[i > 0 ? i - 1 : 0] : prev1;
+        const uint32_t km2 = i > 1 ? keys[i > 1 ? i - 2 : 0] : (i == 1 ? prev1 : prev2);
+        const uint32_t kp1 = i < ITEMS - 1 ? keys[i < ITEMS - 1 ? i + 1 : 0] : next1;
+        const uint32_t kp2 = i < ITEMS - 2 ? keys[i < ITEMS - 2 ? i + 2 : 0] : (i == ITEMS - 2 ? next1 : next2);
         const bool valid = j < fb; // positions before the first bad symbol; padding keys sort behind them
-        const bool head = valid && (j == 0 || kprev != keys[i]);
+        const bool head = valid && (j == 0 || km1 != k0);
         if (head) {
             const int p = vals[i];
             const int sy = c[p];
-            double *o = ivs + (size_t)blockIdx.x * 2 * LC_PAR_MAX_SYMBOLS + 2 * p;
-            o[0] = LC_DMUL((double)sy, u0);
-            o[1] = LC_DMUL((double)(sy + 1), u0);
+            ivb[2 * p] = LC_DMUL((double)sy, u0);
+            ivb[2 * p + 1] = LC_DMUL((double)(sy + 1), u0);
         }
-        if (head && (j + 1 < fb) && knext == keys[i]) { multi_mask |= 1u << i; n_multi++; }
+        if (cum1) {
+            const bool second = valid && !head && (j == 1 || km2 != k0);
+            if (second) { // model after one update with the first visit's symbol
+                const int p = vals[i];
+                const int sy = c[p], s1 = c[i > 0 ? vals[i > 0 ? i - 1 : 0] : prev_val];
+                const double *row = cum1 + (size_t)s1 * (n + 1);
+                ivb[2 * p] = row[sy];
+                ivb[2 * p + 1] = row[sy + 1];
+            }
+            if (head && (j + 2 < fb) && kp1 == k0 && kp2 == k0) { list_mask |= 1u << i; n_list++; }
+        } else if (head && (j + 1 < fb) && kp1 == k0) { list_mask |= 1u << i; n_list++; }
     }
     int g_off = 0, g_total = 0;
-    LcBlockScan(scan_temp).ExclusiveSum(n_multi, g_off, g_total);
+    LcBlockScan(scan_temp).ExclusiveSum(n_list, g_off, g_total);
     unsigned short *gl = glist + (size_t)blockIdx.x * LC_PAR_MAX_GROUPS;
-    while (multi_mask) {
-        const int i = __ffs((int)multi_mask) - 1;
-        multi_mask &= multi_mask - 1;
+    while (list_mask) {
+        const int i = __ffs((int)list_mask) - 1;
+        list_mask &= list_mask - 1;
         gl[g_off++] = (unsigned short)((int)threadIdx.x * ITEMS + i);
     }
     if (threadIdx.x == 0) ngroups[blockIdx.x] = g_total;
@@ -343,16 +367,14 @@ __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, con
     lc_enc_phase_a_block(cfg, codes, B, skeys, spos, first_bad, ivs, lc_smem);
 }
 
-__global__ void __launch_bounds__(32) lc_enc_phase_a_lanes_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
-                                                                  const uint32_t *__restrict__ skeys,
-                                                                  const unsigned short *__restrict__ spos,
-                                                                  const int *__restrict__ first_bad,
-                                                                  const unsigned short *__restrict__ glist,
-                                                                  const int *__restrict__ ngroups, double *ivs,
-                                                                  unsigned int *task_counter)
+#define LCS_BLOCK_WARPS 4
+__global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS) lc_enc_phase_a_sparse_kernel(
+    LcCoderCfg cfg, const int *__restrict__ codes, int B, const uint32_t *__restrict__ skeys,
+    const unsigned short *__restrict__ spos, const int *__restrict__ first_bad, const unsigned short *__restrict__ glist,
+    const int *__restrict__ ngroups, double *ivs, unsigned int *task_counter, const double *__restrict__ tables)
 {
     extern __shared__ __align__(16) char lc_smem[];
-    lc_enc_phase_a_lanes_block(cfg, codes, B, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, lc_smem);
+    lc_enc_phase_a_sparse_block(cfg, codes, B, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables, lc_smem);
 }
 
 __global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
@@ -478,7 +500,8 @@ static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
         if (v2 > need) need = v2;
     }
     if (lc_use_parallel_encoder(cfg)) {
-        const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES;
+        const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES + 256 +
+                            (int64_t)lcv_tables_bytes(cfg.n);
         if (par > need) need = par;
     }
     return need;
@@ -586,19 +609,25 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
         const size_t sort_smem = sizeof(LcBlockSort::TempStorage);
         const size_t a_smem = (size_t)8 * cfg.n * 8;
         static bool attr_done = false;
-        static int phase_a_choice = 0; // 0 auto, 1 warp-per-group, 2 lane-per-group (LC_PHASE_A=warp|lanes)
+        static int phase_a_choice = 0; // 0 auto, 1 dense warp-per-group, 2 sparse lane-per-group (LC_PHASE_A=warp|lanes)
         if (!attr_done) {
             cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
             cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
-            cudaFuncSetAttribute(lc_enc_phase_a_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 256 * 32 * 8 + 256);
+            cudaFuncSetAttribute(lc_enc_phase_a_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 LCS_BLOCK_WARPS * 1024 * 8);
             const char *e = getenv("LC_PHASE_A");
             if (e && e[0] == 'w') phase_a_choice = 1;
             if (e && e[0] == 'l') phase_a_choice = 2;
             attr_done = true;
         }
-        // lane-per-group needs a [n][32] float64 tile per warp: n <= 256
-        const bool lanes_variant = cfg.n <= 256 && phase_a_choice != 1;
+        const bool sparse_variant = phase_a_choice != 1;
+        const int tile = B < LC_PAR_TILE ? B : LC_PAR_TILE;
+        // per-launch tables (u after the first update, exact cumsum rows of the model after one update)
+        double *tables = (double *)((char *)scratch + (((size_t)tile * LC_PAR_STREAM_BYTES + 255) & ~(size_t)255));
+        if (sparse_variant) {
+            lc_v2_tables_kernel<<<1, 256, (size_t)(cfg.n + 64) * 8, st>>>(cfg, tables);
+            LC_CUDA_RET();
+        }
         for (int b0 = 0; b0 < B; b0 += LC_PAR_TILE) {
             const int nb = (B - b0) < LC_PAR_TILE ? (B - b0) : LC_PAR_TILE;
             char *ws = (char *)scratch;
@@ -610,16 +639,16 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
             int *ngroups = (int *)ws;                         ws += (size_t)nb * 4;
             unsigned int *task_counter = (unsigned int *)ws;
             const int *codes = idx + (size_t)b0 * cfg.total;
-            lc_enc_sort_kernel<<<nb, 256, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs);
+            lc_enc_sort_kernel<<<nb, 256, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs,
+                                                           sparse_variant ? tables : (const double *)0);
             LC_CUDA_RET();
-            if (lanes_variant) {
-                const size_t la_smem = (size_t)cfg.n * 32 * 8 + 256;
-                int per_sm = (int)((227u * 1024u) / (la_smem + 1024u));
-                if (per_sm > 16) per_sm = 16;
-                const int la_grid = lc_num_sms() * per_sm;
+            if (sparse_variant) {
+                const size_t sp_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;
+                int blocks_per_sm = (int)((200u * 1024u) / (sp_smem + 1024u));
+                if (blocks_per_sm > 32 / LCS_BLOCK_WARPS) blocks_per_sm = 32 / LCS_BLOCK_WARPS;
                 cudaMemsetAsync(task_counter, 0, 4, st);
-                lc_enc_phase_a_lanes_kernel<<<la_grid, 32, la_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, glist,
-                                                                          ngroups, ivs, task_counter);
+                lc_enc_phase_a_sparse_kernel<<<lc_num_sms() * blocks_per_sm, 32 * LCS_BLOCK_WARPS, sp_smem, st>>>(
+                    cfg, codes, nb, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables);
             } else {
                 lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
             }

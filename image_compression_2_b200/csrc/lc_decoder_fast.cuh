@@ -159,6 +159,17 @@ __device__ __forceinline__ bool lcf_update(LcFast &F, int s)
     return true;
 }
 
+// T after `count` sequential additions of u (np.cumsum over a run of never-observed symbols)
+__device__ __forceinline__ double lcf_add_run(double T, double u, int count)
+{
+    for (; count >= 8; count -= 8) {
+        T = LC_DADD(T, u); T = LC_DADD(T, u); T = LC_DADD(T, u); T = LC_DADD(T, u);
+        T = LC_DADD(T, u); T = LC_DADD(T, u); T = LC_DADD(T, u); T = LC_DADD(T, u);
+    }
+    for (; count > 0; count--) T = LC_DADD(T, u);
+    return T;
+}
+
 // exact np.cumsum values cum[s], cum[s+1] from the register model: fixed-count chains
 __device__ __forceinline__ void lcf_exact_at(const LcFast &F, int s, LcInterval &out)
 {
@@ -169,11 +180,11 @@ __device__ __forceinline__ void lcf_exact_at(const LcFast &F, int s, LcInterval 
         const int sj = __shfl_sync(LC_FULL_MASK, F.my_sym, j);
         const double vj = __shfl_sync(LC_FULL_MASK, F.my_val, j);
         if (sj >= s) { if (sj == s) ps = vj; break; }
-        for (int r = sj - i; r > 0; r--) T = LC_DADD(T, F.u);
+        T = lcf_add_run(T, F.u, sj - i);
         T = LC_DADD(T, vj);
         i = sj + 1;
     }
-    for (int r = s - i; r > 0; r--) T = LC_DADD(T, F.u);
+    T = lcf_add_run(T, F.u, s - i);
     out.sym = s; out.clo = T; out.chi = LC_DADD(T, ps); out.exact = 1;
 }
 

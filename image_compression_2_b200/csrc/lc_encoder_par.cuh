@@ -316,225 +316,4 @@ __device__ __forceinline__ void lc_enc_phase_b_block(const LcCoderCfg &cfg, int 
     }
 }
 
-// =================================================================================================
-// Phase A, lane-per-group variant (n <= 256).
-//
-// In the warp-per-group kernel above all 32 lanes execute the same strictly sequential np.cumsum
-// walk, so 31/32 of the issued work is redundant.  Here every LANE owns one context group: its
-// dense model is a column of a [n][32] float64 tile in shared memory (element i of lane L at
-// tile[i*32+L]: conflict-free for 64-bit accesses), and the lane runs the reference's arithmetic
-// as plain scalar code -- NumPy's 8-accumulator pairwise sum, the sequential prefix, the scaling
-// loop.  Lanes advance one visit per step in lock step and pick up the next group of the stream
-// when theirs ends.  One warp (block) per stream; groups with a single visit never reach a lane.
-// =================================================================================================
-
-// NumPy pairwise sum of one lane's column (n >= 8: blocks of min(n,128), 8 accumulators, binary tree)
-__device__ __forceinline__ double lc_col_pairwise(const double *col, int n, int pw_len, int pw_steps)
-{
-    if (n < 8) {
-        double r = 0.0;
-        for (int i = 0; i < n; i++) r = LC_DADD(r, col[i * 32]);
-        return r;
-    }
-    double bs[8];
-    const int nblk = n / pw_len;
-    for (int b = 0; b < nblk; b++) {
-        const double *p = col + (size_t)b * pw_len * 32;
-        double r0 = p[0], r1 = p[32], r2 = p[64], r3 = p[96], r4 = p[128], r5 = p[160], r6 = p[192], r7 = p[224];
-        for (int t = 1; t < pw_steps; t++) {
-            const double *q = p + t * 256;
-            r0 = LC_DADD(r0, q[0]);   r1 = LC_DADD(r1, q[32]);  r2 = LC_DADD(r2, q[64]);  r3 = LC_DADD(r3, q[96]);
-            r4 = LC_DADD(r4, q[128]); r5 = LC_DADD(r5, q[160]); r6 = LC_DADD(r6, q[192]); r7 = LC_DADD(r7, q[224]);
-        }
-        bs[b] = LC_DADD(LC_DADD(LC_DADD(r0, r1), LC_DADD(r2, r3)), LC_DADD(LC_DADD(r4, r5), LC_DADD(r6, r7)));
-    }
-    // recursive halving over the blocks (n2 = n/2 is a multiple of 128 for n >= 256)
-    for (int w = 1; w < nblk; w <<= 1)
-        for (int b = 0; b + w < nblk; b += 2 * w) bs[b] = LC_DADD(bs[b], bs[b + w]);
-    return bs[0];
-}
-
-// ContextModel.update_model (:119-144) on one lane's column
-__device__ __forceinline__ void lc_col_update(double *col, int n, int pw_len, int pw_steps, double rate, int s)
-{
-    const double p_old = col[s * 32];
-    const double p_new = LC_DADD(p_old, LC_DMUL(rate, LC_DSUB(1.0, p_old)));
-    col[s * 32] = p_new;
-    const double total = lc_col_pairwise(col, n, pw_len, pw_steps);
-    const double others = LC_DSUB(total, p_new);
-    const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, p_new), others) : 0.0;
-    // in-place scaling, eight elements at a time: loads first, then the multiplies, then the stores
-    // (the compiler cannot reorder shared-memory loads across the stores of a rolled loop)
-    int i = 0;
-    for (; i + 8 <= n; i += 8) {
-        double *q = col + i * 32;
-        const double a0 = q[0], a1 = q[32], a2 = q[64], a3 = q[96], a4 = q[128], a5 = q[160], a6 = q[192], a7 = q[224];
-        q[0] = LC_DMUL(a0, f);   q[32] = LC_DMUL(a1, f);  q[64] = LC_DMUL(a2, f);  q[96] = LC_DMUL(a3, f);
-        q[128] = LC_DMUL(a4, f); q[160] = LC_DMUL(a5, f); q[192] = LC_DMUL(a6, f); q[224] = LC_DMUL(a7, f);
-    }
-    for (; i < n; i++) col[i * 32] = LC_DMUL(col[i * 32], f);
-    col[s * 32] = p_new;
-}
-
-// exact np.cumsum prefix of one lane's column: loads in batches of eight ahead of the dependent adds
-__device__ __forceinline__ double lc_col_prefix(const double *col, int s)
-{
-    double T = 0.0;
-    int i = 0;
-    for (; i + 8 <= s; i += 8) {
-        const double *q = col + i * 32;
-        const double a0 = q[0], a1 = q[32], a2 = q[64], a3 = q[96], a4 = q[128], a5 = q[160], a6 = q[192], a7 = q[224];
-        T = LC_DADD(T, a0); T = LC_DADD(T, a1); T = LC_DADD(T, a2); T = LC_DADD(T, a3);
-        T = LC_DADD(T, a4); T = LC_DADD(T, a5); T = LC_DADD(T, a6); T = LC_DADD(T, a7);
-    }
-    for (; i < s; i++) T = LC_DADD(T, col[i * 32]);
-    return T;
-}
-
-// Group list of one stream, produced by phase S (lc_enc_sort_kernel) or, for the emulator, by
-// lc_enc_group_list_warp below: glist[g] = sorted index of the first visit of the g-th context that is
-// visited at least twice; first visits get their closed-form interval (uniform model: cum[i] = i/n).
 #define LC_PAR_MAX_GROUPS (LC_PAR_MAX_SYMBOLS / 2)
-#define LC_PAR_TASK_GROUPS 64
-
-__device__ __forceinline__ int lc_enc_group_list_warp(int lane, const int *codes, const uint32_t *skeys,
-                                                      const unsigned short *spos, int total, double u0, double *ivs,
-                                                      unsigned short *glist)
-{
-    int ngroups = 0;
-    for (int base = 0; base < total; base += 32) {
-        const int j = base + lane;
-        const bool valid = j < total;
-        const uint32_t kj = valid ? skeys[j] : 0u;
-        const bool head = valid && (j == 0 || skeys[j - 1] != kj);
-        if (head) {
-            const int p = spos[j];
-            const int s = codes[p];
-            ivs[2 * p] = LC_DMUL((double)s, u0);
-            ivs[2 * p + 1] = LC_DMUL((double)(s + 1), u0);
-        }
-        const bool multi = head && (j + 1 < total) && (skeys[j + 1] == kj);
-        const unsigned m = __ballot_sync(LC_FULL_MASK, multi);
-        if (multi) glist[ngroups + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
-        ngroups += __popc(m);
-    }
-    return ngroups;
-}
-
-// smem: tile[n*32] doubles | u1tab[32] doubles.
-// Persistent warps pull tasks (stream, chunk of LC_PAR_TASK_GROUPS groups) from *task_counter.
-__device__ __forceinline__ void lc_enc_phase_a_lanes_block(const LcCoderCfg &cfg, const int *codes_all, int B,
-                                                           const uint32_t *skeys_all, const unsigned short *spos_all,
-                                                           const int *first_bad, const unsigned short *glist_all,
-                                                           const int *ngroups_all, double *ivs_all,
-                                                           unsigned int *task_counter, char *smem)
-{
-    const int lane = (int)(threadIdx.x & 31);
-    const int n = cfg.n, pw_len = cfg.pw_len, pw_steps = cfg.pw_steps;
-    const double rate = cfg.rate;
-    const double u0 = LC_DDIV(1.0, (double)n);
-    const double P1 = LC_DADD(u0, LC_DMUL(rate, LC_DSUB(1.0, u0)));
-    double *tile = (double *)smem;
-    double *col = tile + lane;
-    double *u1tab = tile + (size_t)n * 32;
-    // u after the first update, by chain step of the symbol (by symbol when n < 8): each lane computes one entry
-    {
-        const int entries = cfg.pw_chains == 0 ? n : pw_steps;
-        if (lane < entries) {
-            const int s = cfg.pw_chains == 0 ? lane : 8 * lane;
-            for (int i = 0; i < n; i++) col[i * 32] = u0;
-            lc_col_update(col, n, pw_len, pw_steps, rate, s);
-            u1tab[lane] = col[(s == 0 ? 1 : 0) * 32]; // any other symbol: u0 * f
-        }
-        __syncwarp();
-    }
-    const unsigned chunks_per_stream = LC_PAR_MAX_GROUPS / LC_PAR_TASK_GROUPS;
-    const unsigned n_tasks = (unsigned)B * chunks_per_stream;
-    for (;;) {
-        unsigned task = 0;
-        if (lane == 0) task = atomicAdd(task_counter, 1u);
-        task = __shfl_sync(LC_FULL_MASK, task, 0);
-        if (task >= n_tasks) break;
-        const int sidx = (int)(task / chunks_per_stream);
-        const int g_lo = (int)(task % chunks_per_stream) * LC_PAR_TASK_GROUPS;
-        const int ngroups = ngroups_all[sidx];
-        if (g_lo >= ngroups) continue;
-        const int g_hi = (g_lo + LC_PAR_TASK_GROUPS < ngroups) ? g_lo + LC_PAR_TASK_GROUPS : ngroups;
-        const size_t o = (size_t)sidx * LC_PAR_MAX_SYMBOLS;
-        const int *codes = codes_all + (size_t)sidx * cfg.total;
-        const uint32_t *skeys = skeys_all + o;
-        const unsigned short *spos = spos_all + o;
-        const unsigned short *glist = glist_all + (size_t)sidx * LC_PAR_MAX_GROUPS;
-        double *ivs = ivs_all + 2 * o;
-        const int fb = first_bad[sidx];
-        const int total = fb < cfg.total ? fb : cfg.total;
-
-        // every lane walks one group at a time, one visit per step
-        int next = g_lo;   // next unassigned group of this task (warp-uniform)
-        int t = -1;        // sorted index of the visit handled in this step, -1 = idle
-        int visit = 0;     // 2 = second visit of the group (model still implicit), >= 3 = column is live
-        int s1 = 0, p = 0, s = 0;
-        bool last = false;
-        double u1 = 0.0;
-        uint32_t key = 0u;
-        for (;;) {
-            const unsigned need = __ballot_sync(LC_FULL_MASK, t < 0);
-            if (need) {
-                const int g = next + __popc(need & ((1u << lane) - 1u));
-                if (t < 0 && g < g_hi) {
-                    const int j0 = glist[g];
-                    key = skeys[j0];
-                    s1 = codes[spos[j0]];
-                    u1 = u1tab[cfg.pw_chains == 0 ? s1 : ((s1 & (pw_len - 1)) >> 3)];
-                    t = j0 + 1; // its second visit
-                    visit = 2;
-                    p = spos[t]; s = codes[p];
-                    last = (t + 1 >= total) || (skeys[t + 1] != key);
-                }
-                next += __popc(need);
-                if (next > g_hi) next = g_hi;
-            }
-            if (__ballot_sync(LC_FULL_MASK, t >= 0) == 0u) break;
-            if (t >= 0) {
-                // data of the following visit (if any): requested now, used in the next step
-                const bool more = !last;
-                int p_n = 0, s_n = 0;
-                bool last_n = true;
-                if (more) {
-                    p_n = spos[t + 1];
-                    last_n = (t + 2 >= total) || (skeys[t + 2] != key);
-                }
-                double T;
-                double ps;
-                if (visit == 2) {
-                    // model after one update: u1 everywhere, P1 at s1 -- the exact np.cumsum prefix needs no column
-                    T = 0.0;
-                    const int run1 = s < s1 ? s : s1;
-                    for (int i = 0; i < run1; i++) T = LC_DADD(T, u1);
-                    if (s > s1) {
-                        T = LC_DADD(T, P1);
-                        for (int i = s1 + 1; i < s; i++) T = LC_DADD(T, u1);
-                    }
-                    ps = (s == s1) ? P1 : u1;
-                } else {
-                    T = lc_col_prefix(col, s);
-                    ps = col[s * 32];
-                }
-                ivs[2 * p] = T;
-                ivs[2 * p + 1] = LC_DADD(T, ps);
-                if (more) s_n = codes[p_n];
-                if (last) t = -1; // the update after the last visit is never read
-                else {
-                    if (visit == 2) { // the group goes on: materialise the column now
-                        for (int i = 0; i < n; i++) col[i * 32] = u1;
-                        col[s1 * 32] = P1;
-                    }
-                    lc_col_update(col, n, pw_len, pw_steps, rate, s);
-                    t++; visit = 3;
-                    p = p_n; s = s_n; last = last_n;
-                }
-            }
-        }
-        __syncwarp();
-    }
-}

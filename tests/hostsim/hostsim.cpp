@@ -12,6 +12,7 @@
 #include "../../image_compression_2_b200/csrc/lc_encoder_par.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_fast.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_v2.cuh"
+#include "../../image_compression_2_b200/csrc/lc_encoder_sparse.cuh"
 #include <algorithm>
 #include <numeric>
 
@@ -266,7 +267,8 @@ extern "C" void hostsim_stats(long long *out, int reset)
 // ---- parallel encoder: phase S restated on the host (the real kernel uses a CUB block sort and is
 // checked on the GPU), phases A and B run through the emulator
 struct ParAArgs { LcCoderCfg cfg; const int *codes; int B; const uint32_t *skeys; const unsigned short *spos;
-                  const int *first_bad; double *ivs; char *smem; unsigned short *glist; int *ngroups; unsigned int *task_counter; };
+                  const int *first_bad; double *ivs; char *smem; unsigned short *glist; int *ngroups; unsigned int *task_counter;
+                  double *tables; };
 static void para_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
@@ -274,11 +276,16 @@ static void para_body(void *p)
 }
 struct ParBArgs { LcCoderCfg cfg; int B; const int *first_bad; const double *ivs; unsigned char *out_slots;
                   uint32_t slot_bytes; int *nbits, *status, *fault; };
+static void para_tables_body(void *p)
+{
+    ParAArgs *a = (ParAArgs *)p;
+    lcv_tables_block(a->cfg, a->tables, a->smem);
+}
 static void para_lanes_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
-    lc_enc_phase_a_lanes_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->glist, a->ngroups, a->ivs,
-                               a->task_counter, a->smem);
+    lc_enc_phase_a_sparse_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->glist, a->ngroups, a->ivs,
+                                a->task_counter, a->tables, a->smem);
 }
 static void glist_body(void *p)
 {   // phase S part: group list + first-visit intervals (on the GPU this is done by lc_enc_sort_kernel)
@@ -289,8 +296,9 @@ static void glist_body(void *p)
         const size_t o = (size_t)b * LC_PAR_MAX_SYMBOLS;
         const int fb = a->first_bad[b];
         const int total = fb < a->cfg.total ? fb : a->cfg.total;
-        const int ng = lc_enc_group_list_warp(lane, a->codes + (size_t)b * a->cfg.total, a->skeys + o, a->spos + o, total, u0,
-                                              a->ivs + 2 * o, a->glist + (size_t)b * LC_PAR_MAX_GROUPS);
+        const int ng = lc_enc_group_list3_warp(lane, a->codes + (size_t)b * a->cfg.total, a->skeys + o, a->spos + o, total,
+                                               a->cfg.n, u0, a->tables + 64, a->ivs + 2 * o,
+                                               a->glist + (size_t)b * LC_PAR_MAX_GROUPS);
         if (lane == 0) a->ngroups[b] = ng;
     }
 }
@@ -333,15 +341,19 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
         }
     }
     std::vector<double> ivs((size_t)B * LC_PAR_MAX_SYMBOLS * 2, -1.0);
-    std::vector<char> smem(std::max((size_t)nwarps * n * 8, (size_t)n * 32 * 8 + 256 + LC_PAR_MAX_SYMBOLS) + 64);
+    std::vector<char> smem(std::max((size_t)nwarps * n * 8, std::max((size_t)(n + 64) * 8, (size_t)2 * n * 8)) + 64);
     std::vector<unsigned short> glist((size_t)B * LC_PAR_MAX_GROUPS, 0);
     std::vector<int> ngroups(B, 0);
     unsigned int task_counter = 0;
+    std::vector<double> tables(lcv_tables_bytes(n) / 8 + 8, -777.0);
     ParAArgs a{cfg, codes, B, skeys.data(), spos.data(), first_bad.data(), ivs.data(),
-               (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15), glist.data(), ngroups.data(), &task_counter};
-    if (nwarps == 0) { // lane-per-group variant: one warp per block, tasks from a shared counter
+               (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15), glist.data(), ngroups.data(), &task_counter,
+               tables.data()};
+    if (nwarps == 0) { // sparse variant: second visits from the table, one warp per context visited three times or more
+        emu::run_block(para_tables_body, &a, 0u, 1u, 8u);
         for (int b = 0; b < grid; b++) emu::run_warp(glist_body, &a, (unsigned)b, (unsigned)grid);
-        for (int b = 0; b < grid; b++) emu::run_warp(para_lanes_body, &a, (unsigned)b, (unsigned)grid);
+        for (int b = 0; b < grid; b++)
+            for (int w = 0; w < 2; w++) emu::run_warp(para_lanes_body, &a, (unsigned)b, (unsigned)grid, (unsigned)w, 2u);
     } else
     for (int b = 0; b < grid; b++)
         for (int w = 0; w < nwarps; w++) emu::run_warp(para_body, &a, (unsigned)b, (unsigned)grid, (unsigned)w, (unsigned)nwarps);

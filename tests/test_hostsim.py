@@ -211,6 +211,16 @@ def test_lane_per_group_phase_a():
     codes[1, 2, 7] = 99
     out, nbits, status, fault = H.encode_par(codes, 16, 1, nwarps=0)
     assert status.tolist() == [0, 6] and fault[1] == 2 * 64 + 7
+    # contexts that collect more than 32 distinct symbols continue on the dense image
+    for n in (256, 1024):
+        codes = np.zeros((2, 4, 400), np.int32)
+        codes[0, :, 0::2] = 7
+        codes[0, :, 1::2] = rng.integers(0, n, (4, 200))
+        codes[1] = np.clip(np.round(rng.normal(n / 2, n / 28, (4, 400))), 0, n - 1)
+        out, nbits, status, fault = H.encode_par(codes, n, 1, grid=2, nwarps=0)
+        for b in range(2):
+            ref = O.encode_stream(codes[b:b + 1], n, "repaired")
+            assert status[b] == 0 and nbits[b] == ref["nbits"] and out[b, : len(ref["packed"])].tobytes() == ref["packed"]
 
 
 # ---- decoder v2 (decoder warp + updater warps, direct-mapped contexts, integer / table fast paths) ----
