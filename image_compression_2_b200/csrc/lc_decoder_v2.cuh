@@ -28,7 +28,7 @@
 #pragma once
 #include "lc_decoder_fast.cuh"
 
-#define LCV_NU 2
+#define LCV_NU 1
 #define LCV_WARPS (1 + LCV_NU)
 #define LCV_RING 32
 #define LCV_INLINE_K 6
@@ -173,10 +173,9 @@ __device__ __forceinline__ void lcv_br_init(LcvBits &b, const unsigned char *src
     b.win = ((unsigned long long)lcv_br_word(b, 0) << 32) | lcv_br_word(b, 1);
     b.nwin = 64; b.widx = 2; b.nextw = lcv_br_word(b, 2);
 }
-// next nb bits (1..32), MSB first
-__device__ __forceinline__ uint32_t lcv_br_take(LcvBits &b, int nb)
+// drop nb bits (0..32); the window keeps more than 32 valid bits at its top
+__device__ __forceinline__ void lcv_br_skip(LcvBits &b, int nb)
 {
-    const uint32_t v = (uint32_t)(b.win >> (64 - nb));
     b.win <<= nb;
     b.nwin -= nb;
     if (b.nwin <= 32) {
@@ -185,8 +184,25 @@ __device__ __forceinline__ uint32_t lcv_br_take(LcvBits &b, int nb)
         b.widx++;
         b.nextw = lcv_br_word(b, b.widx);
     }
+}
+// next nb bits (1..32), MSB first
+__device__ __forceinline__ uint32_t lcv_br_take(LcvBits &b, int nb)
+{
+    const uint32_t v = (uint32_t)(b.win >> (64 - nb));
+    lcv_br_skip(b, nb);
     return v;
 }
+
+#ifdef LC_HOSTSIM
+static inline float lcv_rcp_f32(float x) { return 1.0f / x; }
+#else
+static __device__ __forceinline__ float lcv_rcp_f32(float x) // x >= 65535 here: no range handling needed
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#endif
 
 // ---- shared/global views of one block
 struct LcV2 {
@@ -321,10 +337,9 @@ struct LcvPost {
 __device__ __forceinline__ void lcv_post(const LcV2 &V, LcvPost &P, int lane, uint32_t key, uint32_t pay)
 {
     const uint32_t j = P.njobs, slot = j & (LCV_RING - 1);
-    if (j >= LCV_RING) { // the job that used this slot must be finished before the slot is reused
-        while (lcv_ld_vol(V.ring_done + slot) != j - LCV_RING + 1u) LCV_SPIN();
-        LCV_FENCE();
-    }
+    // the job that used this slot must be finished before the slot is reused (ring_done starts at slot-RING+1)
+    while (lcv_ld_vol(V.ring_done + slot) != j - LCV_RING + 1u) LCV_SPIN();
+    LCV_FENCE();
     if (lane == 0) {
         lcv_st_vol(V.ring_key + slot, key); lcv_st_vol(V.ring_pay + slot, pay);
         lcv_bar_arrive(V.ring_bar + slot);
@@ -393,6 +408,10 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         LCP_START();
         LCP_ROW(st); LCP_COUNT(st, 0);
         const uint32_t shift = (key & 15u) * 2u;
+        // next position and the symbol above it (written at least C-1 >= 3 symbols ago): requested early
+        int c2 = c + 1, r2 = r;
+        if (c2 == C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
+        const int up2 = r2 > 0 ? (int)V.rows[((r2 - 1) & 1) * C + c2] : -1;
         // ---- decode_symbol (:272-292)
         const uint32_t rng1 = hi - lo, off = code - lo; // range-1, (code-low+1)-1
         const bool pre_ok = hi >= lo && off <= rng1 && rng1 >= 0xffffu;
@@ -404,7 +423,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
                 // uniform model: cum[i] = i/n exactly, so range*cum is exact and everything is integer work.
                 // With a = (code-low+1)*n and E = 1e-10*n*range, the symbol is the s with
                 // s*range < a - E (+- 3e-4) <= (s+1)*range; candidate from a float quotient, checked with margins.
-                const int cand = (int)(__fdividef((float)off, (float)rng1) * (float)n);
+                const int cand = (int)((float)off * lcv_rcp_f32((float)rng1) * (float)n);
                 const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
                 const unsigned long long above = below + rng1 + 1ull;
                 const unsigned long long a = ((unsigned long long)off + 1ull) << V.lg_n;
@@ -510,44 +529,38 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         }
         lo = nlo; hi = nhi;
         LCP_MARK(1);
-        // ---- next position's context (get_context :78-117): its state, and the data that state needs
+        // ---- next position's context (get_context :78-117): its state word is requested now ...
         if (lane == 0) V.rows[(r & 1) * C + c] = (unsigned char)s;
-        int c2 = c + 1, r2 = r;
-        if (c2 == C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
-        // (the row above was written at least C-1 >= 3 symbols ago and ordered by the __syncwarp() below)
-        const int up2 = r2 > 0 ? (int)V.rows[((r2 - 1) & 1) * C + c2] : -1;
         const uint32_t key2 = (uint32_t)((c2 > 0 ? s : -1) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);
         const uint32_t shift2 = (key2 & 15u) * 2u;
-        int st2 = (int)((lcv_ld_vol(V.sbits + (key2 >> 4)) >> shift2) & 3u);
-        uint32_t gw2 = 0u;
-        double2 p0 = {0.0, 0.0}, p1 = p0, p2 = p0, p3 = p0;
+        const uint32_t w2 = lcv_ld_vol(V.sbits + (key2 >> 4));
+        // ---- ... while the coder renormalises (:295-303) and handles underflow (:306-309): closed form, the
+        // d+e new bits come straight from the top of the bit window
+        {
+            const int d = __clz((int)(lo ^ hi)); // leading bits low and high share
+            const uint32_t lo_d = __funnelshift_lc(0u, lo, d), hi_d = __funnelshift_lc(0xffffffffu, hi, d);
+            const int e = __clz((int)~((lo_d & ~hi_d) << 1)); // underflow steps: low = 01.., high = 10..
+            const int t = d + e;
+            const uint32_t em = e ? 0x80000000u : 0u;
+            if (t <= 32) {
+                code = __funnelshift_lc((uint32_t)(br.win >> 32), code, t) ^ em;
+                lcv_br_skip(br, t);
+            } else {
+                const uint32_t b1 = lcv_br_take(br, d);
+                code = __funnelshift_lc(0u, code, d) | b1;
+                const uint32_t b2 = lcv_br_take(br, e);
+                code = ((code << e) | b2) ^ em;
+            }
+            lo = __funnelshift_lc(0u, lo_d, e) & ~em;
+            hi = __funnelshift_lc(0xffffffffu, hi_d, e) | em;
+        }
+        // ---- the data the next context's state needs (loaded straight into the registers the next iteration reads)
+        int st2 = (int)((w2 >> shift2) & 3u);
         bool pend2 = key2 == key; // this symbol's own update of the same context comes first
         if (st2 != 0 && !pend2) {
             // a job on that context among the last LCV_RING posted ones may still be running
             pend2 = __ballot_sync(LC_FULL_MASK, P.my_key == key2) != 0u;
-            if (!pend2) LCV_PREFETCH(st2, key2, gw2, p0, p1, p2, p3);
-        }
-        // ---- renormalise (:295-303) and underflow (:306-309): closed form, one read of d+e bits
-        {
-            const int d = __clz((int)(lo ^ hi)); // leading bits low and high share
-            const uint32_t lo_d = (uint32_t)((unsigned long long)lo << d);
-            const uint32_t hi_d = ~(uint32_t)((unsigned long long)(~hi) << d);
-            const int e = __clz((int)~((lo_d & ~hi_d) << 1)); // underflow steps: low = 01.., high = 10..
-            const int t = d + e;
-            if (t) {
-                if (t <= 32) {
-                    const uint32_t bits = lcv_br_take(br, t);
-                    code = (uint32_t)((unsigned long long)code << t) | bits;
-                } else {
-                    const uint32_t b1 = lcv_br_take(br, d);
-                    code = (uint32_t)((unsigned long long)code << d) | b1;
-                    const uint32_t b2 = lcv_br_take(br, e);
-                    code = (code << e) | b2;
-                }
-                lo = (uint32_t)((unsigned long long)lo_d << e);
-                hi = ~(uint32_t)((unsigned long long)(~hi_d) << e);
-                if (e) { lo &= 0x7fffffffu; hi |= 0x80000000u; code ^= 0x80000000u; }
-            }
+            if (!pend2) LCV_PREFETCH(st2, key2, gw, q0, q1, q2, q3);
         }
         LCP_MARK(2);
         // ---- this context's model moves on
@@ -570,9 +583,9 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             __syncwarp();
             LCV_FENCE();
             st2 = (int)((lcv_ld_vol(V.sbits + (key2 >> 4)) >> shift2) & 3u);
-            LCV_PREFETCH(st2, key2, gw2, p0, p1, p2, p3);
+            LCV_PREFETCH(st2, key2, gw, q0, q1, q2, q3);
         }
-        key = key2; c = c2; r = r2; st = st2; gw = gw2; q0 = p0; q1 = p1; q2 = p2; q3 = p3;
+        key = key2; c = c2; r = r2; st = st2;
         LCP_MARK(3);
     }
     LCP_FLUSH();
@@ -622,7 +635,7 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
     F.u1tab = V.u1tab; F.rows = (unsigned short *)0;
     F.k = 0; F.u = F.u0; F.my_sym = 0x7fffffff; F.my_val = 0.0;
     if (threadIdx.x < 64) V.u1tab[threadIdx.x] = tables[threadIdx.x];
-    if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = 0u; }
+    if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = threadIdx.x - LCV_RING + 1u; }
     LcvPost P; P.njobs = 0u; P.my_key = LCV_SENTINEL; P.my_job = 0u;
     uint32_t ujob = (uint32_t)(warp > 0 ? warp - 1 : 0);
     const uint32_t nwords = (vc.nkeys + 15u) / 16u;

@@ -196,6 +196,12 @@ static inline unsigned int atomicXor(unsigned int *p, unsigned int v) { unsigned
 static inline unsigned int atomicCAS(unsigned int *p, unsigned int c, unsigned int v) { unsigned int o = *p; if (o == c) *p = v; return o; }
 struct double2 { double x, y; };
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline unsigned int __funnelshift_lc(unsigned int lo, unsigned int hi, unsigned int sh)
+{
+    if (sh > 32u) sh = 32u;
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    return sh == 32u ? lo : (unsigned int)((v << sh) >> 32);
+}
 static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((uint64_t)a * b) >> 32); }
 static inline long long __double_as_longlong(double d) { long long b; memcpy(&b, &d, 8); return b; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }
