@@ -292,7 +292,9 @@ __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const 
         }
         keys[i] = k;
     }
-    LcBlockSort(temp).Sort(keys, vals, 0, 22); // real keys < 2^21; padding (low 22 bits all ones) sorts last
+    // real keys are below (n+1)^2 < 2^key_bits; the padding key (all ones in those bits) sorts last
+    const int key_bits = 32 - __clz((n + 1) * (n + 1));
+    LcBlockSort(temp).Sort(keys, vals, 0, key_bits);
     uint32_t *ok = skeys + (size_t)blockIdx.x * LC_PAR_MAX_SYMBOLS + (size_t)threadIdx.x * ITEMS;
     unsigned short *ov = spos + (size_t)blockIdx.x * LC_PAR_MAX_SYMBOLS + (size_t)threadIdx.x * ITEMS;
 #pragma unroll

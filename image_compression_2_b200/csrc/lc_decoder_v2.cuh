@@ -418,17 +418,27 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         int s = 0, s1 = 0;
         uint32_t nlo = 0u, nhi = 0u;
         bool done = false;
+        // The next position's context key needs only the symbol: as soon as a path has its candidate, the state
+        // word of that context is requested from shared memory, so the load overlaps the bounds arithmetic.
+        uint32_t key2 = 0u, w2 = 0u;
+#define LCV_NEXT_CTX(sym_)                                                                                \
+    do {                                                                                                  \
+        key2 = (uint32_t)((c2 > 0 ? (sym_) : -1) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);          \
+        w2 = lcv_ld_vol(V.sbits + (key2 >> 4));                                                           \
+    } while (0)
         if (st == 0) {
             if (pre_ok) {
                 // uniform model: cum[i] = i/n exactly, so range*cum is exact and everything is integer work.
                 // With a = (code-low+1)*n and E = 1e-10*n*range, the symbol is the s with
                 // s*range < a - E (+- 3e-4) <= (s+1)*range; candidate from a float quotient, checked with margins.
-                const int cand = (int)((float)off * lcv_rcp_f32((float)rng1) * (float)n);
+                int cand = (int)((float)off * lcv_rcp_f32((float)rng1) * (float)n);
+                cand = cand > n - 1 ? n - 1 : cand; // (float)off rounds up to 2^32 at most: cand <= n
+                LCV_NEXT_CTX(cand);
                 const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
                 const unsigned long long above = below + rng1 + 1ull;
                 const unsigned long long a = ((unsigned long long)off + 1ull) << V.lg_n;
                 const unsigned long long e_lo = (unsigned long long)(__umulhi(rng1, V.eps_k) >> 8); // <= E < e_lo + 3
-                if (cand >= 0 && cand < n && below + e_lo + 4ull <= a && a + 1ull <= above + e_lo) {
+                if (below + e_lo + 4ull <= a && a + 1ull <= above + e_lo) {
                     s = cand; done = true;
                     nlo = lo + (uint32_t)(below >> V.lg_n);
                     nhi = lo + (uint32_t)(above >> V.lg_n) - 1u;
@@ -448,6 +458,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
                 else if (va <= B0) sc = s1;
                 else sc = s1 + 1 + (int)((va - B0) * ru);
                 sc = sc < 0 ? 0 : (sc > n - 1 ? n - 1 : sc);
+                LCV_NEXT_CTX(sc);
                 const double *row = V.cum1 + (size_t)s1 * (n + 1);
                 const double clo = __ldg(row + sc), chi = __ldg(row + sc + 1);
                 const double xl = LC_DMUL(rd, clo), xh1 = LC_DMUL(rd, chi);
@@ -511,6 +522,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
 #pragma unroll
             for (int j = 0; j < LCV_INLINE_K; j++) if (lane == j && j < k) { F.my_sym = sym[j]; F.my_val = val[j]; }
             if (decided) {
+                LCV_NEXT_CTX(iv.sym);
                 lcf_apply_symbol(F, iv, nd, rd, lo, hi);
                 nlo = lo; nhi = hi; s = iv.sym; done = true;
             }
@@ -524,18 +536,26 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             double num, rdv;
             const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
             if (fs != LC_OK) { status = fs; break; }
+            LCV_NEXT_CTX(iv.sym);
             lcf_apply_symbol(F, iv, num, rdv, lo, hi);
             nlo = lo; nhi = hi; s = iv.sym;
         }
+#undef LCV_NEXT_CTX
         lo = nlo; hi = nhi;
         LCP_MARK(1);
-        // ---- next position's context (get_context :78-117): its state word is requested now ...
+        // ---- next position's context (get_context :78-117): the data its state needs is requested now (loaded
+        // straight into the registers the next iteration reads) and arrives during renormalisation and write-back
         if (lane == 0) V.rows[(r & 1) * C + c] = (unsigned char)s;
-        const uint32_t key2 = (uint32_t)((c2 > 0 ? s : -1) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);
         const uint32_t shift2 = (key2 & 15u) * 2u;
-        const uint32_t w2 = lcv_ld_vol(V.sbits + (key2 >> 4));
-        // ---- ... while the coder renormalises (:295-303) and handles underflow (:306-309): closed form, the
-        // d+e new bits come straight from the top of the bit window
+        int st2 = (int)((w2 >> shift2) & 3u);
+        bool pend2 = key2 == key; // this symbol's own update of the same context comes first
+        if (st2 != 0 && !pend2) {
+            // a job on that context among the last LCV_RING posted ones may still be running
+            pend2 = __ballot_sync(LC_FULL_MASK, P.my_key == key2) != 0u;
+            if (!pend2) LCV_PREFETCH(st2, key2, gw, q0, q1, q2, q3);
+        }
+        // ---- renormalise (:295-303) and underflow (:306-309): closed form, the d+e new bits come straight from
+        // the top of the bit window
         {
             const int d = __clz((int)(lo ^ hi)); // leading bits low and high share
             const uint32_t lo_d = __funnelshift_lc(0u, lo, d), hi_d = __funnelshift_lc(0xffffffffu, hi, d);
@@ -553,14 +573,6 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             }
             lo = __funnelshift_lc(0u, lo_d, e) & ~em;
             hi = __funnelshift_lc(0xffffffffu, hi_d, e) | em;
-        }
-        // ---- the data the next context's state needs (loaded straight into the registers the next iteration reads)
-        int st2 = (int)((w2 >> shift2) & 3u);
-        bool pend2 = key2 == key; // this symbol's own update of the same context comes first
-        if (st2 != 0 && !pend2) {
-            // a job on that context among the last LCV_RING posted ones may still be running
-            pend2 = __ballot_sync(LC_FULL_MASK, P.my_key == key2) != 0u;
-            if (!pend2) LCV_PREFETCH(st2, key2, gw, q0, q1, q2, q3);
         }
         LCP_MARK(2);
         // ---- this context's model moves on

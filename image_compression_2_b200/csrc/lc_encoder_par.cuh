@@ -167,34 +167,34 @@ __device__ __forceinline__ long long lc_enc_phase_b_stream(LcWarp &W, const doub
 }
 
 // Phase B, repaired mode: low/high stay below 2^32, so the state is two uint32, the
-// renormalisation/underflow loops are clz counts, and bits are appended many at a time to a 64-bit
-// accumulator.  Same arithmetic as lc_enc_phase_b_stream, ~4x fewer instructions on the serial chain.
-struct LcBits64 {
+// renormalisation/underflow loops are clz counts and funnel shifts, and bits are appended many at a time.
+// Everything is warp-uniform (every lane runs the same scalar chain; lane 0 stores): the interval of symbol
+// pos+2 is requested with one 16-byte load by all lanes while symbol pos is coded.
+struct LcBits32 {
     uint32_t *out;
     uint32_t cap_words, wpos;
-    unsigned long long acc; // the low `nacc` bits are pending output, nacc < 32 between calls
+    uint32_t acc; // the low `nacc` bits are pending output, nacc < 32 between calls
     int nacc, ovf;
-    long long nbits;
 };
-// append the low nb bits of v, nb in 1..32
-__device__ __forceinline__ void lc_b64_put(LcBits64 &b, uint32_t v, int nb, int lane)
+// append the low nb bits of v (nb in 1..32, v < 2^nb)
+__device__ __forceinline__ void lc_b32_put(LcBits32 &b, uint32_t v, int nb, int lane)
 {
-    b.acc = (b.acc << nb) | v;
-    b.nacc += nb;
-    b.nbits += nb;
-    if (b.nacc >= 32) {
-        b.nacc -= 32;
-        const uint32_t word = (uint32_t)(b.acc >> b.nacc);
+    const unsigned long long comb = ((unsigned long long)b.acc << nb) | v;
+    const int tot = b.nacc + nb;
+    if (tot >= 32) {
+        const uint32_t word = (uint32_t)(comb >> (tot - 32));
         if (b.wpos < b.cap_words) { if (lane == 0) b.out[b.wpos] = __byte_perm(word, 0, 0x0123); }
         else b.ovf = 1;
         b.wpos++;
-    }
+        b.nacc = tot - 32;
+        b.acc = (uint32_t)comb & ((1u << b.nacc) - 1u);
+    } else { b.acc = (uint32_t)comb; b.nacc = tot; }
 }
-__device__ __forceinline__ void lc_b64_put_run(LcBits64 &b, int bit, long long count, int lane)
+__device__ __forceinline__ void lc_b32_put_run(LcBits32 &b, int bit, int count, int lane)
 {
     while (count > 0) {
-        const int take = count > 32 ? 32 : (int)count;
-        lc_b64_put(b, bit ? (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) : 0u, take, lane);
+        const int take = count > 32 ? 32 : count;
+        lc_b32_put(b, bit ? (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) : 0u, take, lane);
         count -= take;
     }
 }
@@ -203,66 +203,56 @@ __device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const dou
                                                              uint32_t *out, uint32_t cap_words, int *status,
                                                              int *fault_index)
 {
-    LcBits64 bw;
-    bw.out = out; bw.cap_words = cap_words; bw.wpos = 0; bw.acc = 0ull; bw.nacc = 0; bw.ovf = 0; bw.nbits = 0;
+    LcBits32 bw;
+    bw.out = out; bw.cap_words = cap_words; bw.wpos = 0; bw.acc = 0u; bw.nacc = 0; bw.ovf = 0;
     uint32_t lo = 0u, hi = 0xffffffffu;
-    long long outstanding = 0;
+    int outstanding = 0, nbits = 0;
     int pos = 0;
-    // The intervals come from DRAM (phase A wrote them) and do not depend on the coder state: each lane
-    // holds one symbol's pair of the current and of the next 32-symbol chunk (coalesced 16-byte loads
-    // issued a whole chunk ahead), and the pair of symbol pos+1 is broadcast while symbol pos is coded.
-    double cur_lo = 0.0, cur_hi = 0.0, nx_lo = 0.0, nx_hi = 0.0;
-    if (lane < limit) { cur_lo = __ldg(ivs + 2 * lane); cur_hi = __ldg(ivs + 2 * lane + 1); }
-    if (32 + lane < limit) { nx_lo = __ldg(ivs + 2 * (32 + lane)); nx_hi = __ldg(ivs + 2 * (32 + lane) + 1); }
-    double c_lo = __shfl_sync(LC_FULL_MASK, cur_lo, 0), c_hi = __shfl_sync(LC_FULL_MASK, cur_hi, 0);
+    const double2 *iv2 = (const double2 *)ivs; // (cum[s], cum[s+1]) per position, 16-byte aligned
+    const double2 zero2 = {0.0, 0.0};
+    double2 cur = limit > 0 ? __ldg(iv2) : zero2;
+    double2 nx1 = limit > 1 ? __ldg(iv2 + 1) : zero2;
     for (; pos < limit; pos++) {
-        const int pn = pos + 1;
-        if ((pn & 31) == 0) { // entering the next chunk: rotate and request the one after it
-            cur_lo = nx_lo; cur_hi = nx_hi;
-            const int q = pn + 32 + lane;
-            if (q < limit) { nx_lo = __ldg(ivs + 2 * q); nx_hi = __ldg(ivs + 2 * q + 1); }
-        }
-        const double n_lo = __shfl_sync(LC_FULL_MASK, cur_lo, pn & 31), n_hi = __shfl_sync(LC_FULL_MASK, cur_hi, pn & 31);
+        const double2 nx2 = pos + 2 < limit ? __ldg(iv2 + pos + 2) : zero2;
         // encode_symbol (:220-224): high = low + int(range*c_hi - 1), low = low + int(range*c_lo)
         const double rd = lc_ll2d_small((long long)hi - (long long)lo + 1); // 0 when the interval has collapsed (hi = lo-1)
-        const long long ah = LC_D2LL(LC_DSUB(LC_DMUL(rd, c_hi), 1.0));
-        const long long al = LC_D2LL(LC_DMUL(rd, c_lo));
+        const long long ah = LC_D2LL(LC_DSUB(LC_DMUL(rd, cur.y), 1.0));
+        const long long al = LC_D2LL(LC_DMUL(rd, cur.x));
         hi = lo + (uint32_t)ah;
         lo = lo + (uint32_t)al;
-        const int d = __clz((int)(lo ^ hi));
+        const int d = __clz((int)(lo ^ hi)); // leading bits low and high share: that many bits are emitted
         if (d) {
-            if (outstanding == 0) lc_b64_put(bw, hi >> (32 - d), d, lane);
+            nbits += d + outstanding;
+            if (outstanding == 0) lc_b32_put(bw, hi >> (32 - d), d, lane);
             else {
                 const int b1 = (int)(hi >> 31);
-                lc_b64_put(bw, (uint32_t)b1, 1, lane);
-                lc_b64_put_run(bw, 1 - b1, outstanding, lane);
+                lc_b32_put(bw, (uint32_t)b1, 1, lane);
+                lc_b32_put_run(bw, 1 - b1, outstanding, lane);
                 outstanding = 0;
-                if (d > 1) lc_b64_put(bw, (hi << 1) >> (33 - d), d - 1, lane);
+                if (d > 1) lc_b32_put(bw, (hi << 1) >> (33 - d), d - 1, lane);
             }
-            if (d == 32) { lo = 0u; hi = 0xffffffffu; }
-            else { lo <<= d; hi = (hi << d) | ((1u << d) - 1u); }
         }
-        const int e = __clz((int)~((lo & ~hi) << 1));
-        if (e) {
-            outstanding += e;
-            lo = (lo << e) & 0x7fffffffu;
-            hi = ((hi << e) & 0x7fffffffu) | 0x80000000u | ((1u << e) - 1u);
-        }
+        const uint32_t lo_d = __funnelshift_lc(0u, lo, d), hi_d = __funnelshift_lc(0xffffffffu, hi, d);
+        const int e = __clz((int)~((lo_d & ~hi_d) << 1)); // underflow steps: low = 01.., high = 10..
+        const uint32_t em = e ? 0x80000000u : 0u;
+        outstanding += e;
+        lo = __funnelshift_lc(0u, lo_d, e) & ~em;
+        hi = __funnelshift_lc(0xffffffffu, hi_d, e) | em;
         if (bw.ovf) break;
-        c_lo = n_lo; c_hi = n_hi;
+        cur = nx1; nx1 = nx2;
     }
     *fault_index = pos;
     if (bw.ovf) { *status = LC_OUT_OVERFLOW; return 0; }
     // finish_encoding (:230-245)
     outstanding += 1;
     const int first = (lo & 0x40000000u) != 0 ? 1 : 0;
-    lc_b64_put(bw, (uint32_t)first, 1, lane);
-    lc_b64_put_run(bw, 1 - first, outstanding, lane);
-    const long long nbits = bw.nbits;
-    if (bw.nacc > 0) lc_b64_put(bw, 0u, 32 - bw.nacc, lane); // zero-pad the last word
+    lc_b32_put(bw, (uint32_t)first, 1, lane);
+    lc_b32_put_run(bw, 1 - first, outstanding, lane);
+    nbits += 1 + outstanding;
+    if (bw.nacc > 0) lc_b32_put(bw, 0u, 32 - bw.nacc, lane); // zero-pad the last word
     if (bw.ovf) { *status = LC_OUT_OVERFLOW; return 0; }
     *status = LC_OK;
-    return nbits;
+    return (long long)nbits;
 }
 
 // ---- block entry points --------------------------------------------------------------------------
