@@ -359,7 +359,7 @@ def run_b200(args):
         dec_ms = sum(t_dec) / len(t_dec)
         facts = {}
         try:
-            facts = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_facts.json"))).get("lc_fast_decode_kernel", {})
+            facts = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_facts.json"))).get("lc_decode_v2_kernel", {})
         except Exception:
             pass
         same_cfg = facts.get("streams") == B and facts.get("n_symbols") == n
@@ -375,8 +375,9 @@ def run_b200(args):
                        "parity": parity_note, "streams_per_s": value / SYMS},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(res["h2d_bytes"]),
                     "d2h_bytes_per_step": int(res["d2h_bytes"]), "ms_per_step": 1e3 * float(e_total) / args.steps},
-            "gpu_launches": 8 * args.steps,
-            "roofline": {"kernel": "lc_fast_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            # per step: quantise, tables, sort, phase A, phase B, size scan, compaction, tables, decode, redo pass
+            "gpu_launches": 10 * args.steps,
+            "roofline": {"kernel": "lc_decode_v2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": facts.get("dram_bytes_per_launch") if same_cfg else None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
@@ -384,10 +385,10 @@ def run_b200(args):
                          "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms_total / args.steps),
                          "warp_inst_per_symbol": facts.get("warp_inst_per_symbol") if same_cfg else None,
                          "issue_slot_utilisation": facts.get("issue_slot_utilisation") if same_cfg else None,
-                         "ncu": "profiles/r01_ncu_all_kernels_v5.md",
+                         "ncu": "profiles/r01_ncu_all_kernels_v6.md",
                          "note": "decode = dependent chain per stream: latency/issue-bound, not HBM-bound "
                                  "(DESIGN.md section 5); traffic above the algorithmic bytes is the per-stream "
-                                 "context table + record pool"},
+                                 "context words + 64-byte records"},
             "clocks": clocks,
             "rank_bytes": [int(x) for x in sizes.tolist()],
         }

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(32) lc_fast_decode_kernel(LcCoderCfg cfg, cons
 
 // Decoder v2 (lc_decoder_v2.cuh): one block per stream = one decoder warp + LCV_NU updater warps; a
 // one-block kernel first fills the per-launch tables (u after the first update, exact cumsum rows).
-__global__ void __launch_bounds__(256) lc_v2_tables_kernel(LcCoderCfg cfg, double *tables)
+__global__ void __launch_bounds__(32) lc_v2_tables_kernel(LcCoderCfg cfg, double *tables)
 {
     extern __shared__ __align__(16) char lc_smem[];
     lcv_tables_block(cfg, tables, lc_smem);
@@ -627,7 +627,7 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
         // per-launch tables (u after the first update, exact cumsum rows of the model after one update)
         double *tables = (double *)((char *)scratch + (((size_t)tile * LC_PAR_STREAM_BYTES + 255) & ~(size_t)255));
         if (sparse_variant) {
-            lc_v2_tables_kernel<<<1, 256, (size_t)(cfg.n + 64) * 8, st>>>(cfg, tables);
+            lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
             LC_CUDA_RET();
         }
         for (int b0 = 0; b0 < B; b0 += LC_PAR_TILE) {
@@ -706,7 +706,7 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
             v2_attr = true;
         }
         if (vc.sm_bytes > 64 * 1024) return -22;
-        lc_v2_tables_kernel<<<1, 256, (size_t)(cfg.n + 64) * 8, st>>>(cfg, tables);
+        lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
         LC_CUDA_RET();
         lc_decode_v2_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits, B,
                                                                      idx_out, deq_table, deq_out, status, fault_index,

@@ -121,31 +121,36 @@ static __device__ __forceinline__ void lcv_bar_wait(unsigned long long *b, uint3
 }
 #endif
 
-// ---- tables kernel body: u after the first update per chain step, its reciprocal, and the exact
-// np.cumsum (:346-347) of the model after one update with s1, for every s1.  One block.
+// ---- tables kernel body, one warp (block) per first symbol s1: u after the first update with s1 (its value
+// depends only on s1's accumulator-chain step; the block of the step's first symbol publishes it with its
+// reciprocal), and the exact np.cumsum (:346-347) of the model after that update.
 __device__ __forceinline__ void lcv_tables_block(const LcCoderCfg &cfg, double *tables, char *smem)
 {
     double *u1g = tables, *ru1g = tables + 32, *cum1 = tables + 64;
-    const int n = cfg.n;
-    if (threadIdx.x < 32) {
-        LcFast F;
-        F.n = n; F.lane = (int)threadIdx.x; F.rate = cfg.rate; F.u0 = LC_DDIV(1.0, (double)n);
-        F.pw_len = cfg.pw_len; F.pw_steps = cfg.pw_steps; F.pw_chains = cfg.pw_chains;
-        F.dense = (double *)smem; F.u1tab = (double *)smem + n;
-        lcf_tables_init(F);
-        const int entries = F.pw_chains == 0 ? n : F.pw_steps;
-        if (F.lane < entries) { u1g[F.lane] = F.u1tab[F.lane]; ru1g[F.lane] = lc_rcp_fast(F.u1tab[F.lane]); }
-    }
-    __syncthreads();
-    const double u0 = LC_DDIV(1.0, (double)n);
-    const double P1 = LC_DADD(u0, LC_DMUL(cfg.rate, LC_DSUB(1.0, u0)));
-    const double *u1s = (const double *)smem + n;
-    for (int s1 = (int)threadIdx.x; s1 < n; s1 += (int)blockDim.x) {
-        const double u = u1s[cfg.pw_chains == 0 ? s1 : ((s1 & (cfg.pw_len - 1)) >> 3)];
-        double *row = cum1 + (size_t)s1 * (n + 1);
-        double T = 0.0;
-        row[0] = 0.0;
-        for (int i = 0; i < n; i++) { T = LC_DADD(T, i == s1 ? P1 : u); row[i + 1] = T; }
+    const int n = cfg.n, lane = (int)(threadIdx.x & 31);
+    LcFast F;
+    F.n = n; F.lane = lane; F.rate = cfg.rate; F.u0 = LC_DDIV(1.0, (double)n);
+    F.pw_len = cfg.pw_len; F.pw_steps = cfg.pw_steps; F.pw_chains = cfg.pw_chains;
+    F.dense = (double *)smem;
+    const double P1 = LC_DADD(F.u0, LC_DMUL(F.rate, LC_DSUB(1.0, F.u0)));
+    for (int s1 = (int)blockIdx.x; s1 < n; s1 += (int)gridDim.x) {
+        // ContextModel.update_model (:119-144) on the uniform vector
+        for (int i = lane; i < n; i += 32) F.dense[i] = (i == s1) ? P1 : F.u0;
+        __syncwarp();
+        const double total = lcf_pairwise_total(F);
+        const double others = LC_DSUB(total, P1);
+        const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, P1), others) : 0.0;
+        const double u = LC_DMUL(F.u0, f);
+        __syncwarp();
+        const int t = cfg.pw_chains == 0 ? s1 : ((s1 & (cfg.pw_len - 1)) >> 3);
+        const bool publishes = cfg.pw_chains == 0 ? true : (s1 == 8 * t);
+        if (lane == 0 && publishes) { u1g[t] = u; ru1g[t] = lc_rcp_fast(u); }
+        if (lane == 0) {
+            double *row = cum1 + (size_t)s1 * (n + 1);
+            double T = 0.0;
+            row[0] = 0.0;
+            for (int i = 0; i < n; i++) { T = LC_DADD(T, i == s1 ? P1 : u); row[i + 1] = T; }
+        }
     }
 }
 

@@ -247,7 +247,7 @@ extern "C" int hostsim_decode_v2(const unsigned char *bytes, const long long *of
     a.d.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     a.tables = tables.data();
     a.scratch2 = (char *)(((uintptr_t)scratch2.data() + 255) & ~(uintptr_t)255);
-    emu::run_block(decv2_tables_body, &a, 0u, 1u, 8u);
+    for (int b = 0; b < 3; b++) emu::run_warp(decv2_tables_body, &a, (unsigned)b, 3u);
     for (int b = 0; b < grid; b++) emu::run_block(decv2_body, &a, (unsigned)b, (unsigned)grid, LCV_WARPS);
     int redo = 0;
     for (int b = 0; b < B; b++) redo += status[b] == LC_NEEDS_GENERIC;
@@ -350,7 +350,7 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
                (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15), glist.data(), ngroups.data(), &task_counter,
                tables.data()};
     if (nwarps == 0) { // sparse variant: second visits from the table, one warp per context visited three times or more
-        emu::run_block(para_tables_body, &a, 0u, 1u, 8u);
+        for (int b = 0; b < 3; b++) emu::run_warp(para_tables_body, &a, (unsigned)b, 3u);
         for (int b = 0; b < grid; b++) emu::run_warp(glist_body, &a, (unsigned)b, (unsigned)grid);
         for (int b = 0; b < grid; b++)
             for (int w = 0; w < 2; w++) emu::run_warp(para_lanes_body, &a, (unsigned)b, (unsigned)grid, (unsigned)w, 2u);
