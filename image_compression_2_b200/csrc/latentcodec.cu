@@ -14,6 +14,7 @@
 #include "lc_decoder_fast.cuh"
 #include "lc_decoder_v2.cuh"
 #include "lc_encoder_sparse.cuh"
+#include "lc_encoder_pack.cuh"
 
 #define LC_CUDA_RET()                                                     \
     do {                                                                  \
@@ -386,6 +387,22 @@ __global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int 
     lc_enc_phase_b_block(cfg, B, first_bad, ivs, slots, slot_bytes, nbits, status, fault);
 }
 
+// phase B split (lc_encoder_pack.cuh): B1 = the serial (low, high) recurrence, B2 = parallel bit placement
+__global__ void __launch_bounds__(32) lc_enc_phase_b1_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
+                                                             double *ivs, int *first_out)
+{
+    lc_enc_phase_b1_block(cfg, B, first_bad, ivs, first_out);
+}
+
+__global__ void __launch_bounds__(LC_B2_THREADS) lc_enc_phase_b2_kernel(LcCoderCfg cfg, int B,
+                                                                        const int *__restrict__ first_bad,
+                                                                        const double *__restrict__ ivs, unsigned char *slots,
+                                                                        uint32_t slot_bytes, int *nbits, int *status, int *fault)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lc_enc_phase_b2_block(cfg, B, first_bad, ivs, slots, slot_bytes, nbits, status, fault, lc_smem);
+}
+
 // =================================================================================================
 // K4: stream compaction -- exclusive scan of the 16-byte-aligned stream sizes, then a word copy
 // =================================================================================================
@@ -615,6 +632,7 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
         if (!attr_done) {
             cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
             cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
+            cudaFuncSetAttribute(lc_enc_phase_b2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             cudaFuncSetAttribute(lc_enc_phase_a_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  LCS_BLOCK_WARPS * 1024 * 8);
             const char *e = getenv("LC_PHASE_A");
@@ -655,8 +673,18 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
                 lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
             }
             LC_CUDA_RET();
-            lc_enc_phase_b_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, ivs, slots + (size_t)b0 * slot_bytes,
-                                                    (uint32_t)slot_bytes, out_nbits + b0, status + b0, fault_index + b0);
+            const size_t b2_smem = (size_t)slot_bytes + 4 + 24 * 4;
+            if (cfg.mode == LC_MODE_REPAIRED && b2_smem <= 96 * 1024) {
+                // B1: the serial recurrence (leaves its first finish bit in out_nbits); B2: parallel bit placement
+                lc_enc_phase_b1_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, ivs, out_nbits + b0);
+                LC_CUDA_RET();
+                lc_enc_phase_b2_kernel<<<nb, LC_B2_THREADS, b2_smem, st>>>(cfg, nb, first_bad, ivs,
+                                                                           slots + (size_t)b0 * slot_bytes, (uint32_t)slot_bytes,
+                                                                           out_nbits + b0, status + b0, fault_index + b0);
+            } else {
+                lc_enc_phase_b_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, ivs, slots + (size_t)b0 * slot_bytes,
+                                                        (uint32_t)slot_bytes, out_nbits + b0, status + b0, fault_index + b0);
+            }
             LC_CUDA_RET();
         }
     } else {

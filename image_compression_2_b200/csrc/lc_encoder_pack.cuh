@@ -1,0 +1,228 @@
+// Phase B of the parallel encoder in two kernels (repaired coder mode).
+//
+// ArithmeticCoder.encode_symbol / _renormalize_encoder / _handle_underflow / finish_encoding
+// (cabac_compression.py:189-245) have one truly serial part -- the (low, high) recurrence -- and one part that is
+// serial only in the reference's formulation: appending the emitted bits.  Measured on the benchmark the fused
+// loop ran at ~500 cycles/symbol for a recurrence whose dependent chain is ~120 cycles, because every in-order
+// instruction of the bit writer sits between two steps of the chain.  So:
+//   B1  one warp per stream, serial: the recurrence only.  Per symbol it leaves an 8-byte record
+//       (high after the interval update | d << 32 | e << 40): the d leading bits low and high share are the bits
+//       that symbol emits, e is its count of underflow steps.  Records overwrite the first half of the symbol's
+//       (cum[s], cum[s+1]) pair, which has been consumed by then.
+//   B2  one 256-thread block per stream, parallel: the emitted string of symbol i is
+//       [b][pending_i x !b][d_i - 1 more bits] with pending_i = the e's accumulated since the previous emitting
+//       symbol -- a segmented sum; bit offsets are a prefix sum of the lengths.  Two block scans, then every thread
+//       ORs its 32 symbols' bits into a shared-memory image of the stream, which is written out coalesced
+//       (MSB-first bytes, zero-padded).  This is the warp/block scan formulation of "bitstream-offset compaction".
+// The bitstream is bit-identical to the serial writer's by construction (same bits, same order).
+#pragma once
+#include "lc_encoder_par.cuh"
+
+#define LC_B2_THREADS 256
+#define LC_B2_ITEMS (LC_PAR_MAX_SYMBOLS / LC_B2_THREADS)
+
+// ---- B1: the (low, high) recurrence.  `pairs`: in (cum[s], cum[s+1]) per position; out: record in the first 8 bytes.
+// Returns the first bit of finish_encoding (low's second-highest bit).
+__device__ __forceinline__ int lc_enc_b1_stream(int lane, double *pairs, int limit)
+{
+    uint32_t lo = 0u, hi = 0xffffffffu;
+    const double2 *iv2 = (const double2 *)pairs;
+    unsigned long long *rec = (unsigned long long *)pairs;
+    const double2 zero2 = {0.0, 0.0};
+    // one symbol of the recurrence
+#define LC_B1_STEP(iv_, pos_)                                                                                       \
+    do {                                                                                                            \
+        /* encode_symbol (:220-224): high = low + int(range*c_hi - 1), low = low + int(range*c_lo) */               \
+        const double rd_ = lc_ll2d_small((long long)hi - (long long)lo + 1); /* 0 when the interval has collapsed */ \
+        const long long ah_ = LC_D2LL(LC_DSUB(LC_DMUL(rd_, (iv_).y), 1.0));                                         \
+        const long long al_ = LC_D2LL(LC_DMUL(rd_, (iv_).x));                                                       \
+        hi = lo + (uint32_t)ah_;                                                                                    \
+        lo = lo + (uint32_t)al_;                                                                                    \
+        const int d_ = __clz((int)(lo ^ hi)); /* leading bits low and high share: that many bits are emitted */     \
+        const uint32_t lo_d_ = __funnelshift_lc(0u, lo, d_), hi_d_ = __funnelshift_lc(0xffffffffu, hi, d_);         \
+        const int e_ = __clz((int)~((lo_d_ & ~hi_d_) << 1)); /* underflow steps: low = 01.., high = 10.. */         \
+        if (lane == 0)                                                                                              \
+            rec[2 * (pos_)] = (unsigned long long)hi | ((unsigned long long)(uint32_t)(d_ | (e_ << 8)) << 32);      \
+        const uint32_t em_ = e_ ? 0x80000000u : 0u;                                                                 \
+        lo = __funnelshift_lc(0u, lo_d_, e_) & ~em_;                                                                \
+        hi = __funnelshift_lc(0xffffffffu, hi_d_, e_) | em_;                                                        \
+    } while (0)
+    // groups of four symbols: the next group's intervals are requested before the current group is coded, so no
+    // instruction of the chain waits for a load
+    double2 c0 = limit > 0 ? iv2[0] : zero2, c1 = limit > 1 ? iv2[1] : zero2;
+    double2 c2 = limit > 2 ? iv2[2] : zero2, c3 = limit > 3 ? iv2[3] : zero2;
+    for (int g = 0; g < limit; g += 4) {
+        const double2 n0 = g + 4 < limit ? iv2[g + 4] : zero2, n1 = g + 5 < limit ? iv2[g + 5] : zero2;
+        const double2 n2 = g + 6 < limit ? iv2[g + 6] : zero2, n3 = g + 7 < limit ? iv2[g + 7] : zero2;
+        LC_B1_STEP(c0, g);
+        if (g + 1 < limit) LC_B1_STEP(c1, g + 1);
+        if (g + 2 < limit) LC_B1_STEP(c2, g + 2);
+        if (g + 3 < limit) LC_B1_STEP(c3, g + 3);
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+#undef LC_B1_STEP
+    return (lo & 0x40000000u) != 0u ? 1 : 0;
+}
+
+// ---- B2 helpers: block-wide scans over LC_B2_THREADS threads (warp shuffles + one shared array)
+__device__ __forceinline__ int lc_b2_excl_sum(int v, int *sm /*[8]*/, int &total)
+{
+    const int lane = (int)(threadIdx.x & 31), wid = (int)(threadIdx.x >> 5);
+    int incl = v;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(LC_FULL_MASK, incl, off);
+        if (lane >= off) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) sm[wid] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < LC_B2_THREADS / 32; w++) { const int x = sm[w]; if (w < wid) base += x; tot += x; }
+    total = tot;
+    return base + incl - v;
+}
+// segmented sum: element = (flag: the segment restarts inside this element, sum: e's after the last restart, or all
+// of them).  Returns the pending count carried INTO this thread's chunk; `all` = the count after the last chunk.
+__device__ __forceinline__ int lc_b2_excl_seg(int flag, int sum, int *smf, int *sms /*[8] each*/, int &all)
+{
+    const int lane = (int)(threadIdx.x & 31), wid = (int)(threadIdx.x >> 5);
+    int f = flag, s = sum; // inclusive scan within the warp
+    for (int off = 1; off < 32; off <<= 1) {
+        const int pf = __shfl_up_sync(LC_FULL_MASK, f, off), ps = __shfl_up_sync(LC_FULL_MASK, s, off);
+        if (lane >= off) { if (!f) s += ps; f |= pf; }
+    }
+    __syncthreads();
+    if (lane == 31) { smf[wid] = f; sms[wid] = s; }
+    __syncthreads();
+    int cf = 0, cs = 0, af = 0, as = 0; // carry into this warp; aggregate of all warps
+    for (int w = 0; w < LC_B2_THREADS / 32; w++) {
+        const int wf = smf[w], ws = sms[w];
+        if (w < wid) { cs = wf ? ws : cs + ws; cf |= wf; }
+        as = wf ? ws : as + ws; af |= wf;
+    }
+    all = as; (void)af; (void)cf;
+    // exclusive value for this lane: inclusive value of the previous lane (or the warp carry for lane 0)
+    int pf = __shfl_up_sync(LC_FULL_MASK, f, 1), ps = __shfl_up_sync(LC_FULL_MASK, s, 1);
+    if (lane == 0) { pf = 0; ps = 0; }
+    return pf ? ps : cs + ps;
+}
+
+// OR the low nb bits of v (nb in 1..32) into the MSB-first bit image at bit offset `off`
+__device__ __forceinline__ void lc_b2_or_bits(uint32_t *img, int off, uint32_t v, int nb)
+{
+    const int w = off >> 5, sh = 32 - (off & 31) - nb;
+    if (sh >= 0) atomicOr(img + w, v << sh);
+    else { atomicOr(img + w, v >> (-sh)); atomicOr(img + w + 1, v << (32 + sh)); }
+}
+__device__ __forceinline__ void lc_b2_or_ones(uint32_t *img, int off, int count)
+{
+    while (count > 0) {
+        const int take = count > 32 ? 32 : count;
+        lc_b2_or_bits(img, off, take == 32 ? 0xffffffffu : ((1u << take) - 1u), take);
+        off += take; count -= take;
+    }
+}
+
+// ---- B2: one block per stream.  smem: uint32 image[cap_words + 1] | int scratch[24]
+__device__ __forceinline__ void lc_enc_b2_block(const double *pairs, int limit, int first, uint32_t *slot,
+                                                uint32_t cap_words, int *nbits_out, int *status_out, int *fault_out,
+                                                char *smem)
+{
+    uint32_t *img = (uint32_t *)smem;
+    int *sc = (int *)(img + cap_words + 1);
+    const unsigned long long *rec = (const unsigned long long *)pairs;
+    const int tid = (int)threadIdx.x;
+    const int p0 = tid * LC_B2_ITEMS;
+    for (uint32_t i = tid; i < cap_words + 1; i += LC_B2_THREADS) img[i] = 0u;
+    // pass 1: this chunk's length (pending count carried in taken as 0), whether it emits, pending count it leaves
+    // (the e's before the chunk's first emitting symbol -- `head` -- join the count carried in: that symbol's run
+    // is carry + head, added once the carry is known)
+    int len0 = 0, has = 0, tail = 0, head = 0;
+    for (int i = 0; i < LC_B2_ITEMS; i++) {
+        const int p = p0 + i;
+        if (p >= limit) break;
+        const uint32_t meta = (uint32_t)(rec[2 * p] >> 32);
+        const int d = (int)(meta & 0xffu), e = (int)((meta >> 8) & 0xffu);
+        if (d) {
+            if (!has) { head = tail; len0 += d; } else len0 += d + tail;
+            has = 1; tail = e;
+        } else tail += e;
+    }
+    if (!has) head = tail;
+    int pend_all = 0;
+    const int carry = lc_b2_excl_seg(has, has ? tail : head, sc, sc + 8, pend_all);
+    const int len = len0 + (has ? carry + head : 0);
+    int body_bits = 0;
+    int off = lc_b2_excl_sum(len, sc + 16, body_bits);
+    // finish_encoding (:230-245): outstanding += 1; first bit, then `outstanding` copies of its inverse
+    const int fin_run = pend_all + 1;
+    const long long total_bits = (long long)body_bits + 1 + fin_run;
+    const bool ovf = (total_bits + 31) / 32 > (long long)cap_words;
+    __syncthreads(); // image cleared by everyone
+    if (ovf) {
+        if (tid == 0) { *status_out = LC_OUT_OVERFLOW; *nbits_out = 0; *fault_out = limit; }
+        return;
+    }
+    // pass 2: place the bits
+    int pend = carry;
+    for (int i = 0; i < LC_B2_ITEMS; i++) {
+        const int p = p0 + i;
+        if (p >= limit) break;
+        const unsigned long long r = rec[2 * p];
+        const uint32_t hi = (uint32_t)r, meta = (uint32_t)(r >> 32);
+        const int d = (int)(meta & 0xffu), e = (int)((meta >> 8) & 0xffu);
+        if (d) {
+            const uint32_t b1 = hi >> 31;
+            if (pend == 0) lc_b2_or_bits(img, off, hi >> (32 - d), d);
+            else {
+                if (b1) lc_b2_or_bits(img, off, 1u, 1);
+                else lc_b2_or_ones(img, off + 1, pend);
+                if (d > 1) lc_b2_or_bits(img, off + 1 + pend, (hi << 1) >> (33 - d), d - 1);
+            }
+            off += d + pend;
+            pend = e;
+        } else pend += e;
+    }
+    if (tid == 0) {
+        if (first) lc_b2_or_bits(img, body_bits, 1u, 1);
+        else lc_b2_or_ones(img, body_bits + 1, fin_run);
+    }
+    __syncthreads();
+    const uint32_t nwords = (uint32_t)((total_bits + 31) / 32);
+    for (uint32_t i = tid; i < nwords; i += LC_B2_THREADS) slot[i] = __byte_perm(img[i], 0, 0x0123); // MSB-first bytes
+    if (tid == 0) { *nbits_out = (int)total_bits; *status_out = LC_OK; *fault_out = limit; }
+}
+
+// ---- block entry points
+// B1: one warp per stream (blockDim.x = 32); first_out[b] = first bit of finish_encoding
+__device__ __forceinline__ void lc_enc_phase_b1_block(const LcCoderCfg &cfg, int B, const int *first_bad, double *ivs,
+                                                      int *first_out)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
+        const int fb = first_bad[sidx];
+        const int first = lc_enc_b1_stream(lane, ivs + 2 * (size_t)sidx * LC_PAR_MAX_SYMBOLS, fb < cfg.total ? fb : cfg.total);
+        if (lane == 0) first_out[sidx] = first;
+        __syncwarp();
+    }
+}
+// B2: one block of LC_B2_THREADS per stream; nbits[b] holds B1's first bit on entry
+__device__ __forceinline__ void lc_enc_phase_b2_block(const LcCoderCfg &cfg, int B, const int *first_bad, const double *ivs,
+                                                      unsigned char *out_slots, uint32_t slot_bytes, int *nbits, int *status,
+                                                      int *fault, char *smem)
+{
+    for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
+        const int fb = first_bad[sidx];
+        const int limit = fb < cfg.total ? fb : cfg.total;
+        const int first = nbits[sidx];
+        __syncthreads(); // everyone has read the first bit (and is done with the previous stream's image)
+        lc_enc_b2_block(ivs + 2 * (size_t)sidx * LC_PAR_MAX_SYMBOLS, limit, first,
+                        (uint32_t *)(out_slots + (size_t)sidx * slot_bytes), slot_bytes / 4, nbits + sidx, status + sidx,
+                        fault + sidx, smem);
+        __syncthreads();
+        if (threadIdx.x == 0 && status[sidx] == LC_OK && fb < cfg.total) {
+            // the serial encoder stops at the first out-of-range symbol
+            status[sidx] = LC_BAD_SYMBOL; fault[sidx] = fb; nbits[sidx] = 0;
+        }
+    }
+}

@@ -14,7 +14,8 @@ SRCS = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "cuda_emul.h"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_par.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_fast.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v2.cuh"),
-        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_sparse.cuh")]
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_sparse.cuh"),
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_pack.cuh")]
 _lib = None
 
 

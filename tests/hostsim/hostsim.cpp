@@ -13,6 +13,7 @@
 #include "../../image_compression_2_b200/csrc/lc_decoder_fast.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_v2.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_sparse.cuh"
+#include "../../image_compression_2_b200/csrc/lc_encoder_pack.cuh"
 #include <algorithm>
 #include <numeric>
 
@@ -308,6 +309,18 @@ static void parb_body(void *p)
     lc_enc_phase_b_block(a->cfg, a->B, a->first_bad, a->ivs, a->out_slots, a->slot_bytes, a->nbits, a->status,
                          a->fault);
 }
+struct ParB2Args { ParBArgs b; char *smem; };
+static void parb1_body(void *p)
+{
+    ParB2Args *a = (ParB2Args *)p;
+    lc_enc_phase_b1_block(a->b.cfg, a->b.B, a->b.first_bad, const_cast<double *>(a->b.ivs), a->b.nbits);
+}
+static void parb2_body(void *p)
+{
+    ParB2Args *a = (ParB2Args *)p;
+    lc_enc_phase_b2_block(a->b.cfg, a->b.B, a->b.first_bad, a->b.ivs, a->b.out_slots, a->b.slot_bytes, a->b.nbits,
+                          a->b.status, a->b.fault, a->smem);
+}
 
 extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int C, int n, double rate, int mode,
                                   unsigned char *out_slots, unsigned slot_bytes, int *nbits, int *status, int *fault,
@@ -358,6 +371,12 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
     for (int b = 0; b < grid; b++)
         for (int w = 0; w < nwarps; w++) emu::run_warp(para_body, &a, (unsigned)b, (unsigned)grid, (unsigned)w, (unsigned)nwarps);
     ParBArgs bb{cfg, B, first_bad.data(), ivs.data(), out_slots, slot_bytes, nbits, status, fault};
+    if (mode == LC_MODE_REPAIRED && nwarps != 1) { // the two-kernel phase B, as the host launches it in this mode
+        std::vector<char> smem2((size_t)slot_bytes + 4 + 24 * 4 + 64);
+        ParB2Args b2{bb, (char *)(((uintptr_t)smem2.data() + 15) & ~(uintptr_t)15)};
+        for (int b = 0; b < grid; b++) emu::run_warp(parb1_body, &b2, (unsigned)b, (unsigned)grid);
+        for (int b = 0; b < grid; b++) emu::run_block(parb2_body, &b2, (unsigned)b, (unsigned)grid, LC_B2_THREADS / 32);
+    } else
     for (int b = 0; b < grid; b++) emu::run_warp(parb_body, &bb, (unsigned)b, (unsigned)grid);
     return 0;
 }
