@@ -248,17 +248,20 @@ __global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_kernel(LcCoder
 
 // =================================================================================================
 // K3-parallel: the encoder split by context group (lc_encoder_par.cuh)
-//   phase S: keys + stable sort by key (one 256-thread block per stream, CUB block radix sort)
+//   phase S: keys + stable sort by key (one block per stream, CUB block radix sort)
 //   phase A: exact intervals per position, one warp per context group, 8 warps per stream
 //   phase B: the serial range coder over those intervals, one warp per stream
 // =================================================================================================
-typedef cub::BlockRadixSort<uint32_t, 256, LC_PAR_MAX_SYMBOLS / 256, unsigned short> LcBlockSort;
-typedef cub::BlockScan<int, 256> LcBlockScan;
+#ifndef LC_SORT_THREADS
+#define LC_SORT_THREADS 1024
+#endif
+typedef cub::BlockRadixSort<uint32_t, LC_SORT_THREADS, LC_PAR_MAX_SYMBOLS / LC_SORT_THREADS, unsigned short> LcBlockSort;
+typedef cub::BlockScan<int, LC_SORT_THREADS> LcBlockScan;
 
 // Also emits what needs no model: the closed-form interval of every first visit (uniform model: cum[i] = i/n) and,
 // when `tables` is given, the interval of every second visit (table of exact cumsums of the model after one update,
 // lcv_tables_block), plus glist/ngroups = the contexts visited at least three times (the work items of phase A).
-__global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const int *__restrict__ codes,
+__global__ void __launch_bounds__(LC_SORT_THREADS) lc_enc_sort_kernel(LcCoderCfg cfg, const int *__restrict__ codes,
                                                           uint32_t *__restrict__ skeys, unsigned short *__restrict__ spos,
                                                           int *__restrict__ first_bad, unsigned short *__restrict__ glist,
                                                           int *__restrict__ ngroups, double *__restrict__ ivs,
@@ -267,12 +270,12 @@ __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const 
     extern __shared__ __align__(16) char lc_smem[];
     LcBlockSort::TempStorage &temp = *reinterpret_cast<LcBlockSort::TempStorage *>(lc_smem);
     __shared__ int s_first_bad;
-    constexpr int ITEMS = LC_PAR_MAX_SYMBOLS / 256;
+    constexpr int ITEMS = LC_PAR_MAX_SYMBOLS / LC_SORT_THREADS;
     const int total = cfg.total, n = cfg.n, C = cfg.C, RC = cfg.R * cfg.C;
     const int *c = codes + (size_t)blockIdx.x * total;
     if (threadIdx.x == 0) s_first_bad = total;
     __syncthreads();
-    for (int p = threadIdx.x; p < total; p += 256) {
+    for (int p = threadIdx.x; p < total; p += LC_SORT_THREADS) {
         const int s = c[p];
         if (s < 0 || s >= n) atomicMin(&s_first_bad, p);
     }
@@ -303,8 +306,8 @@ __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const 
     if (threadIdx.x == 0) first_bad[blockIdx.x] = fb;
 
     // neighbours across thread boundaries: sorted index j = tid*ITEMS + i
-    __shared__ uint32_t s_last[256], s_last2[256], s_first[256], s_first2[256];
-    __shared__ unsigned short s_last_val[256];
+    __shared__ uint32_t s_last[LC_SORT_THREADS], s_last2[LC_SORT_THREADS], s_first[LC_SORT_THREADS], s_first2[LC_SORT_THREADS];
+    __shared__ unsigned short s_last_val[LC_SORT_THREADS];
     __shared__ LcBlockScan::TempStorage scan_temp;
     s_last[threadIdx.x] = keys[ITEMS - 1];
     s_last2[threadIdx.x] = keys[ITEMS - 2];
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(256) lc_enc_sort_kernel(LcCoderCfg cfg, const 
     s_first[threadIdx.x] = keys[0];
     s_first2[threadIdx.x] = keys[1];
     __syncthreads();
-    const bool has_prev = threadIdx.x > 0, has_next = threadIdx.x < 255;
+    const bool has_prev = threadIdx.x > 0, has_next = threadIdx.x < LC_SORT_THREADS - 1;
     const uint32_t prev1 = has_prev ? s_last[threadIdx.x - 1] : 0u, prev2 = has_prev ? s_last2[threadIdx.x - 1] : 0u;
     const unsigned short prev_val = has_prev ? s_last_val[threadIdx.x - 1] : (unsigned short)0;
     const uint32_t next1 = has_next ? s_first[threadIdx.x + 1] : LC_PAR_KEY_PAD;
@@ -659,7 +662,7 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
             int *ngroups = (int *)ws;                         ws += (size_t)nb * 4;
             unsigned int *task_counter = (unsigned int *)ws;
             const int *codes = idx + (size_t)b0 * cfg.total;
-            lc_enc_sort_kernel<<<nb, 256, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs,
+            lc_enc_sort_kernel<<<nb, LC_SORT_THREADS, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs,
                                                            sparse_variant ? tables : (const double *)0);
             LC_CUDA_RET();
             if (sparse_variant) {

@@ -88,6 +88,8 @@ static inline uint64_t lcv_tables_bytes(int n) { return (uint64_t)(64 + (uint64_
 #define LCV_FENCE() ((void)0)
 static inline uint32_t lcv_ld_vol(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 static inline void lcv_st_vol(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+static inline uint32_t lcv_ld_acq(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+static inline void lcv_st_rel(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 static inline void lcv_bar_init(unsigned long long *b) { *(volatile unsigned long long *)b = 0ull; } // completed phases
 static inline void lcv_bar_arrive(unsigned long long *b) { *(volatile unsigned long long *)b += 1ull; }
 static inline void lcv_bar_wait(unsigned long long *b, uint32_t parity)
@@ -99,6 +101,18 @@ static inline void lcv_bar_wait(unsigned long long *b, uint32_t parity)
 #define LCV_FENCE() __threadfence_block()
 static __device__ __forceinline__ uint32_t lcv_ld_vol(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 static __device__ __forceinline__ void lcv_st_vol(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+// acquire load / release store at CTA scope (what the LCV_FENCE + volatile pairs express, without the full
+// MEMBAR.SC the fence compiles to: that one also waits for the decoder's outstanding prefetch loads)
+static __device__ __forceinline__ uint32_t lcv_ld_acq(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+static __device__ __forceinline__ void lcv_st_rel(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 static __device__ __forceinline__ void lcv_bar_init(unsigned long long *b)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
@@ -343,8 +357,7 @@ __device__ __forceinline__ void lcv_post(const LcV2 &V, LcvPost &P, int lane, ui
 {
     const uint32_t j = P.njobs, slot = j & (LCV_RING - 1);
     // the job that used this slot must be finished before the slot is reused (ring_done starts at slot-RING+1)
-    while (lcv_ld_vol(V.ring_done + slot) != j - LCV_RING + 1u) LCV_SPIN();
-    LCV_FENCE();
+    while (lcv_ld_acq(V.ring_done + slot) != j - LCV_RING + 1u) LCV_SPIN();
     if (lane == 0) {
         lcv_st_vol(V.ring_key + slot, key); lcv_st_vol(V.ring_pay + slot, pay);
         lcv_bar_arrive(V.ring_bar + slot);
