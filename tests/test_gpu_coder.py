@@ -226,3 +226,44 @@ def test_cfg4_large_batch_roundtrip():
     assert int(out["dec_status"].abs().sum()) == 0 and torch.equal(out["dec_idx"], out["idx"])
     want = O.quantize_affine(synth_latents("enc_like", 8192, 1000 + 4 * 100000)[:8].numpy(), 8)[1]
     assert np.array_equal(out["deq"][:8].cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_decoder_v2_and_sparse_encoder_special_paths():
+    """The paths the synthetic latents rarely reach: contexts with 7..32 distinct symbols (pool records) and more
+    than 32 (decoder: stream redone by the generic kernel; encoder phase A: dense continuation), small alphabets,
+    short rows, several images sharing a model -- bitstreams and decoded symbols equal the oracle's."""
+    from image_compression_2_b200 import coder
+    rng = np.random.default_rng(31)
+    cases = []
+    wide = np.zeros((3, 4, 400), np.int32)
+    wide[0, :, 0::2] = 7
+    wide[0, :, 1::2] = rng.integers(0, 256, (4, 200))          # > 32 distinct symbols in one context
+    wide[1, :, 0::2] = 5
+    wide[1, :, 1::2] = rng.integers(100, 120, (4, 200))        # 7..20 distinct symbols
+    wide[2] = np.clip(np.round(rng.normal(128, 9, (4, 400))), 0, 255)
+    cases.append((256, wide))
+    for n, shape, sd in ((8, (4, 6, 64), 1.0), (16, (3, 16, 512), 0.6), (128, (3, 8, 200), 9.0), (64, (5, 3, 5), 4.0),
+                         (256, (2, 2, 2000), 30.0)):
+        cases.append((n, np.clip(np.round(rng.normal(n / 2, sd, shape)), 0, n - 1).astype(np.int32)))
+    for n, codes in cases:
+        streams, nbits, status, fault = coder.cabac_encode_batch(codes, n_symbols=n)
+        for b in range(codes.shape[0]):
+            ref = O.encode_stream(codes[b:b + 1], n, "repaired")
+            assert status[b] == 0 and nbits[b] == ref["nbits"] and streams[b] == ref["packed"], (n, b)
+        dec, dst, dfi = coder.cabac_decode_batch(streams, codes.shape, n_symbols=n)
+        for b in range(codes.shape[0]):
+            rd = O.decode_stream(streams[b], n, (1,) + codes.shape[1:], "repaired")
+            k = int(rd["fault_index"]) if rd["status"] else codes[b].size
+            assert dst[b] == rd["status"] and (rd["status"] == 0 or dfi[b] == k), (n, b)
+            assert np.array_equal(dec[b].ravel()[:k], rd["symbols"].ravel()[:k]), (n, b)
+    # the reference's batched call: images share coder and model
+    imgs = np.clip(np.round(rng.normal(32, 3, (3, 4, 64))), 0, 63).astype(np.int32)
+    ref = O.encode_stream(imgs, 64, "repaired")
+    packed, nb = coder.cabac_encode_packed(imgs, coder.ContextModel(64))
+    assert nb == ref["nbits"] and packed == ref["packed"]
+    assert np.array_equal(coder.cabac_decode(packed, coder.ContextModel(64), imgs.shape), imgs)
+    # a tiny output slot is reported, not overrun (two-kernel phase B)
+    from image_compression_2_b200 import codec
+    idx = torch.from_numpy(rng.integers(0, 256, (2, 4, 64)).astype(np.int32)).cuda()
+    enc = codec.encode_batch(idx.reshape(-1), codec.layout_independent((2, 4, 64)), 256, slot_bytes=64)
+    assert enc.status.cpu().tolist() == [5, 5]
