@@ -13,6 +13,7 @@
 #include "lc_encoder_par.cuh"
 #include "lc_decoder_fast.cuh"
 #include "lc_decoder_v2.cuh"
+#include "lc_decoder_v3.cuh"
 #include "lc_encoder_sparse.cuh"
 #include "lc_encoder_pack.cuh"
 
@@ -244,6 +245,19 @@ __global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_kernel(LcCoder
 {
     extern __shared__ __align__(16) char lc_smem[];
     lcv_decode_block(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables, lc_smem);
+}
+
+// Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream
+__global__ void __launch_bounds__(32 * LC3_WARPS, 7) lc_decode_v3_kernel(LcCoderCfg cfg, LcV2Cfg vc,
+                                                                          const unsigned char *__restrict__ bytes,
+                                                                          const long long *__restrict__ offsets,
+                                                                          const int *__restrict__ nbits, int B, int *out,
+                                                                          const float *__restrict__ deq_table,
+                                                                          float *deq_out, int *status, int *fault,
+                                                                          char *scratch, const double *tables)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lc3_decode_block(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables, lc_smem);
 }
 
 // =================================================================================================
@@ -492,12 +506,20 @@ static int lc_grid_for(const LcCoderCfg &cfg, int B)
 static bool lc_use_parallel_encoder(const LcCoderCfg &cfg) { return cfg.has_ctx && cfg.total <= LC_PAR_MAX_SYMBOLS; }
 
 // decoder v2: which kernel decodes (LC_DECODER=fast keeps the previous kernel, for A/B runs), grid, scratch
-static bool lc_use_decoder_v2(const LcCoderCfg &cfg)
+// 0: register-model kernel, 2: v2 (default), 3: v3 -- measured slower than v2 on the benchmark (11.1 vs 10.7 ms/step:
+// the two hand-overs per symbol cost what the decoder warp saves), kept selectable.  LC_DECODER=fast|v2|v3.
+static int lc_decoder_choice()
 {
     static int choice = -1;
-    if (choice < 0) { const char *e = getenv("LC_DECODER"); choice = (e && e[0] == 'f') ? 0 : 1; }
-    return choice == 1 && lcv_eligible(cfg);
+    if (choice < 0) {
+        const char *e = getenv("LC_DECODER");
+        choice = 2;
+        if (e && e[0] == 'f') choice = 0;
+        if (e && e[0] == 'v' && e[1] == '3') choice = 3;
+    }
+    return choice;
 }
+static bool lc_use_decoder_v2(const LcCoderCfg &cfg) { return lc_decoder_choice() != 0 && lcv_eligible(cfg); }
 static int lc_v2_grid(const LcV2Cfg &vc, int B)
 {
     int per_sm = (int)((227u * 1024u) / (vc.sm_bytes + 1024u));
@@ -734,14 +756,20 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
         static bool v2_attr = false;
         if (!v2_attr) {
             cudaFuncSetAttribute(lc_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(lc_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             v2_attr = true;
         }
         if (vc.sm_bytes > 64 * 1024) return -22;
         lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
         LC_CUDA_RET();
-        lc_decode_v2_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits, B,
-                                                                     idx_out, deq_table, deq_out, status, fault_index,
-                                                                     (char *)scratch, tables);
+        if (lc_decoder_choice() == 3 && cfg.total <= (1 << 21))
+            lc_decode_v3_kernel<<<g2, 32 * LC3_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
+                                                                         B, idx_out, deq_table, deq_out, status,
+                                                                         fault_index, (char *)scratch, tables);
+        else
+            lc_decode_v2_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
+                                                                         B, idx_out, deq_table, deq_out, status,
+                                                                         fault_index, (char *)scratch, tables);
         LC_CUDA_RET();
         lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
                                                          deq_table, deq_out, status, fault_index, (char *)scratch,

@@ -43,7 +43,7 @@ struct LcV2Cfg {
     uint32_t eps_k;       // floor(1e-10 * n * 2^40): the -1e-10 of decode_symbol in units of range/2^40
     uint32_t pool_bytes;  // overflow-record pool per block
     // shared memory carve-up
-    uint32_t sm_bits, sm_rows, sm_ring, sm_tab, sm_dense, sm_misc, sm_bytes;
+    uint32_t sm_bits, sm_rows, sm_ring, sm_tab, sm_dense, sm_misc, sm_mail, sm_bytes;
     // per-block global scratch carve-up
     uint64_t g_word, g_rec, g_pool, g_stride;
 };
@@ -67,6 +67,7 @@ static inline void lcv_cfg_make(const LcCoderCfg &c, LcV2Cfg *v)
     v->sm_tab = off;   off += 2 * 32 * 8;              // u1tab[32] | ru1tab[32]
     v->sm_dense = off; off += LCV_NU * (uint32_t)c.n * 8;
     v->sm_misc = off;  off += 16;                      // pool_top | abort
+    v->sm_mail = off;  off += 96;                      // decoder v3: symbol word | packet header | pad | 64 B packet data
     v->sm_bytes = lc_round_up(off, 16);
     uint64_t g = 0;
     v->g_word = g; g += ((uint64_t)v->nkeys * 4 + 255) & ~(uint64_t)255;
@@ -383,6 +384,141 @@ __device__ __forceinline__ bool lcv_gap_search(double u, double ru, double dv, d
     return true;
 }
 
+// decode_symbol (:272-292) for one symbol: the symbol, and low/high after the interval update (before
+// renormalisation), from the context's state st and the data that state needs (gw: the context word for states 1
+// and 3; q0..q3: the inline record for state 2).  on_candidate(sym) is called as soon as a path has its candidate
+// symbol (again with the final symbol if the exact evaluation was needed).  Returns LC_OK or the fault status.
+template <class OnCandidate>
+__device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int st, uint32_t gw, const double2 &q0,
+                                                 const double2 &q1, const double2 &q2, const double2 &q3, uint32_t lo,
+                                                 uint32_t hi, uint32_t code, int &s, int &s1, uint32_t &nlo, uint32_t &nhi,
+                                                 int &fallback, OnCandidate on_candidate)
+{
+    const int lane = F.lane, n = F.n;
+    const double cfix = 1e-10;
+    fallback = 0;
+    // ---- decode_symbol (:272-292)
+    const uint32_t rng1 = hi - lo, off = code - lo; // range-1, (code-low+1)-1
+    const bool pre_ok = hi >= lo && off <= rng1 && rng1 >= 0xffffu;
+    bool done = false;
+    s = 0; s1 = 0; nlo = 0u; nhi = 0u;
+    if (st == 0) {
+        if (pre_ok) {
+            // uniform model: cum[i] = i/n exactly, so range*cum is exact and everything is integer work.
+            // With a = (code-low+1)*n and E = 1e-10*n*range, the symbol is the s with
+            // s*range < a - E (+- 3e-4) <= (s+1)*range; candidate from a float quotient, checked with margins.
+            int cand = (int)((float)off * lcv_rcp_f32((float)rng1) * (float)n);
+            cand = cand > n - 1 ? n - 1 : cand; // (float)off rounds up to 2^32 at most: cand <= n
+            on_candidate(cand);
+            const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
+            const unsigned long long above = below + rng1 + 1ull;
+            const unsigned long long a = ((unsigned long long)off + 1ull) << V.lg_n;
+            const unsigned long long e_lo = (unsigned long long)(__umulhi(rng1, V.eps_k) >> 8); // <= E < e_lo + 3
+            if (below + e_lo + 4ull <= a && a + 1ull <= above + e_lo) {
+                s = cand; done = true;
+                nlo = lo + (uint32_t)(below >> V.lg_n);
+                nhi = lo + (uint32_t)(above >> V.lg_n) - 1u;
+            }
+        }
+    } else if (st == 1) {
+        s1 = (int)(gw & 0x3FFu);
+        if (s1 >= n) s1 = n - 1; // only on a stream already flagged for the generic kernel
+        if (pre_ok) { // model after one update: exact np.cumsum values from the per-launch table
+            const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
+            const int t = lcf_tab_index(F, s1);
+            const double u = V.u1tab[t], ru = V.ru1tab[t];
+            const double va = nd * lc_rcp_fast(rd) - cfix;
+            const double A0 = (double)s1 * u, B0 = A0 + F.P1;
+            int sc;
+            if (va < A0) sc = (int)(va * ru);
+            else if (va <= B0) sc = s1;
+            else sc = s1 + 1 + (int)((va - B0) * ru);
+            sc = sc < 0 ? 0 : (sc > n - 1 ? n - 1 : sc);
+            on_candidate(sc);
+            const double *row = V.cum1 + (size_t)s1 * (n + 1);
+            const double clo = __ldg(row + sc), chi = __ldg(row + sc + 1);
+            const double xl = LC_DMUL(rd, clo), xh1 = LC_DMUL(rd, chi);
+            const double tgt = nd - cfix * rd; // ~ v*range; |error| < 3e-6 for range <= 2^32
+            if (tgt - xl > 1e-5 && xh1 - tgt >= 1e-5) { // cum[sc] < v <= cum[sc+1], decided with margin
+                s = sc; done = true;
+                nlo = lo + (uint32_t)LC_D2LL(xl);
+                nhi = lo + (uint32_t)LC_D2LL(LC_DSUB(xh1, 1.0));
+            }
+        }
+    } else if (st == 2) {
+        const double u = q0.x;
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(q3.y);
+        int k = (int)((sb >> 48) & 0xffu);
+        if (k > LCV_INLINE_K) k = LCV_INLINE_K;
+        double val[LCV_INLINE_K] = {q0.y, q1.x, q1.y, q2.x, q2.y, q3.x};
+        int sym[LCV_INLINE_K];
+#pragma unroll
+        for (int j = 0; j < LCV_INLINE_K; j++) sym[j] = (int)((sb >> (8 * j)) & 0xffu);
+        bool decided = false;
+        LcInterval iv; iv.sym = 0; iv.clo = 0.0; iv.chi = 0.0; iv.exact = 0;
+        const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
+        if (pre_ok) {
+            const double ru = lc_rcp_fast(u);
+            const double va = nd * lc_rcp_fast(rd) - cfix;
+            // approximate cum before (A) and after (Bv) every entry
+            double A[LCV_INLINE_K], Bv[LCV_INLINE_K];
+            double S = 0.0, Bk = 0.0; // Bk/g0: end of the last valid entry (start of the tail gap)
+            int g0 = 0;
+#pragma unroll
+            for (int j = 0; j < LCV_INLINE_K; j++) {
+                A[j] = (double)(sym[j] - j) * u + S;
+                S += val[j];
+                Bv[j] = A[j] + val[j];
+                if (j < k) { Bk = Bv[j]; g0 = sym[j] + 1; }
+            }
+            // first entry whose upper bound reaches v (descending scan: the last assignment wins)
+            int l = k;
+            double Al = 0.0, Bl = 0.0, Bp = 0.0;
+            int sl = 0, gf = 0;
+#pragma unroll
+            for (int j = LCV_INLINE_K - 1; j >= 0; j--) {
+                if (j < k && Bv[j] >= va) {
+                    l = j; Al = A[j]; Bl = Bv[j]; sl = sym[j];
+                    Bp = j > 0 ? Bv[j > 0 ? j - 1 : 0] : 0.0;
+                    gf = j > 0 ? sym[j > 0 ? j - 1 : 0] + 1 : 0;
+                }
+            }
+            if (l < k) {
+                if (va - Al > F.delta_v) {
+                    if (Bl - va >= F.delta_v) { iv.sym = sl; iv.clo = Al; iv.chi = Bl; decided = true; }
+                } else if (Al - va >= F.delta_v) {
+                    decided = lcv_gap_search(u, ru, F.delta_v, va, Bp, gf, sl - gf, iv);
+                }
+            } else {
+                decided = lcv_gap_search(u, ru, F.delta_v, va, Bk, g0, n - g0, iv);
+            }
+        }
+        // lane-distributed copy of the record for the exact paths
+        F.k = k; F.u = u; F.my_sym = 0x7fffffff; F.my_val = 0.0;
+#pragma unroll
+        for (int j = 0; j < LCV_INLINE_K; j++) if (lane == j && j < k) { F.my_sym = sym[j]; F.my_val = val[j]; }
+        if (decided) {
+            on_candidate(iv.sym);
+            lcf_apply_symbol(F, iv, nd, rd, lo, hi);
+            nlo = lo; nhi = hi; s = iv.sym; done = true;
+        }
+    } else {
+        lcv_load_pool(F, V, gw);
+    }
+    if (!done) { // exact evaluation shared with the other kernels
+        fallback = 1;
+        if (st == 1) lcf_state_first(F, s1);
+        LcInterval iv;
+        double num, rdv;
+        const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
+        if (fs != LC_OK) return fs;
+        on_candidate(iv.sym);
+        lcf_apply_symbol(F, iv, num, rdv, lo, hi);
+        nlo = lo; nhi = hi; s = iv.sym;
+    }
+    return LC_OK;
+}
+
 // issue the global loads the next visit of context `key` needs (state st): the 4-byte word (states 1, 3) or the
 // inline record (state 2).  Only called when no job on that context can still be running.
 #define LCV_PREFETCH(st_, key_, gw_, q0_, q1_, q2_, q3_)                                   \
@@ -419,7 +555,6 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     uint32_t gw = 0u;  //   states 1, 3: the context's 4-byte word
     double2 q0 = {0.0, 0.0}, q1 = q0, q2 = q0, q3 = q0; // state 2: the inline record  u | val[6] | sym[6] k
     P.my_key = LCV_SENTINEL; // contexts of the previous stream are not this stream's
-    const double cfix = 1e-10;
     LCP_DECL
     LCP_INIT();
     for (; pos < F.total; pos++) {
@@ -430,135 +565,20 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         int c2 = c + 1, r2 = r;
         if (c2 == C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
         const int up2 = r2 > 0 ? (int)V.rows[((r2 - 1) & 1) * C + c2] : -1;
-        // ---- decode_symbol (:272-292)
-        const uint32_t rng1 = hi - lo, off = code - lo; // range-1, (code-low+1)-1
-        const bool pre_ok = hi >= lo && off <= rng1 && rng1 >= 0xffffu;
-        int s = 0, s1 = 0;
-        uint32_t nlo = 0u, nhi = 0u;
-        bool done = false;
-        // The next position's context key needs only the symbol: as soon as a path has its candidate, the state
-        // word of that context is requested from shared memory, so the load overlaps the bounds arithmetic.
-        uint32_t key2 = 0u, w2 = 0u;
-#define LCV_NEXT_CTX(sym_)                                                                                \
-    do {                                                                                                  \
-        key2 = (uint32_t)((c2 > 0 ? (sym_) : -1) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);          \
-        w2 = lcv_ld_vol(V.sbits + (key2 >> 4));                                                           \
-    } while (0)
-        if (st == 0) {
-            if (pre_ok) {
-                // uniform model: cum[i] = i/n exactly, so range*cum is exact and everything is integer work.
-                // With a = (code-low+1)*n and E = 1e-10*n*range, the symbol is the s with
-                // s*range < a - E (+- 3e-4) <= (s+1)*range; candidate from a float quotient, checked with margins.
-                int cand = (int)((float)off * lcv_rcp_f32((float)rng1) * (float)n);
-                cand = cand > n - 1 ? n - 1 : cand; // (float)off rounds up to 2^32 at most: cand <= n
-                LCV_NEXT_CTX(cand);
-                const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
-                const unsigned long long above = below + rng1 + 1ull;
-                const unsigned long long a = ((unsigned long long)off + 1ull) << V.lg_n;
-                const unsigned long long e_lo = (unsigned long long)(__umulhi(rng1, V.eps_k) >> 8); // <= E < e_lo + 3
-                if (below + e_lo + 4ull <= a && a + 1ull <= above + e_lo) {
-                    s = cand; done = true;
-                    nlo = lo + (uint32_t)(below >> V.lg_n);
-                    nhi = lo + (uint32_t)(above >> V.lg_n) - 1u;
-                }
-            }
-        } else if (st == 1) {
-            s1 = (int)(gw & 0x3FFu);
-            if (s1 >= n) s1 = n - 1; // only on a stream already flagged for the generic kernel
-            if (pre_ok) { // model after one update: exact np.cumsum values from the per-launch table
-                const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
-                const int t = lcf_tab_index(F, s1);
-                const double u = V.u1tab[t], ru = V.ru1tab[t];
-                const double va = nd * lc_rcp_fast(rd) - cfix;
-                const double A0 = (double)s1 * u, B0 = A0 + F.P1;
-                int sc;
-                if (va < A0) sc = (int)(va * ru);
-                else if (va <= B0) sc = s1;
-                else sc = s1 + 1 + (int)((va - B0) * ru);
-                sc = sc < 0 ? 0 : (sc > n - 1 ? n - 1 : sc);
-                LCV_NEXT_CTX(sc);
-                const double *row = V.cum1 + (size_t)s1 * (n + 1);
-                const double clo = __ldg(row + sc), chi = __ldg(row + sc + 1);
-                const double xl = LC_DMUL(rd, clo), xh1 = LC_DMUL(rd, chi);
-                const double tgt = nd - cfix * rd; // ~ v*range; |error| < 3e-6 for range <= 2^32
-                if (tgt - xl > 1e-5 && xh1 - tgt >= 1e-5) { // cum[sc] < v <= cum[sc+1], decided with margin
-                    s = sc; done = true;
-                    nlo = lo + (uint32_t)LC_D2LL(xl);
-                    nhi = lo + (uint32_t)LC_D2LL(LC_DSUB(xh1, 1.0));
-                }
-            }
-        } else if (st == 2) {
-            const double u = q0.x;
-            const unsigned long long sb = (unsigned long long)__double_as_longlong(q3.y);
-            int k = (int)((sb >> 48) & 0xffu);
-            if (k > LCV_INLINE_K) k = LCV_INLINE_K;
-            double val[LCV_INLINE_K] = {q0.y, q1.x, q1.y, q2.x, q2.y, q3.x};
-            int sym[LCV_INLINE_K];
-#pragma unroll
-            for (int j = 0; j < LCV_INLINE_K; j++) sym[j] = (int)((sb >> (8 * j)) & 0xffu);
-            bool decided = false;
-            LcInterval iv; iv.sym = 0; iv.clo = 0.0; iv.chi = 0.0; iv.exact = 0;
-            const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
-            if (pre_ok) {
-                const double ru = lc_rcp_fast(u);
-                const double va = nd * lc_rcp_fast(rd) - cfix;
-                // approximate cum before (A) and after (Bv) every entry
-                double A[LCV_INLINE_K], Bv[LCV_INLINE_K];
-                double S = 0.0, Bk = 0.0; // Bk/g0: end of the last valid entry (start of the tail gap)
-                int g0 = 0;
-#pragma unroll
-                for (int j = 0; j < LCV_INLINE_K; j++) {
-                    A[j] = (double)(sym[j] - j) * u + S;
-                    S += val[j];
-                    Bv[j] = A[j] + val[j];
-                    if (j < k) { Bk = Bv[j]; g0 = sym[j] + 1; }
-                }
-                // first entry whose upper bound reaches v (descending scan: the last assignment wins)
-                int l = k;
-                double Al = 0.0, Bl = 0.0, Bp = 0.0;
-                int sl = 0, gf = 0;
-#pragma unroll
-                for (int j = LCV_INLINE_K - 1; j >= 0; j--) {
-                    if (j < k && Bv[j] >= va) {
-                        l = j; Al = A[j]; Bl = Bv[j]; sl = sym[j];
-                        Bp = j > 0 ? Bv[j > 0 ? j - 1 : 0] : 0.0;
-                        gf = j > 0 ? sym[j > 0 ? j - 1 : 0] + 1 : 0;
-                    }
-                }
-                if (l < k) {
-                    if (va - Al > F.delta_v) {
-                        if (Bl - va >= F.delta_v) { iv.sym = sl; iv.clo = Al; iv.chi = Bl; decided = true; }
-                    } else if (Al - va >= F.delta_v) {
-                        decided = lcv_gap_search(u, ru, F.delta_v, va, Bp, gf, sl - gf, iv);
-                    }
-                } else {
-                    decided = lcv_gap_search(u, ru, F.delta_v, va, Bk, g0, n - g0, iv);
-                }
-            }
-            // lane-distributed copy of the record for the exact paths
-            F.k = k; F.u = u; F.my_sym = 0x7fffffff; F.my_val = 0.0;
-#pragma unroll
-            for (int j = 0; j < LCV_INLINE_K; j++) if (lane == j && j < k) { F.my_sym = sym[j]; F.my_val = val[j]; }
-            if (decided) {
-                LCV_NEXT_CTX(iv.sym);
-                lcf_apply_symbol(F, iv, nd, rd, lo, hi);
-                nlo = lo; nhi = hi; s = iv.sym; done = true;
-            }
-        } else {
-            lcv_load_pool(F, V, gw);
-        }
-        if (!done) { // exact evaluation shared with the other kernels
-            LCP_COUNT(4, st);
-            if (st == 1) lcf_state_first(F, s1);
-            LcInterval iv;
-            double num, rdv;
-            const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
+        // ---- decode_symbol (:272-292).  The next position's context key needs only the symbol: as soon as a path
+        // has its candidate, the state word of that context is requested from shared memory, so the load overlaps
+        // the bounds arithmetic.
+        int s = 0, s1 = 0, fell_back = 0;
+        uint32_t nlo = 0u, nhi = 0u, key2 = 0u, w2 = 0u;
+        {
+            const int fs = lcv_decode_symbol(F, V, st, gw, q0, q1, q2, q3, lo, hi, code, s, s1, nlo, nhi, fell_back,
+                                             [&](int sym_) {
+                                                 key2 = (uint32_t)((c2 > 0 ? sym_ : -1) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);
+                                                 w2 = lcv_ld_vol(V.sbits + (key2 >> 4));
+                                             });
             if (fs != LC_OK) { status = fs; break; }
-            LCV_NEXT_CTX(iv.sym);
-            lcf_apply_symbol(F, iv, num, rdv, lo, hi);
-            nlo = lo; nhi = hi; s = iv.sym;
+            if (fell_back) LCP_COUNT(4, st);
         }
-#undef LCV_NEXT_CTX
         lo = nlo; hi = nhi;
         LCP_MARK(1);
         // ---- next position's context (get_context :78-117): the data its state needs is requested now (loaded

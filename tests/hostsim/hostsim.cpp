@@ -12,6 +12,7 @@
 #include "../../image_compression_2_b200/csrc/lc_encoder_par.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_fast.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_v2.cuh"
+#include "../../image_compression_2_b200/csrc/lc_decoder_v3.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_sparse.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_pack.cuh"
 #include <algorithm>
@@ -230,6 +231,14 @@ static void decv2_body(void *p)
     lcv_decode_block(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table, a->d.deq_out,
                      a->d.status, a->d.fault, a->scratch2, a->tables, a->d.smem);
 }
+static void decv3_body(void *p)
+{
+    DecV2Args *a = (DecV2Args *)p;
+    lc3_decode_block(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table, a->d.deq_out,
+                     a->d.status, a->d.fault, a->scratch2, a->tables, a->d.smem);
+}
+static int g_decoder_version = 2;
+extern "C" void hostsim_set_decoder_version(int v) { g_decoder_version = v; }
 extern "C" int hostsim_decode_v2(const unsigned char *bytes, const long long *offsets, const int *nbits, int B,
                                  int imgs, int R, int C, int n, double rate, int *out, const float *deq_table,
                                  float *deq_out, int *status, int *fault, int grid, int *n_redone)
@@ -249,7 +258,10 @@ extern "C" int hostsim_decode_v2(const unsigned char *bytes, const long long *of
     a.tables = tables.data();
     a.scratch2 = (char *)(((uintptr_t)scratch2.data() + 255) & ~(uintptr_t)255);
     for (int b = 0; b < 3; b++) emu::run_warp(decv2_tables_body, &a, (unsigned)b, 3u);
-    for (int b = 0; b < grid; b++) emu::run_block(decv2_body, &a, (unsigned)b, (unsigned)grid, LCV_WARPS);
+    if (g_decoder_version == 3)
+        for (int b = 0; b < grid; b++) emu::run_block(decv3_body, &a, (unsigned)b, (unsigned)grid, LC3_WARPS);
+    else
+        for (int b = 0; b < grid; b++) emu::run_block(decv2_body, &a, (unsigned)b, (unsigned)grid, LCV_WARPS);
     int redo = 0;
     for (int b = 0; b < B; b++) redo += status[b] == LC_NEEDS_GENERIC;
     *n_redone = redo;

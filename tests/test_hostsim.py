@@ -229,7 +229,8 @@ def _v2_ok(n, shape):
     return 8 <= n <= 256 and len(shape) == 3 and 4 <= shape[2] <= 4096
 
 
-def test_decoder_v2_matches_reference_vectors():
+@pytest.mark.parametrize("ver", ["v2", "v3"])
+def test_decoder_v2_matches_reference_vectors(ver):
     ran = 0
     for fixture in ("kat.npz", "coder_small.npz", "coder_full.npz"):
         for name, rec in coder_cases(golden(fixture), mode="repaired").items():
@@ -237,7 +238,7 @@ def test_decoder_v2_matches_reference_vectors():
             if not _pow2(n) or codes.ndim != 3 or "enc_error" in rec or not _v2_ok(n, codes.shape):
                 continue
             batch = codes[None]
-            dec, st, fi, _ = H.decode([rec["packed"].tobytes()], n, batch.shape, 1, fast="v2")
+            dec, st, fi, _ = H.decode([rec["packed"].tobytes()], n, batch.shape, 1, fast=ver)
             ref = rec["decoded"].reshape(batch.shape)
             if "dec_error" in rec:
                 k = int(rec["dec_fault_index"])
@@ -251,7 +252,8 @@ def test_decoder_v2_matches_reference_vectors():
     assert ran > 40
 
 
-def test_decoder_v2_against_oracle_decoder():
+@pytest.mark.parametrize("ver", ["v2", "v3"])
+def test_decoder_v2_against_oracle_decoder(ver):
     """Random streams over the alphabets v2 accepts, including narrow 4-bit data the reference itself cannot
     round-trip (hazards H1-H3): same symbols, same fault class, same fault index as the oracle decoder."""
     rng = np.random.default_rng(77)
@@ -262,7 +264,7 @@ def test_decoder_v2_against_oracle_decoder():
         codes[0, 0, :8] = n - 1
         streams = [O.encode_stream(codes[b:b + 1], n)["packed"] for b in range(shape[0])]
         cb = np.linspace(-1, 1, n).astype(np.float32)
-        dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast="v2", grid=2, codebook=cb)
+        dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast=ver, grid=2, codebook=cb)
         for b in range(shape[0]):
             ref = O.decode_stream(streams[b], n, (1,) + shape[1:])
             k = int(ref["fault_index"]) if ref["status"] else codes[b].size
@@ -271,7 +273,8 @@ def test_decoder_v2_against_oracle_decoder():
             assert np.array_equal(deq[b][:k], cb[dec[b].ravel()[:k]])
 
 
-def test_decoder_v2_wide_contexts_and_images_sharing_a_model():
+@pytest.mark.parametrize("ver", ["v2", "v3"])
+def test_decoder_v2_wide_contexts_and_images_sharing_a_model(ver):
     rng = np.random.default_rng(31)
     n = 256
     codes = np.zeros((2, 4, 400), np.int32)
@@ -280,7 +283,7 @@ def test_decoder_v2_wide_contexts_and_images_sharing_a_model():
     codes[1] = np.clip(np.round(rng.normal(128, 9, (4, 400))), 0, n - 1)
     streams = [O.encode_stream(codes[b:b + 1], n)["packed"] for b in range(2)]
     cb = np.linspace(-1, 1, n).astype(np.float32)
-    dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast="v2", grid=1, codebook=cb)
+    dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast=ver, grid=1, codebook=cb)
     assert H.decode.last_redone == 1
     assert not st.any() and np.array_equal(dec, codes) and np.array_equal(deq.reshape(codes.shape), cb[codes])
     # records between 7 and 32 entries live in the pool
@@ -288,16 +291,16 @@ def test_decoder_v2_wide_contexts_and_images_sharing_a_model():
     codes[0, :, 0::2] = 5
     codes[0, :, 1::2] = rng.integers(100, 120, (6, 150))
     streams = [O.encode_stream(codes, n)["packed"]]
-    dec, st, fi, _ = H.decode(streams, n, codes.shape, 1, fast="v2", grid=1)
+    dec, st, fi, _ = H.decode(streams, n, codes.shape, 1, fast=ver, grid=1)
     assert H.decode.last_redone == 0 and not st.any() and np.array_equal(dec, codes)
     # the reference's batched call: several images share coder and model (cabac_compression.py:330-337)
     imgs = np.clip(np.round(rng.normal(32, 3, (3, 4, 64))), 0, 63).astype(np.int32)
     packed = O.encode_stream(imgs, 64)["packed"]
-    dec, st, fi, _ = H.decode([packed], 64, (1,) + imgs.shape, 1, fast="v2", grid=1)
+    dec, st, fi, _ = H.decode([packed], 64, (1,) + imgs.shape, 1, fast=ver, grid=1)
     assert not st.any() and np.array_equal(dec[0], imgs)
     # corrupted stream: whatever the oracle decoder does, v2 does
     bad = bytearray(packed); bad[len(bad) // 2] ^= 0x5a
     ref = O.decode_stream(bytes(bad), 64, imgs.shape)
-    dec, st, fi, _ = H.decode([bytes(bad)], 64, (1,) + imgs.shape, 1, fast="v2", grid=1)
+    dec, st, fi, _ = H.decode([bytes(bad)], 64, (1,) + imgs.shape, 1, fast=ver, grid=1)
     k = int(ref["fault_index"]) if ref["status"] else imgs.size
     assert st[0] == ref["status"] and np.array_equal(dec.ravel()[:k], ref["symbols"].ravel()[:k])
