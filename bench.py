@@ -375,8 +375,9 @@ def run_b200(args):
                        "parity": parity_note, "streams_per_s": value / SYMS},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(res["h2d_bytes"]),
                     "d2h_bytes_per_step": int(res["d2h_bytes"]), "ms_per_step": 1e3 * float(e_total) / args.steps},
-            # per step: quantise, tables, sort, phase A, phase B, size scan, compaction, tables, decode, redo pass
-            "gpu_launches": 10 * args.steps,
+            # per step: quantise, tables, two-visit table, sort, phase A, phase B1, B2, size scan, compaction,
+            # tables, decode, redo pass
+            "gpu_launches": 12 * args.steps,
             "roofline": {"kernel": "lc_decode_v2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": facts.get("dram_bytes_per_launch") if same_cfg else None,

@@ -391,10 +391,20 @@ __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, con
 __global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS) lc_enc_phase_a_sparse_kernel(
     LcCoderCfg cfg, const int *__restrict__ codes, int B, const uint32_t *__restrict__ skeys,
     const unsigned short *__restrict__ spos, const int *__restrict__ first_bad, const unsigned short *__restrict__ glist,
-    const int *__restrict__ ngroups, double *ivs, unsigned int *task_counter, const double *__restrict__ tables)
+    const int *__restrict__ ngroups, double *ivs, unsigned int *task_counter, const double *__restrict__ tables,
+    const double *__restrict__ t2)
 {
     extern __shared__ __align__(16) char lc_smem[];
-    lc_enc_phase_a_sparse_block(cfg, codes, B, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables, lc_smem);
+    lc_enc_phase_a_sparse_block(cfg, codes, B, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables, t2,
+                                lc_smem);
+}
+
+// per-launch table of the models after two visits (lcs_t2_block)
+__global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS) lc_enc_t2_kernel(LcCoderCfg cfg, const double *__restrict__ tables,
+                                                                         double *t2)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lcs_t2_block(cfg, tables, t2, lc_smem);
 }
 
 __global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
@@ -544,8 +554,9 @@ static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
         if (v2 > need) need = v2;
     }
     if (lc_use_parallel_encoder(cfg)) {
-        const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES + 256 +
-                            (int64_t)lcv_tables_bytes(cfg.n);
+        const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES + 512 +
+                            (int64_t)lcv_tables_bytes(cfg.n) +
+                            (cfg.n <= LCS_T2_MAX_N ? (int64_t)cfg.n * cfg.n * LCS_T2_STRIDE * 8 : 0);
         if (par > need) need = par;
     }
     return need;
@@ -669,9 +680,18 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
         const int tile = B < LC_PAR_TILE ? B : LC_PAR_TILE;
         // per-launch tables (u after the first update, exact cumsum rows of the model after one update)
         double *tables = (double *)((char *)scratch + (((size_t)tile * LC_PAR_STREAM_BYTES + 255) & ~(size_t)255));
+        // ... and, for alphabets up to LCS_T2_MAX_N symbols, the models after two visits.  The second table pays
+        // for itself once the batch holds a few times n*n/1000 streams.
+        double *t2 = (double *)0;
         if (sparse_variant) {
             lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
             LC_CUDA_RET();
+            if (cfg.n <= LCS_T2_MAX_N && (long long)B * 1000 >= (long long)cfg.n * cfg.n) {
+                t2 = tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255) / 8;
+                const size_t t2_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;
+                lc_enc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, t2_smem, st>>>(cfg, tables, t2);
+                LC_CUDA_RET();
+            }
         }
         for (int b0 = 0; b0 < B; b0 += LC_PAR_TILE) {
             const int nb = (B - b0) < LC_PAR_TILE ? (B - b0) : LC_PAR_TILE;
@@ -693,7 +713,7 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
                 if (blocks_per_sm > 32 / LCS_BLOCK_WARPS) blocks_per_sm = 32 / LCS_BLOCK_WARPS;
                 cudaMemsetAsync(task_counter, 0, 4, st);
                 lc_enc_phase_a_sparse_kernel<<<lc_num_sms() * blocks_per_sm, 32 * LCS_BLOCK_WARPS, sp_smem, st>>>(
-                    cfg, codes, nb, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables);
+                    cfg, codes, nb, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables, t2);
             } else {
                 lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
             }

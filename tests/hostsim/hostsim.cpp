@@ -281,7 +281,7 @@ extern "C" void hostsim_stats(long long *out, int reset)
 // checked on the GPU), phases A and B run through the emulator
 struct ParAArgs { LcCoderCfg cfg; const int *codes; int B; const uint32_t *skeys; const unsigned short *spos;
                   const int *first_bad; double *ivs; char *smem; unsigned short *glist; int *ngroups; unsigned int *task_counter;
-                  double *tables; };
+                  double *tables; double *t2; };
 static void para_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
@@ -298,7 +298,12 @@ static void para_lanes_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
     lc_enc_phase_a_sparse_block(a->cfg, a->codes, a->B, a->skeys, a->spos, a->first_bad, a->glist, a->ngroups, a->ivs,
-                                a->task_counter, a->tables, a->smem);
+                                a->task_counter, a->tables, a->t2, a->smem);
+}
+static void para_t2_body(void *p)
+{
+    ParAArgs *a = (ParAArgs *)p;
+    lcs_t2_block(a->cfg, a->tables, a->t2, a->smem);
 }
 static void glist_body(void *p)
 {   // phase S part: group list + first-visit intervals (on the GPU this is done by lc_enc_sort_kernel)
@@ -373,10 +378,18 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
     std::vector<double> tables(lcv_tables_bytes(n) / 8 + 8, -777.0);
     ParAArgs a{cfg, codes, B, skeys.data(), spos.data(), first_bad.data(), ivs.data(),
                (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15), glist.data(), ngroups.data(), &task_counter,
-               tables.data()};
+               tables.data(), (double *)0};
+    std::vector<double> t2;
+    if (nwarps == 0 && n <= 64) { // small alphabets also exercise the table of models after two visits
+        t2.assign((size_t)n * n * LCS_T2_STRIDE, -555.0);
+        a.t2 = t2.data();
+    }
     if (nwarps == 0) { // sparse variant: second visits from the table, one warp per context visited three times or more
         for (int b = 0; b < 3; b++) emu::run_warp(para_tables_body, &a, (unsigned)b, 3u);
         for (int b = 0; b < grid; b++) emu::run_warp(glist_body, &a, (unsigned)b, (unsigned)grid);
+        if (a.t2)
+            for (int b = 0; b < 2; b++)
+                for (int w = 0; w < 2; w++) emu::run_warp(para_t2_body, &a, (unsigned)b, 2u, (unsigned)w, 2u);
         for (int b = 0; b < grid; b++)
             for (int w = 0; w < 2; w++) emu::run_warp(para_lanes_body, &a, (unsigned)b, (unsigned)grid, (unsigned)w, 2u);
     } else
