@@ -4,7 +4,7 @@ dequantisation, behind the reference's own Python API.  See DESIGN.md / INTEGRAT
 
 Importing the package does not need a GPU; every operation does (there is no CPU fallback).
 """
-from . import codec, coder, compressors, containers, pipeline, sharding  # noqa: F401
+from . import codec, coder, compressors, containers, pipeline, sharding, stats  # noqa: F401
 from .coder import ContextModel, cabac_decode, cabac_encode  # noqa: F401
 from .compressors import (CABACCompressor, GumbelSoftmaxCompressor, GumbelSoftmaxDiscretization,  # noqa: F401
                           StyleGAN3Compressor)

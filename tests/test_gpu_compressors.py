@@ -130,3 +130,14 @@ def test_pipeline_host_roundtrip():
             assert nbits[b] == ref["nbits"]
             assert blob[offs[b]:offs[b] + len(ref["packed"])].tobytes() == ref["packed"]
         assert res["h2d_bytes"] > lat.numel() * 4 and res["d2h_bytes"] > lat.numel() * 4
+
+
+def test_bitrate_stats_of_a_coded_batch():
+    from image_compression_2_b200 import LatentPipeline, stats
+    from tests.helpers import synth_latents
+    lat = synth_latents("enc_like", 32, 4242)
+    pipe = LatentPipeline(n_symbols=256)
+    enc = pipe.encode(pipe.quantize(lat.cuda()))
+    st = stats.encoded_batch_stats(enc)
+    assert st["streams"] == 32 and 7.9 < st["coded_bits_per_symbol"] < 8.1
+    assert st["packed_bytes"]["total"] == int(((enc.nbits.cpu().numpy() + 7) // 8).sum())

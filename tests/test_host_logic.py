@@ -116,6 +116,20 @@ def test_pack_streams_layout():
     assert data[:3].numpy().tobytes() == b"abc" and data[16:33].numpy().tobytes() == b"x" * 17
 
 
+def test_bitrate_stats():
+    from image_compression_2_b200 import stats
+    nbits = torch.tensor([65600, 65700, 65500, 0], dtype=torch.int32)
+    st = stats.bitrate_stats(nbits, 8192, 256, status=torch.tensor([0, 0, 0, 5]))
+    assert st["streams"] == 3 and st["raw_bits_per_stream"] == 65536.0
+    assert abs(st["coded_bits_per_symbol"] - 65600 / 8192) < 1e-12
+    assert st["orig_size"] == 8192.0 and st["reference_comp_size"] == 65600.0          # defect D1: bits as bytes
+    assert abs(st["compression_ratio_reference"] - 8192.0 / 65600.0) < 1e-12
+    assert st["packed_bytes"]["total"] == 8200 + 8213 + 8188 and st["cabac_vs_raw"] < 1.0
+    assert sum(st["histogram_bits_per_symbol"]["counts"]) == 3
+    with pytest.raises(ValueError):
+        stats.bitrate_stats(nbits[3:], 8192, 256, status=torch.tensor([5]))
+
+
 def test_shard_ranges():
     from image_compression_2_b200.sharding import shard_range
     for B, G in ((65536, 8), (1024, 3), (5, 8), (0, 4)):
