@@ -244,7 +244,22 @@ __global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_kernel(LcCoder
                                                                           char *scratch, const double *tables)
 {
     extern __shared__ __align__(16) char lc_smem[];
-    lcv_decode_block(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables, lc_smem);
+    lcv_decode_block<0, 0, 0>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables,
+                              lc_smem);
+}
+
+// the W+ latent shape of the reference (8-bit codes of a [16,512] latent, one image per stream), fixed at compile time
+__global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_w8_kernel(LcCoderCfg cfg, LcV2Cfg vc,
+                                                                             const unsigned char *__restrict__ bytes,
+                                                                             const long long *__restrict__ offsets,
+                                                                             const int *__restrict__ nbits, int B, int *out,
+                                                                             const float *__restrict__ deq_table,
+                                                                             float *deq_out, int *status, int *fault,
+                                                                             char *scratch, const double *tables)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lcv_decode_block<256, 512, 16>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch,
+                                   tables, lc_smem);
 }
 
 // Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream
@@ -777,6 +792,7 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
         if (!v2_attr) {
             cudaFuncSetAttribute(lc_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             cudaFuncSetAttribute(lc_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(lc_decode_v2_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             v2_attr = true;
         }
         if (vc.sm_bytes > 64 * 1024) return -22;
@@ -786,6 +802,10 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
             lc_decode_v3_kernel<<<g2, 32 * LC3_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
                                                                          B, idx_out, deq_table, deq_out, status,
                                                                          fault_index, (char *)scratch, tables);
+        else if (cfg.n == 256 && cfg.C == 512 && cfg.R == 16 && cfg.imgs == 1 && !getenv("LC_DECODER_GENERIC"))
+            lc_decode_v2_w8_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets,
+                                                                            nbits, B, idx_out, deq_table, deq_out, status,
+                                                                            fault_index, (char *)scratch, tables);
         else
             lc_decode_v2_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
                                                                          B, idx_out, deq_table, deq_out, status,

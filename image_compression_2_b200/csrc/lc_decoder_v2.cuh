@@ -654,7 +654,9 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     }
 }
 
-// Block entry: LCV_WARPS warps, persistent over streams.
+// Block entry: LCV_WARPS warps, persistent over streams.  FN/FC/FR > 0 fix the alphabet size and the image shape at
+// compile time (one image per stream): keys, shifts, margins and loop bounds become immediates on the serial chain.
+template <int FN, int FC, int FR>
 __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const LcV2Cfg &vc, const unsigned char *bytes,
                                                  const long long *offsets, const int *nbits, int B, int *out,
                                                  const float *deq_table, float *deq_out, int *status, int *fault,
@@ -684,6 +686,13 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
     F.dense = (double *)(smem + vc.sm_dense) + (size_t)(warp > 0 ? warp - 1 : 0) * cfg.n;
     F.u1tab = V.u1tab; F.rows = (unsigned short *)0;
     F.k = 0; F.u = F.u0; F.my_sym = 0x7fffffff; F.my_val = 0.0;
+    if (FN > 0) {
+        F.n = FN; F.C = FC; F.R = FR; F.total = FR * FC;
+        F.pw_len = FN < 128 ? FN : 128; F.pw_steps = F.pw_len / 8; F.pw_chains = 8 * (FN / F.pw_len);
+        int lg = 0; while ((1 << lg) < FN) lg++;
+        V.lg_n = (uint32_t)lg;
+        V.eps_k = (uint32_t)(1e-10 * (double)FN * 1099511627776.0);
+    }
     if (threadIdx.x < 64) V.u1tab[threadIdx.x] = tables[threadIdx.x];
     if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = threadIdx.x - LCV_RING + 1u; }
     LcvPost P; P.njobs = 0u; P.my_key = LCV_SENTINEL; P.my_job = 0u;

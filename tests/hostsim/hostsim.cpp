@@ -228,7 +228,11 @@ static void decv2_tables_body(void *p)
 static void decv2_body(void *p)
 {
     DecV2Args *a = (DecV2Args *)p;
-    lcv_decode_block(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table, a->d.deq_out,
+    if (a->d.cfg.n == 256 && a->d.cfg.C == 512 && a->d.cfg.R == 16 && a->d.cfg.imgs == 1)
+        lcv_decode_block<256, 512, 16>(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table,
+                                       a->d.deq_out, a->d.status, a->d.fault, a->scratch2, a->tables, a->d.smem);
+    else
+    lcv_decode_block<0, 0, 0>(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table, a->d.deq_out,
                      a->d.status, a->d.fault, a->scratch2, a->tables, a->d.smem);
 }
 static void decv3_body(void *p)
