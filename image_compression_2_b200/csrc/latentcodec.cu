@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(32) lc_v2_tables_kernel(LcCoderCfg cfg, double
     lcv_tables_block(cfg, tables, lc_smem);
 }
 
-__global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_kernel(LcCoderCfg cfg, LcV2Cfg vc,
+__global__ void __launch_bounds__(32 * LCV_WARPS, 8) lc_decode_v2_kernel(LcCoderCfg cfg, LcV2Cfg vc,
                                                                           const unsigned char *__restrict__ bytes,
                                                                           const long long *__restrict__ offsets,
                                                                           const int *__restrict__ nbits, int B, int *out,
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_kernel(LcCoder
 }
 
 // the W+ latent shape of the reference (8-bit codes of a [16,512] latent, one image per stream), fixed at compile time
-__global__ void __launch_bounds__(32 * LCV_WARPS, 7) lc_decode_v2_w8_kernel(LcCoderCfg cfg, LcV2Cfg vc,
+__global__ void __launch_bounds__(32 * LCV_WARPS, 8) lc_decode_v2_w8_kernel(LcCoderCfg cfg, LcV2Cfg vc,
                                                                              const unsigned char *__restrict__ bytes,
                                                                              const long long *__restrict__ offsets,
                                                                              const int *__restrict__ nbits, int B, int *out,
@@ -548,7 +548,7 @@ static bool lc_use_decoder_v2(const LcCoderCfg &cfg) { return lc_decoder_choice(
 static int lc_v2_grid(const LcV2Cfg &vc, int B)
 {
     int per_sm = (int)((227u * 1024u) / (vc.sm_bytes + 1024u));
-    if (per_sm > 7) per_sm = 7;
+    if (per_sm > 8) per_sm = 8; // two warps of <= 128 registers per block
     if (per_sm < 1) per_sm = 1;
     long long g = (long long)lc_num_sms() * per_sm;
     if (g > B) g = B;
