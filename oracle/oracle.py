@@ -50,6 +50,16 @@ def lib():
         L.orc_decode_stream.argtypes = [u8p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, i32p, i64p]
         L.orc_decode_stream.restype = ctypes.c_int
+        f64p = ctypes.POINTER(ctypes.c_double)
+        model_io = [ctypes.c_int64, i32p, i32p, i64p, f64p, ctypes.c_int64, i64p, i32p, i32p, i64p, f64p]
+        L.orc_encode_stream_model.argtypes = [i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_double, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int64,
+                                              i64p, i64p] + model_io
+        L.orc_encode_stream_model.restype = ctypes.c_int
+        L.orc_decode_stream_model.argtypes = [u8p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, i32p,
+                                              i64p] + model_io
+        L.orc_decode_stream_model.restype = ctypes.c_int
         L.orc_pack_bits.argtypes = [u8p, ctypes.c_int64, u8p]
         L.orc_pack_bits.restype = None
         L.orc_roundtrip_stream.argtypes = [i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -151,3 +161,69 @@ def roundtrip_stream(codes, n_symbols, mode="repaired", rate=0.05):
                                     _p(bits, ctypes.c_uint8), cap, _p(packed, ctypes.c_uint8),
                                     _p(dec, ctypes.c_int32), ctypes.byref(nbits))
     return st, nbits.value
+
+
+# ---- stateful model variants (the reference mutates one ContextModel across calls, defect D5) ---------------
+# A model is a dict {(left, up): (float64[n] vector, count)}; the global context `()` of non-3-D data is (-2, -2).
+
+def _model_arrays(model, n):
+    keys = list(model.keys())
+    left = np.array([k[0] for k in keys], np.int32).reshape(-1)
+    up = np.array([k[1] for k in keys], np.int32).reshape(-1)
+    counts = np.array([int(model[k][1]) for k in keys], np.int64).reshape(-1)
+    vecs = np.ascontiguousarray(np.stack([np.asarray(model[k][0], np.float64) for k in keys]) if keys
+                                else np.zeros((0, n)), np.float64)
+    pad = lambda a: a if a.size else np.zeros(1, a.dtype)  # noqa: E731
+    return len(keys), pad(left), pad(up), pad(counts), (vecs if vecs.size else np.zeros((1, n)))
+
+
+def _model_out(total, nin, n):
+    cap = total + nin + 1
+    return (cap, ctypes.c_int64(0), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int64),
+            np.zeros((cap, n), np.float64))
+
+
+def _model_dict(nout, left, up, counts, vecs):
+    return {(int(left[i]), int(up[i])): (vecs[i].copy(), int(counts[i])) for i in range(nout)}
+
+
+def encode_stream_model(codes, n_symbols, model, mode="repaired", rate=0.05):
+    """encode_stream starting from `model`; returns (result dict, model after the call)."""
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    B, R, C, has_ctx = _shape3(codes.shape)
+    cap_bits = codes.size * 80 + 64
+    bits = np.empty(cap_bits, np.uint8)
+    nbits, fault = ctypes.c_int64(0), ctypes.c_int64(0)
+    nin, il, iu, ic, iv = _model_arrays(model, n_symbols)
+    cap, nout, ol, ou, oc, ov = _model_out(codes.size, nin, n_symbols)
+    f64 = ctypes.c_double
+    st = lib().orc_encode_stream_model(_p(codes, ctypes.c_int32), B, R, C, int(n_symbols), float(rate), MODES[mode],
+                                       has_ctx, _p(bits, ctypes.c_uint8), cap_bits, ctypes.byref(nbits),
+                                       ctypes.byref(fault), nin, _p(il, ctypes.c_int32), _p(iu, ctypes.c_int32),
+                                       _p(ic, ctypes.c_int64), _p(iv, f64), cap, ctypes.byref(nout),
+                                       _p(ol, ctypes.c_int32), _p(ou, ctypes.c_int32), _p(oc, ctypes.c_int64), _p(ov, f64))
+    bits = bits[:nbits.value].copy()
+    res = dict(status=st, fault_index=fault.value, nbits=nbits.value, bits=bits,
+               packed=np.packbits(bits).tobytes() if st == OK else b"")
+    return res, _model_dict(nout.value, ol, ou, oc, ov)
+
+
+def decode_stream_model(packed, n_symbols, shape, model, mode="repaired", rate=0.05):
+    """decode_stream starting from `model`; returns (result dict, model after the call)."""
+    buf = np.frombuffer(bytes(packed), dtype=np.uint8)
+    nbytes = buf.size
+    if buf.size == 0:
+        buf = np.zeros(1, np.uint8)
+    B, R, C, has_ctx = _shape3(tuple(shape))
+    total = B * R * C
+    out = np.zeros(total, np.int32)
+    fault = ctypes.c_int64(0)
+    nin, il, iu, ic, iv = _model_arrays(model, n_symbols)
+    cap, nout, ol, ou, oc, ov = _model_out(total, nin, n_symbols)
+    f64 = ctypes.c_double
+    st = lib().orc_decode_stream_model(_p(buf, ctypes.c_uint8), nbytes, B, R, C, int(n_symbols), float(rate), MODES[mode],
+                                       has_ctx, _p(out, ctypes.c_int32), ctypes.byref(fault), nin,
+                                       _p(il, ctypes.c_int32), _p(iu, ctypes.c_int32), _p(ic, ctypes.c_int64), _p(iv, f64),
+                                       cap, ctypes.byref(nout), _p(ol, ctypes.c_int32), _p(ou, ctypes.c_int32),
+                                       _p(oc, ctypes.c_int64), _p(ov, f64))
+    return dict(status=st, fault_index=fault.value, symbols=out.reshape(shape)), _model_dict(nout.value, ol, ou, oc, ov)

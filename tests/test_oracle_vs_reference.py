@@ -45,3 +45,49 @@ def test_one_full_stream_8bit():
     z = (torch.randn(1, 16, 512) * 0.14).numpy()
     codes = O.quantize_codebook(z, torch.linspace(-1, 1, 256).numpy())
     _compare(codes, 256, "repaired")
+
+
+def _ref_model_dict(cm):
+    """The reference object's state as {(left, up): (vector, count)}; `()` (non-3-D data) maps to (-2, -2)."""
+    out = {}
+    for k, v in cm.context_models.items():
+        kk = (-2, -2) if len(k) == 0 else (int(k[0]), int(k[1]))
+        out[kk] = (np.asarray(v, np.float64), int(cm.context_counts.get(k, 0)))
+    return out
+
+
+def _same_model(a, b):
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k][1] == b[k][1], k
+        assert np.array_equal(a[k][0], b[k][0]), k
+
+
+def test_shared_model_across_calls_defect_d5():
+    """One ContextModel mutated by successive cabac_encode / cabac_decode calls, as CABACCompressor does
+    (cabac_compression.py:438,478,517): bits, decoded symbols and the model object's state after every call."""
+    cc = R.set_mode("repaired")
+    rng = np.random.default_rng(11)
+    for n, shape in ((16, (2, 3, 30)), (64, (1, 4, 48)), (256, (1, 2, 64)), (16, (50,))):
+        a = np.clip(np.round(rng.normal(n / 2, max(1, n / 16), shape)), 0, n - 1).astype(np.int32)
+        b = np.clip(np.round(rng.normal(n / 2, max(1, n / 16), shape)), 0, n - 1).astype(np.int32)
+        cm = cc.ContextModel(n_symbols=n)
+        model = {}
+        for codes in (a, b):
+            bits = np.frombuffer(cc.cabac_encode(codes, cm), np.uint8)
+            mine, model = O.encode_stream_model(codes, n, model)
+            assert mine["status"] == O.OK and np.array_equal(bits, mine["bits"])
+            _same_model(_ref_model_dict(cm), model)
+        # decoding with the model the encoder left behind (what CABACCompressor.decompress does): usually garbage
+        packed = O.encode_stream(a, n)["packed"]
+        dec, derr = None, None
+        try:
+            dec = cc.cabac_decode(packed, cm, a.shape)
+        except (IndexError, ZeroDivisionError, ValueError) as e:
+            derr = type(e).__name__
+        mine, model2 = O.decode_stream_model(packed, n, a.shape, model)
+        if derr is None and mine["status"] == O.OK:
+            assert np.array_equal(np.asarray(dec, np.int32), mine["symbols"])
+            _same_model(_ref_model_dict(cm), model2)
+        else:
+            assert derr is not None or mine["status"] == O.DEC_NEG_SYMBOL
