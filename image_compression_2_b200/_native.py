@@ -23,6 +23,12 @@ SIGNATURES = {
     "lc_coder_grid": (ctypes.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "lc_encode_batch": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64, _vp, _i64,
                                        _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "lc_stateful_table_bytes": (_i64, [_i32, _i32]),
+    "lc_stateful_table_offset": (_i64, [_i32, _i32, _i32]),
+    "lc_stateful_encode": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
+                                          _vp, _vp]),
+    "lc_stateful_decode": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64, _vp, _vp, _vp,
+                                          _vp]),
     "lc_decode_batch": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
 }

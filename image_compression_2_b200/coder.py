@@ -5,9 +5,12 @@ containers only -- the model itself lives on the GPU), cabac_encode (:315-359), 
 (:363-406).  Same argument meaning, same return types, same exception classes.
 
 Deviations, all documented in DESIGN.md:
-  * only a FRESH (empty) ContextModel is accepted (the reference mutates one shared model across
-    calls, defect D5); a non-empty model raises NotImplementedError -- there is no CPU fallback;
-  * the model object is not filled in after the call;
+  * a FRESH (empty) ContextModel takes the fast kernels and is NOT filled in after the call, unless it was
+    created with track_state=True;
+  * a non-empty model (or track_state=True) takes the stateful kernel (csrc/lc_stateful.cuh): the stream is coded
+    from that model and the object is left holding what the reference's object would hold (the reference mutates
+    one shared model across calls, defect D5).  Supported for alphabets up to 256 symbols with (left,up)
+    contexts, up to 1024 with the single global context; otherwise NotImplementedError -- no CPU fallback;
   * DEFAULT_MODE is "repaired": the file as shipped ("verbatim") raises ValueError within a few
     hundred symbols on any realistic stream (defect D3).  mode="verbatim" reproduces that.
 """
@@ -27,22 +30,75 @@ class DecodeFault(IndexError):
 class ContextModel:
     """Parameter holder with the reference constructor (cabac_compression.py:66-76)."""
 
-    def __init__(self, n_symbols=256, context_size=5, adaptation_rate=0.05):
+    def __init__(self, n_symbols=256, context_size=5, adaptation_rate=0.05, track_state=False):
         self.n_symbols = n_symbols
         self.context_size = context_size
         self.adaptation_rate = adaptation_rate
-        self.context_models = {}
-        self.context_counts = {}
+        self.context_models = {}   # (left, up) or () -> float64[n_symbols], as the reference keeps them
+        self.context_counts = {}   # ... -> number of update_model calls
+        self.track_state = track_state  # extension: fill the two dicts in even when the model starts empty
 
     def is_fresh(self):
         return len(self.context_models) == 0 and len(self.context_counts) == 0
 
 
-def _require_fresh(context_model):
+def _wants_state(context_model):
     models = getattr(context_model, "context_models", None)
-    if models is not None and len(models) != 0:
-        raise NotImplementedError("the CUDA coder starts every stream from a fresh ContextModel; "
-                                  "pre-populated models are not supported and there is no CPU fallback")
+    return bool(getattr(context_model, "track_state", False)) or (models is not None and len(models) != 0)
+
+
+class _StatefulTable:
+    """Device table of csrc/lc_stateful.cuh for one call: the given model scattered in, the result gathered out."""
+
+    def __init__(self, context_model, layout, dev):
+        lib = _native_lib()
+        n, has_ctx = int(context_model.n_symbols), int(layout.has_ctx)
+        nbytes = lib.lc_stateful_table_bytes(n, has_ctx)
+        if nbytes < 0:
+            raise NotImplementedError("stateful coding needs a power-of-two alphabet of at most 256 symbols with "
+                                      "(left,up) contexts (1024 with the global context); there is no CPU fallback")
+        self.n, self.has_ctx, self.nkeys = n, has_ctx, ((n + 1) ** 2 if has_ctx else 1)
+        off_c, off_v = lib.lc_stateful_table_offset(n, has_ctx, 1), lib.lc_stateful_table_offset(n, has_ctx, 2)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.buf[:off_v].zero_()
+        self.valid = self.buf[:self.nkeys]
+        self.counts = self.buf[off_c:off_c + 4 * self.nkeys].view(torch.int32)
+        self.vecs = self.buf[off_v:off_v + 8 * self.nkeys * n].view(torch.float64).view(self.nkeys, n)
+        models = getattr(context_model, "context_models", {}) or {}
+        if len(models):
+            keys = list(models.keys())
+            idx = torch.tensor([self._index(k) for k in keys], dtype=torch.long, device=dev)
+            vecs = np.stack([np.asarray(models[k], np.float64).reshape(n) for k in keys])
+            counts = getattr(context_model, "context_counts", {}) or {}
+            self.vecs[idx] = torch.from_numpy(vecs).to(dev)
+            self.valid[idx] = 1
+            self.counts[idx] = torch.tensor([int(counts.get(k, 0)) for k in keys], dtype=torch.int32, device=dev)
+
+    def _index(self, key):
+        if not self.has_ctx:
+            if len(key) != 0:
+                raise ValueError("model keys must be () for non-3-D data, got %r" % (key,))
+            return 0
+        left, up = int(key[0]), int(key[1])
+        if not (-1 <= left < self.n and -1 <= up < self.n):
+            raise ValueError("context %r outside the alphabet" % (key,))
+        return (left + 1) * (self.n + 1) + (up + 1)
+
+    def export(self, context_model):
+        """Leave in context_model what the reference object holds after the call (cabac_compression.py:143-144,157)."""
+        idx = torch.nonzero(self.valid).reshape(-1)
+        vecs = self.vecs[idx].cpu().numpy()
+        counts = self.counts[idx].cpu().numpy()
+        for j, k in enumerate(idx.cpu().numpy().tolist()):
+            key = ((k // (self.n + 1)) - 1, (k % (self.n + 1)) - 1) if self.has_ctx else ()
+            context_model.context_models[key] = vecs[j].copy()
+            if counts[j] > 0:
+                context_model.context_counts[key] = int(counts[j])
+
+
+def _native_lib():
+    from . import _native
+    return _native.load()
 
 
 def _device(device=None):
@@ -80,13 +136,28 @@ def cabac_encode(data, context_model, mode=None, device=None):
 
 def cabac_encode_packed(data, context_model, mode=None, device=None):
     """Same stream as cabac_encode, returned as (MSB-first packed bytes, nbits)."""
-    _require_fresh(context_model)
     dev = _device(device)
     arr = np.ascontiguousarray(np.asarray(data), dtype=np.int32)
     layout = codec.layout_reference(arr.shape)
     if layout.total == 0:
         raise ValueError("empty input")
     idx = torch.from_numpy(arr.reshape(-1)).to(dev)
+    if _wants_state(context_model):
+        from . import _native
+        lib = _native.load()
+        table = _StatefulTable(context_model, layout, dev)
+        slot_bytes = (layout.total * 12 + 256 + 15) // 16 * 16
+        slot = torch.empty(slot_bytes, dtype=torch.uint8, device=dev)
+        res = torch.zeros(3, dtype=torch.int32, device=dev)
+        _native.check(lib.lc_stateful_encode(idx.data_ptr(), layout.imgs, layout.R, layout.C, int(context_model.n_symbols),
+                                             float(context_model.adaptation_rate), codec.MODES[mode or DEFAULT_MODE],
+                                             layout.has_ctx, table.buf.data_ptr(), table.buf.numel(), slot.data_ptr(),
+                                             slot_bytes, res[0:].data_ptr(), res[1:].data_ptr(), res[2:].data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "lc_stateful_encode")
+        nb, st, fi = (int(x) for x in res.cpu())
+        table.export(context_model)  # the reference has mutated the model up to the fault before it raises
+        raise_for_status(st, fi, "cabac_encode")
+        return slot[:(nb + 7) // 8].cpu().numpy().tobytes(), nb
     enc = codec.encode_batch(idx, layout, context_model.n_symbols, mode=mode or DEFAULT_MODE,
                              adaptation_rate=context_model.adaptation_rate)
     streams, nbits, status, fault = enc.to_host()
@@ -101,11 +172,25 @@ def cabac_encode_packed(data, context_model, mode=None, device=None):
 def cabac_decode(encoded_bytes, context_model, shape, mode=None, device=None):
     """cabac_compression.py:363.  encoded_bytes: MSB-first PACKED bits (what the reference decoder
     reads, :260-270).  Returns int32 ndarray of `shape`."""
-    _require_fresh(context_model)
     dev = _device(device)
     shape = tuple(int(s) for s in shape)
     layout = codec.layout_reference(shape)
     data, offsets, nbits = codec.pack_streams_for_device([bytes(encoded_bytes)], dev)
+    if _wants_state(context_model):
+        from . import _native
+        lib = _native.load()
+        table = _StatefulTable(context_model, layout, dev)
+        out = torch.empty(layout.total, dtype=torch.int32, device=dev)
+        res = torch.zeros(2, dtype=torch.int32, device=dev)
+        _native.check(lib.lc_stateful_decode(data.data_ptr(), len(bytes(encoded_bytes)), layout.imgs, layout.R, layout.C,
+                                             int(context_model.n_symbols), float(context_model.adaptation_rate),
+                                             codec.MODES[mode or DEFAULT_MODE], layout.has_ctx, table.buf.data_ptr(),
+                                             table.buf.numel(), out.data_ptr(), res[0:].data_ptr(), res[1:].data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "lc_stateful_decode")
+        st, fi = (int(x) for x in res.cpu())
+        table.export(context_model)
+        raise_for_status(st, fi, "cabac_decode")
+        return out.cpu().numpy().reshape(shape)
     idx, _, status, fault = codec.decode_batch(data, offsets, nbits, layout, context_model.n_symbols,
                                                mode=mode or DEFAULT_MODE,
                                                adaptation_rate=context_model.adaptation_rate)

@@ -175,11 +175,14 @@ class CABACCompressor:
     container="packed" (default) makes save_compressed/load_compressed round-trip: MSB-first packed
     bits and a correct header.  container="reference" reproduces the reference's output byte for
     byte (one byte per bit, comp_size counted in bits, header = 6; defects D1/D4), which its own
-    loader cannot read back.  Every call starts from a fresh context model (defect D5 not kept).
+    loader cannot read back.  Every call starts from a fresh context model (defect D5 not kept) unless
+    shared_model=True: then, as in the reference (:438,478,517), ONE ContextModel is mutated by every compress and
+    decompress call (the stateful kernel, csrc/lc_stateful.cuh) -- a decompress after a compress then starts from
+    the encoder's final model and does not reproduce the latents, exactly as the reference behaves.
     mode: "repaired" (default) or "verbatim" -- see image_compression_2_b200.coder."""
 
     def __init__(self, encoder, generator, discretization=None, n_embeddings=256, training_resolution=None,
-                 container="packed", mode=None):
+                 container="packed", mode=None, shared_model=False):
         self.encoder = encoder
         self.generator = generator
         self.training_resolution = training_resolution
@@ -187,7 +190,8 @@ class CABACCompressor:
             discretization = GumbelSoftmaxDiscretization(latent_dim=getattr(encoder, "w_dim", 512),
                                                          n_embeddings=n_embeddings)
         self.discretization = discretization
-        self.context_model = coder.ContextModel(n_symbols=n_embeddings)
+        self.context_model = coder.ContextModel(n_symbols=n_embeddings, track_state=bool(shared_model))
+        self.shared_model = bool(shared_model)
         self.container = container
         self.mode = mode
 
@@ -210,7 +214,11 @@ class CABACCompressor:
         n = self.discretization.n_embeddings
         shape = tuple(idx.shape)
         orig_size = idx.numel() * np.log2(n) / 8
-        if use_cabac:
+        if use_cabac and self.shared_model:
+            packed, nb = coder.cabac_encode_packed(idx.cpu().numpy(), self.context_model, mode=self.mode, device=idx.device)
+            encoded = (np.unpackbits(np.frombuffer(packed, dtype=np.uint8))[:nb].tobytes()
+                       if self.container == "reference" else packed)
+        elif use_cabac:
             layout = codec.layout_reference(shape)
             enc = codec.encode_batch(idx.reshape(-1), layout, n, mode=self.mode or coder.DEFAULT_MODE,
                                      adaptation_rate=self.context_model.adaptation_rate)
@@ -233,6 +241,9 @@ class CABACCompressor:
         n = metadata.get("n_embeddings", self.discretization.n_embeddings)
         dev = _module_device(self.generator, None) or self.discretization.codebook.device
         cb = self.discretization.codebook.to(dev)
+        if metadata.get("use_cabac", True) and self.shared_model:
+            codes = coder.cabac_decode(bytes(encoded_bytes), self.context_model, shape, mode=self.mode, device=dev)
+            return codec.dequantize_codebook(torch.from_numpy(codes).to(dev), cb)
         if metadata.get("use_cabac", True):
             layout = codec.layout_reference(shape)
             data, offsets, nbits = codec.pack_streams_for_device([bytes(encoded_bytes)], dev)

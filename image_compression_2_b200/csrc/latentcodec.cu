@@ -16,6 +16,7 @@
 #include "lc_decoder_v3.cuh"
 #include "lc_encoder_sparse.cuh"
 #include "lc_encoder_pack.cuh"
+#include "lc_stateful.cuh"
 
 #define LC_CUDA_RET()                                                     \
     do {                                                                  \
@@ -445,6 +446,31 @@ __global__ void __launch_bounds__(LC_B2_THREADS) lc_enc_phase_b2_kernel(LcCoderC
     lc_enc_phase_b2_block(cfg, B, first_bad, ivs, slots, slot_bytes, nbits, status, fault, lc_smem);
 }
 
+// stateful coder (lc_stateful.cuh): one warp, one stream, dense models in a direct-mapped table
+__global__ void __launch_bounds__(32) lc_stateful_encode_kernel(LcCoderCfg cfg, const int *__restrict__ codes,
+                                                                LcStatefulTable T, unsigned char *slot, uint32_t slot_bytes,
+                                                                int *nbits, int *status, int *fault)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    LcWarp W;
+    lc_warp_init(W, cfg, lc_smem, (char *)0);
+    int fi = 0;
+    const long long nb = lcs_encode_stream(W, T, codes, (uint32_t *)slot, slot_bytes / 4, &fi);
+    if (W.lane == 0) { *nbits = (int)nb; *status = W.status; *fault = fi; }
+}
+
+__global__ void __launch_bounds__(32) lc_stateful_decode_kernel(LcCoderCfg cfg, const unsigned char *__restrict__ bytes,
+                                                                long long nbytes, LcStatefulTable T, int *out, int *status,
+                                                                int *fault)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    LcWarp W;
+    lc_warp_init(W, cfg, lc_smem, (char *)0);
+    int fi = 0;
+    lcs_decode_stream(W, T, bytes, nbytes, out, &fi);
+    if (W.lane == 0) { *status = W.status; *fault = fi; }
+}
+
 // =================================================================================================
 // K4: stream compaction -- exclusive scan of the 16-byte-aligned stream sizes, then a word copy
 // =================================================================================================
@@ -847,5 +873,67 @@ int lc_debug_profile(unsigned long long *out64)
     return 0;
 }
 #endif
+
+static int lc_stateful_check(LcCoderCfg &cfg, LcStatefulTable &T, int imgs, int R, int C, int n, double rate, int mode,
+                             int has_ctx, void *table, int64_t table_bytes)
+{
+    int rc = lc_make_cfg(cfg, imgs, R, C, n, rate, mode, has_ctx);
+    if (rc) return rc;
+    if (has_ctx && n > 256) return -22;
+    if (!table || (((uintptr_t)table) & 255) != 0) return -22;
+    if (table_bytes < (int64_t)lc_stateful_bytes(n, cfg.has_ctx)) return -12;
+    T.valid = (unsigned char *)table;
+    T.counts = (int *)((char *)table + lc_stateful_off_counts(n, cfg.has_ctx));
+    T.vecs = (double *)((char *)table + lc_stateful_off_vecs(n, cfg.has_ctx));
+    return 0;
+}
+
+int64_t lc_stateful_table_bytes(int n_symbols, int has_ctx)
+{
+    if (n_symbols < 2 || n_symbols > 1024 || (n_symbols & (n_symbols - 1)) || (has_ctx && n_symbols > 256)) return -22;
+    return (int64_t)lc_stateful_bytes(n_symbols, has_ctx ? 1 : 0);
+}
+
+int64_t lc_stateful_table_offset(int n_symbols, int has_ctx, int which)
+{
+    if (lc_stateful_table_bytes(n_symbols, has_ctx) < 0) return -22;
+    if (which == 0) return 0;
+    if (which == 1) return (int64_t)lc_stateful_off_counts(n_symbols, has_ctx ? 1 : 0);
+    if (which == 2) return (int64_t)lc_stateful_off_vecs(n_symbols, has_ctx ? 1 : 0);
+    return -22;
+}
+
+int lc_stateful_encode(const int32_t *idx, int imgs, int R, int C, int n_symbols, double adaptation_rate, int mode,
+                       int has_ctx, void *table, int64_t table_bytes, uint8_t *slot, int64_t slot_bytes,
+                       int32_t *out_nbits, int32_t *status, int32_t *fault_index, void *stream)
+{
+    LcCoderCfg cfg;
+    LcStatefulTable T;
+    if (!idx || !slot || !out_nbits || !status || !fault_index) return -22;
+    if (slot_bytes < 16 || (slot_bytes & 3) || slot_bytes > 0xfffffff0ll) return -22;
+    int rc = lc_stateful_check(cfg, T, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx, table, table_bytes);
+    if (rc) return rc;
+    const size_t smem = (size_t)cfg.n * 8;
+    lc_stateful_encode_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(cfg, idx, T, slot, (uint32_t)slot_bytes, out_nbits,
+                                                                    status, fault_index);
+    LC_CUDA_RET();
+    return 0;
+}
+
+int lc_stateful_decode(const uint8_t *bytes, int64_t nbytes, int imgs, int R, int C, int n_symbols,
+                       double adaptation_rate, int mode, int has_ctx, void *table, int64_t table_bytes, int32_t *idx_out,
+                       int32_t *status, int32_t *fault_index, void *stream)
+{
+    LcCoderCfg cfg;
+    LcStatefulTable T;
+    if (!bytes || nbytes < 0 || !idx_out || !status || !fault_index || (((uintptr_t)bytes) & 3) != 0) return -22;
+    int rc = lc_stateful_check(cfg, T, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx, table, table_bytes);
+    if (rc) return rc;
+    const size_t smem = (size_t)cfg.n * 8;
+    lc_stateful_decode_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(cfg, bytes, (long long)nbytes, T, idx_out, status,
+                                                                    fault_index);
+    LC_CUDA_RET();
+    return 0;
+}
 
 } // extern "C"

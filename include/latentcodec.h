@@ -106,6 +106,30 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
                     int64_t scratch_bytes, int32_t *idx_out, const float *deq_table, float *deq_out, int32_t *status,
                     int32_t *fault_index, void *stream);
 
+/* ---- stateful coder: the reference's shared ContextModel (cabac_compression.py:438,478,517) --------------------- */
+
+/* The reference mutates one ContextModel object in cabac_encode and cabac_decode and across calls.  These two entry
+ * points code ONE stream (imgs images of R x C sharing coder and model, or has_ctx = 0) starting from the model held
+ * in `table` and leave the model the reference object would hold afterwards in it.  Table layout (device memory,
+ * lc_stateful_table_bytes bytes, key = (left+1)*(n+1) + (up+1) with -1 sentinels, one key when has_ctx = 0):
+ *   uint8 valid[nkeys]                      at byte 0            1 = the context exists in context_models
+ *   int32 counts[nkeys]                     at lc_stateful_table_offset(..., 1)   context_counts
+ *   float64 vectors[nkeys][n]               at lc_stateful_table_offset(..., 2)   the probability vectors
+ * The caller zeroes valid/counts, scatters the given model in, and gathers the valid entries after the call.
+ * n_symbols: power of two, <= 256 when has_ctx (the table is (n+1)^2 * n * 8 bytes), <= 1024 otherwise. */
+int64_t lc_stateful_table_bytes(int n_symbols, int has_ctx);
+int64_t lc_stateful_table_offset(int n_symbols, int has_ctx, int which);
+
+/* cabac_encode (:315-359) from/into the table's model.  slot: output, slot_bytes (multiple of 4) bytes. */
+int lc_stateful_encode(const int32_t *idx, int imgs, int R, int C, int n_symbols, double adaptation_rate, int mode,
+                       int has_ctx, void *table, int64_t table_bytes, uint8_t *slot, int64_t slot_bytes,
+                       int32_t *out_nbits, int32_t *status, int32_t *fault_index, void *stream);
+
+/* cabac_decode (:363-406) from/into the table's model.  bytes: 4-byte aligned, readable to a multiple of 4. */
+int lc_stateful_decode(const uint8_t *bytes, int64_t nbytes, int imgs, int R, int C, int n_symbols,
+                       double adaptation_rate, int mode, int has_ctx, void *table, int64_t table_bytes, int32_t *idx_out,
+                       int32_t *status, int32_t *fault_index, void *stream);
+
 /* number of thread blocks (= resident streams) the coder kernels launch for B streams */
 int lc_coder_grid(int B, int imgs, int R, int C, int n_symbols, int has_ctx);
 

@@ -155,11 +155,64 @@ def test_corrupt_streams_fault_like_the_oracle():
         assert np.array_equal(dec[b], ref["symbols"][0])
 
 
-def test_non_fresh_model_is_refused():
+def _model_of(cm):
+    """coder.ContextModel state as the oracle's {(left, up): (vector, count)} (global context: (-2, -2))."""
+    return {((-2, -2) if len(k) == 0 else (int(k[0]), int(k[1]))): (np.asarray(v, np.float64), int(cm.context_counts.get(k, 0)))
+            for k, v in cm.context_models.items()}
+
+
+def _same_model(a, b):
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k][1] == b[k][1] and np.array_equal(a[k][0], b[k][0]), k
+
+
+@pytest.mark.parametrize("n,shape", [(16, (2, 3, 30)), (64, (1, 4, 48)), (256, (1, 16, 128)), (16, (50,)), (1024, (40,))])
+def test_shared_context_model_across_calls(n, shape):
+    """The reference mutates ONE ContextModel in cabac_encode, cabac_decode and across calls (defect D5).  With a
+    non-empty model (or track_state=True) the stream is coded from that state and the object ends up holding what
+    the reference object would: bits, decoded symbols and every vector/count equal the oracle's (which is pinned
+    against the live reference in tests/test_oracle_vs_reference.py)."""
     from image_compression_2_b200 import coder
+    rng = np.random.default_rng(5 + n)
+    a = np.clip(np.round(rng.normal(n / 2, max(1, n / 16), shape)), 0, n - 1).astype(np.int32)
+    b = np.clip(np.round(rng.normal(n / 2, max(1, n / 16), shape)), 0, n - 1).astype(np.int32)
+    cm = coder.ContextModel(n, track_state=True)
+    model = {}
+    for codes in (a, b):
+        packed, nbits = coder.cabac_encode_packed(codes, cm)
+        ref, model = O.encode_stream_model(codes, n, model)
+        assert nbits == ref["nbits"] and packed == ref["packed"]
+        _same_model(_model_of(cm), model)
+    # a fresh untracked model is left alone and gives the fast kernels' (= fresh-model) stream
+    cm0 = coder.ContextModel(n)
+    packed0, _ = coder.cabac_encode_packed(a, cm0)
+    assert cm0.is_fresh() and packed0 == O.encode_stream(a, n)["packed"]
+    # decoding a fresh-model stream with the mutated model (what CABACCompressor.decompress does in the reference)
+    ref, model2 = O.decode_stream_model(packed0, n, a.shape, model)
+    try:
+        dec = coder.cabac_decode(packed0, cm, a.shape)
+        assert ref["status"] == 0 and np.array_equal(dec, ref["symbols"])
+    except (IndexError, ZeroDivisionError) as e:
+        assert ref["status"] != 0, e
+    _same_model(_model_of(cm), model2)
+    # decoding with the matching model state round-trips
+    cm_e, cm_d = coder.ContextModel(n, track_state=True), coder.ContextModel(n, track_state=True)
+    for codes in (a, b):
+        packed, _ = coder.cabac_encode_packed(codes, cm_e)
+        assert np.array_equal(coder.cabac_decode(packed, cm_d, codes.shape), codes)
+    _same_model(_model_of(cm_e), _model_of(cm_d))
+
+
+def test_stateful_model_limits():
+    from image_compression_2_b200 import coder
+    cm = coder.ContextModel(1024)
+    cm.context_models[(0, 0)] = np.ones(1024) / 1024
+    with pytest.raises(NotImplementedError):  # (left,up) contexts: the dense table is limited to 256 symbols
+        coder.cabac_encode(np.zeros((1, 2, 8), np.int32), cm)
     cm = coder.ContextModel(16)
-    cm.context_models[(0, 0)] = np.ones(16) / 16
-    with pytest.raises(NotImplementedError):
+    cm.context_models[(99, 0)] = np.ones(16) / 16
+    with pytest.raises(ValueError):
         coder.cabac_encode(np.zeros((1, 2, 8), np.int32), cm)
 
 

@@ -141,3 +141,22 @@ def test_bitrate_stats_of_a_coded_batch():
     st = stats.encoded_batch_stats(enc)
     assert st["streams"] == 32 and 7.9 < st["coded_bits_per_symbol"] < 8.1
     assert st["packed_bytes"]["total"] == int(((enc.nbits.cpu().numpy() + 7) // 8).sum())
+
+
+def test_cabac_compressor_shared_model_like_the_reference():
+    """shared_model=True: one ContextModel across compress calls (cabac_compression.py:438,478): the second image is
+    coded from the first image's final model -- the oracle's stateful encoder gives the same bytes."""
+    from image_compression_2_b200 import CABACCompressor
+    enc, gen = StubEncoder().cuda(), StubGenerator().cuda()
+    comp = CABACCompressor(enc, gen, n_embeddings=64, shared_model=True)
+    fresh = CABACCompressor(enc, gen, n_embeddings=64)
+    x1, x2 = torch.randn(1, 3, 64, 64).cuda(), torch.randn(1, 3, 64, 64).cuda()
+    model = {}
+    for x in (x1, x2):
+        encoded, meta = comp.compress(x)
+        codes = fresh._codes_device(x).cpu().numpy()
+        ref, model = O.encode_stream_model(codes, 64, model)
+        assert encoded == ref["packed"] and meta["comp_size"] == len(ref["packed"])
+    assert len(comp.context_model.context_models) == len(model)
+    e1, _ = fresh.compress(x2)
+    assert e1 == O.encode_stream(fresh._codes_device(x2).cpu().numpy(), 64)["packed"] and e1 != encoded
