@@ -552,7 +552,7 @@ static int lc_grid_for(const LcCoderCfg &cfg, int B)
 
 // parallel-encoder workspace per stream: sorted keys (4 B) + positions (2 B) + two float64 bounds
 #define LC_PAR_STREAM_BYTES ((int64_t)LC_PAR_MAX_SYMBOLS * (4 + 2 + 8 + 8) + LC_PAR_MAX_GROUPS * 2 + 32)
-#define LC_PAR_TILE 2048
+#define LC_PAR_TILE 8192
 
 static bool lc_use_parallel_encoder(const LcCoderCfg &cfg) { return cfg.has_ctx && cfg.total <= LC_PAR_MAX_SYMBOLS; }
 
