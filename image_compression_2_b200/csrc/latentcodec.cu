@@ -242,11 +242,12 @@ __global__ void __launch_bounds__(32 * LCV_WARPS, 8) lc_decode_v2_kernel(LcCoder
                                                                           const int *__restrict__ nbits, int B, int *out,
                                                                           const float *__restrict__ deq_table,
                                                                           float *deq_out, int *status, int *fault,
-                                                                          char *scratch, const double *tables)
+                                                                          char *scratch, const double *tables,
+                                                                          const char *t2)
 {
     extern __shared__ __align__(16) char lc_smem[];
     lcv_decode_block<0, 0, 0>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables,
-                              lc_smem);
+                              t2, lc_smem);
 }
 
 // the W+ latent shape of the reference (8-bit codes of a [16,512] latent, one image per stream), fixed at compile time
@@ -256,11 +257,12 @@ __global__ void __launch_bounds__(32 * LCV_WARPS, 8) lc_decode_v2_w8_kernel(LcCo
                                                                              const int *__restrict__ nbits, int B, int *out,
                                                                              const float *__restrict__ deq_table,
                                                                              float *deq_out, int *status, int *fault,
-                                                                             char *scratch, const double *tables)
+                                                                             char *scratch, const double *tables,
+                                                                             const char *t2)
 {
     extern __shared__ __align__(16) char lc_smem[];
     lcv_decode_block<256, 512, 16>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch,
-                                   tables, lc_smem);
+                                   tables, t2, lc_smem);
 }
 
 // Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream
@@ -408,19 +410,20 @@ __global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS) lc_enc_phase_a_sparse_ke
     LcCoderCfg cfg, const int *__restrict__ codes, int B, const uint32_t *__restrict__ skeys,
     const unsigned short *__restrict__ spos, const int *__restrict__ first_bad, const unsigned short *__restrict__ glist,
     const int *__restrict__ ngroups, double *ivs, unsigned int *task_counter, const double *__restrict__ tables,
-    const double *__restrict__ t2)
+    const char *__restrict__ t2)
 {
     extern __shared__ __align__(16) char lc_smem[];
     lc_enc_phase_a_sparse_block(cfg, codes, B, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables, t2,
                                 lc_smem);
 }
 
-// per-launch table of the models after two visits (lcs_t2_block)
-__global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS) lc_enc_t2_kernel(LcCoderCfg cfg, const double *__restrict__ tables,
-                                                                         double *t2)
+// per-launch records of the models after two visits (lcv_t2_block), used by the encoder's phase A and the
+// decoder's updater warps
+__global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS) lc_t2_kernel(LcCoderCfg cfg, const double *__restrict__ tables,
+                                                                     char *t2)
 {
     extern __shared__ __align__(16) char lc_smem[];
-    lcs_t2_block(cfg, tables, t2, lc_smem);
+    lcv_t2_block(cfg, tables, t2, lc_smem);
 }
 
 __global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
@@ -584,7 +587,8 @@ static int64_t lc_v2_scratch_need(const LcCoderCfg &cfg, int B)
 {
     LcV2Cfg vc;
     lcv_cfg_make(cfg, &vc);
-    return (int64_t)lc_v2_grid(vc, B) * (int64_t)vc.g_stride + (int64_t)lcv_tables_bytes(cfg.n) + 256;
+    return (int64_t)lc_v2_grid(vc, B) * (int64_t)vc.g_stride + (int64_t)lcv_tables_bytes(cfg.n) + 512 +
+           (int64_t)cfg.n * cfg.n * 64;
 }
 
 static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
@@ -597,7 +601,7 @@ static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
     if (lc_use_parallel_encoder(cfg)) {
         const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES + 512 +
                             (int64_t)lcv_tables_bytes(cfg.n) +
-                            (cfg.n <= LCS_T2_MAX_N ? (int64_t)cfg.n * cfg.n * LCS_T2_STRIDE * 8 : 0);
+                            (cfg.n <= LCS_T2_MAX_N ? (int64_t)cfg.n * cfg.n * 64 : 0);
         if (par > need) need = par;
     }
     return need;
@@ -723,14 +727,14 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
         double *tables = (double *)((char *)scratch + (((size_t)tile * LC_PAR_STREAM_BYTES + 255) & ~(size_t)255));
         // ... and, for alphabets up to LCS_T2_MAX_N symbols, the models after two visits.  The second table pays
         // for itself once the batch holds a few times n*n/1000 streams.
-        double *t2 = (double *)0;
+        char *t2 = (char *)0;
         if (sparse_variant) {
             lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
             LC_CUDA_RET();
             if (cfg.n <= LCS_T2_MAX_N && (long long)B * 1000 >= (long long)cfg.n * cfg.n) {
-                t2 = tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255) / 8;
+                t2 = (char *)tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255);
                 const size_t t2_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;
-                lc_enc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, t2_smem, st>>>(cfg, tables, t2);
+                lc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, t2_smem, st>>>(cfg, tables, t2);
                 LC_CUDA_RET();
             }
         }
@@ -824,6 +828,13 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
         if (vc.sm_bytes > 64 * 1024) return -22;
         lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
         LC_CUDA_RET();
+        // records of the models after two visits: the updater's job for a second visit becomes a copy
+        char *t2 = (char *)0;
+        if (lc_decoder_choice() == 2 && (long long)B * 1000 >= (long long)cfg.n * cfg.n) {
+            t2 = (char *)tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255);
+            lc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, (size_t)LCS_BLOCK_WARPS * cfg.n * 8, st>>>(cfg, tables, t2);
+            LC_CUDA_RET();
+        }
         if (lc_decoder_choice() == 3 && cfg.total <= (1 << 21))
             lc_decode_v3_kernel<<<g2, 32 * LC3_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
                                                                          B, idx_out, deq_table, deq_out, status,
@@ -831,11 +842,11 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
         else if (cfg.n == 256 && cfg.C == 512 && cfg.R == 16 && cfg.imgs == 1 && !getenv("LC_DECODER_GENERIC"))
             lc_decode_v2_w8_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets,
                                                                             nbits, B, idx_out, deq_table, deq_out, status,
-                                                                            fault_index, (char *)scratch, tables);
+                                                                            fault_index, (char *)scratch, tables, t2);
         else
             lc_decode_v2_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
                                                                          B, idx_out, deq_table, deq_out, status,
-                                                                         fault_index, (char *)scratch, tables);
+                                                                         fault_index, (char *)scratch, tables, t2);
         LC_CUDA_RET();
         lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
                                                          deq_table, deq_out, status, fault_index, (char *)scratch,

@@ -236,6 +236,7 @@ struct LcV2 {
     char *grec;               // per context: 64-byte inline record  u | val[6] | sym[6] k pad
     char *pool;
     const double *cum1;
+    const char *t2;           // per-launch records of the models after two visits (lcv_t2_block), or null
     uint32_t pool_bytes, eps_k, lg_n;
 };
 
@@ -260,7 +261,54 @@ __device__ __forceinline__ void lcv_load_pool(LcFast &F, const LcV2 &V, uint32_t
     F.my_sym = valid ? (int)__ldcg((const unsigned short *)(rec + 8 + (8 << cl)) + F.lane) : 0x7fffffff;
 }
 
-// lane-distributed register model from an inline record
+// store the register model (at most LCV_INLINE_K entries) as a 64-byte record  u | val[6] | sym[6] k
+__device__ __forceinline__ void lcv_record_store(char *rec, const LcFast &F)
+{
+    if (F.lane == 0) { __stcg((double *)rec, F.u); __stcg((unsigned char *)rec + 62, (unsigned char)F.k); }
+    if (F.lane < F.k) {
+        __stcg((double *)(rec + 8) + F.lane, F.my_val);
+        __stcg((unsigned char *)rec + 56 + F.lane, (unsigned char)F.my_sym);
+    }
+}
+
+// Records of the model after the first TWO visits of a context, for every ordered pair (s1, s2): like cum1 they
+// depend only on (n, rate), so n^2 updates once per launch replace one update per context (a quarter of the
+// encoder's phase A, and the updater's job for every second visit -- which becomes a 64-byte copy).  n <= 256.
+// Record (s1*n + s2) at t2 + 64*(s1*n + s2).  One warp per pair; smem: one n-double image per warp.
+__device__ __forceinline__ void lcv_t2_block(const LcCoderCfg &cfg, const double *tables, char *t2, char *smem)
+{
+    const int warp = (int)(threadIdx.x >> 5), n_warps = (int)(blockDim.x >> 5);
+    LcFast F;
+    F.n = cfg.n; F.C = cfg.C; F.R = cfg.R; F.total = cfg.total; F.lane = (int)(threadIdx.x & 31);
+    F.rate = cfg.rate; F.delta = cfg.delta; F.u0 = LC_DDIV(1.0, (double)cfg.n);
+    F.delta_v = 0.0; F.tmargin = 0.0;
+    F.P1 = LC_DADD(F.u0, LC_DMUL(F.rate, LC_DSUB(1.0, F.u0)));
+    F.slot_cap = 0; F.slot_shift = 0; F.pool_bytes = 0; F.pool_top = 0;
+    F.pw_len = cfg.pw_len; F.pw_steps = cfg.pw_steps; F.pw_chains = cfg.pw_chains;
+    F.slots = (unsigned long long *)0; F.pool = (char *)0;
+    F.dense = (double *)smem + (size_t)warp * cfg.n;
+    F.u1tab = const_cast<double *>(tables); F.rows = (unsigned short *)0;
+    F.k = 0; F.u = F.u0; F.my_sym = 0x7fffffff; F.my_val = 0.0;
+    const int n = cfg.n, pairs = n * n;
+    for (int e = (int)blockIdx.x * n_warps + warp; e < pairs; e += (int)gridDim.x * n_warps) {
+        lcf_state_first(F, e / n);
+        lcf_update(F, e % n); // k <= 2: cannot overflow
+        lcv_record_store(t2 + (size_t)e * 64, F);
+        __syncwarp();
+    }
+}
+
+// lane-distributed register model from a 64-byte record
+__device__ __forceinline__ void lcv_record_load(LcFast &F, const char *rec)
+{
+    int k = (int)__ldcg((const unsigned char *)rec + 62);
+    if (k > LCV_INLINE_K) k = LCV_INLINE_K;
+    F.k = k;
+    F.u = __ldcg((const double *)rec);
+    const bool valid = F.lane < k;
+    F.my_val = valid ? __ldcg((const double *)(rec + 8) + F.lane) : 0.0;
+    F.my_sym = valid ? (int)__ldcg((const unsigned char *)rec + 56 + F.lane) : 0x7fffffff;
+}
 __device__ __forceinline__ void lcv_load_inline(LcFast &F, const LcV2 &V, uint32_t key)
 {
     const char *rec = V.grec + (size_t)key * 64;
@@ -294,6 +342,19 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
             const int s = LCV_PAY_S(pay), st = LCV_PAY_ST(pay);
             const uint32_t shift = (key & 15u) * 2u;
             uint32_t word = 0u;
+            if (st == 1 && V.t2) {
+                // second visit: the model after (s1, s) is a per-launch record -- copy it
+                if (F.lane < 4) {
+                    const double2 v = __ldg((const double2 *)(V.t2 + ((size_t)LCV_PAY_S1(pay) * F.n + s) * 64) + F.lane);
+                    __stcg((double2 *)(V.grec + (size_t)key * 64) + F.lane, v);
+                }
+                LCV_FENCE();
+                if (F.lane == 0) atomicXor(V.sbits + (key >> 4), 3u << shift); // 01 -> 10
+                __syncwarp();
+                LCV_FENCE();
+                if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+                continue;
+            }
             if (st == 1) lcf_state_first(F, LCV_PAY_S1(pay));
             else if (st == 2) lcv_load_inline(F, V, key);
             else { word = __ldcg(V.gword + key); lcv_load_pool(F, V, word); }
@@ -301,12 +362,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
             if (!lcf_update(F, s)) {
                 if (F.lane == 0) atomicCAS(V.abort_code, 0u, (uint32_t)LC_NEEDS_GENERIC);
             } else if (F.k <= LCV_INLINE_K) {
-                char *rec = V.grec + (size_t)key * 64;
-                if (F.lane == 0) { __stcg((double *)rec, F.u); __stcg((unsigned char *)rec + 62, (unsigned char)F.k); }
-                if (F.lane < F.k) {
-                    __stcg((double *)(rec + 8) + F.lane, F.my_val);
-                    __stcg((unsigned char *)rec + 56 + F.lane, (unsigned char)F.my_sym);
-                }
+                lcv_record_store(V.grec + (size_t)key * 64, F);
                 LCV_FENCE();
                 if (st == 1 && F.lane == 0) atomicXor(V.sbits + (key >> 4), 3u << shift); // 01 -> 10
             } else {
@@ -660,7 +716,7 @@ template <int FN, int FC, int FR>
 __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const LcV2Cfg &vc, const unsigned char *bytes,
                                                  const long long *offsets, const int *nbits, int B, int *out,
                                                  const float *deq_table, float *deq_out, int *status, int *fault,
-                                                 char *scratch, const double *tables, char *smem)
+                                                 char *scratch, const double *tables, const char *t2, char *smem)
 {
     const int warp = (int)(threadIdx.x >> 5);
     LcV2 V;
@@ -674,6 +730,7 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
     char *sc = scratch + (size_t)blockIdx.x * vc.g_stride;
     V.gword = (uint32_t *)(sc + vc.g_word); V.grec = sc + vc.g_rec; V.pool = sc + vc.g_pool;
     V.cum1 = tables + 64;
+    V.t2 = t2;
     V.pool_bytes = vc.pool_bytes; V.eps_k = vc.eps_k; V.lg_n = vc.lg_n;
     LcFast F;
     F.n = cfg.n; F.C = cfg.C; F.R = cfg.R; F.total = cfg.total; F.lane = (int)(threadIdx.x & 31);

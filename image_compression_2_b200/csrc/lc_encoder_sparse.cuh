@@ -19,40 +19,10 @@
 // Every float64 operation is the reference's operation on the same operands in the same order.
 #pragma once
 #include "lc_encoder_par.cuh"
-#include "lc_decoder_fast.cuh"
+#include "lc_decoder_v2.cuh"
 
 #define LCS_TASK_GROUPS 16
-#define LCS_T2_MAX_N 256 // the table of models after two visits is built for alphabets up to this size
-#define LCS_T2_STRIDE 4  // doubles per entry: u | val of the smaller symbol | val of the larger symbol | unused
-
-// Model after the first TWO visits of a context, for every ordered pair (s1, s2) of symbols: like cum1 it depends
-// only on (n, rate), so it is computed once per launch (n^2 updates, ~1.5 % of phase A's work on the benchmark)
-// instead of once per context (a quarter of phase A's work).  Entry (s1*n + s2): u, then the values of the (one or
-// two) observed symbols in ascending symbol order.  One warp per pair.
-__device__ __forceinline__ void lcs_t2_block(const LcCoderCfg &cfg, const double *tables, double *t2, char *smem)
-{
-    const int warp = (int)(threadIdx.x >> 5), n_warps = (int)(blockDim.x >> 5);
-    LcFast F;
-    F.n = cfg.n; F.C = cfg.C; F.R = cfg.R; F.total = cfg.total; F.lane = (int)(threadIdx.x & 31);
-    F.rate = cfg.rate; F.delta = cfg.delta; F.u0 = LC_DDIV(1.0, (double)cfg.n);
-    F.delta_v = 0.0; F.tmargin = 0.0;
-    F.P1 = LC_DADD(F.u0, LC_DMUL(F.rate, LC_DSUB(1.0, F.u0)));
-    F.slot_cap = 0; F.slot_shift = 0; F.pool_bytes = 0; F.pool_top = 0;
-    F.pw_len = cfg.pw_len; F.pw_steps = cfg.pw_steps; F.pw_chains = cfg.pw_chains;
-    F.slots = (unsigned long long *)0; F.pool = (char *)0;
-    F.dense = (double *)smem + (size_t)warp * cfg.n;
-    F.u1tab = const_cast<double *>(tables); F.rows = (unsigned short *)0;
-    F.k = 0; F.u = F.u0; F.my_sym = 0x7fffffff; F.my_val = 0.0;
-    const int n = cfg.n, pairs = n * n;
-    for (int e = (int)blockIdx.x * n_warps + warp; e < pairs; e += (int)gridDim.x * n_warps) {
-        lcf_state_first(F, e / n);
-        lcf_update(F, e % n); // k <= 2: cannot overflow
-        double *o = t2 + (size_t)e * LCS_T2_STRIDE;
-        if (F.lane == 0) o[0] = F.u;
-        if (F.lane < F.k) o[1 + F.lane] = F.my_val;
-        __syncwarp();
-    }
-}
+#define LCS_T2_MAX_N 256 // the table of models after two visits (lcv_t2_block) is built for alphabets up to this size
 
 // Work list of phase A for one stream, and the intervals that need no model: glist[g] = sorted index of the first
 // visit of the g-th context visited at least three times; first visits get i/n, second visits the table row of
@@ -97,7 +67,7 @@ __device__ __forceinline__ void lc_enc_phase_a_sparse_block(const LcCoderCfg &cf
                                                             const int *first_bad, const unsigned short *glist_all,
                                                             const int *ngroups_all, double *ivs_all,
                                                             unsigned int *task_counter, const double *tables,
-                                                            const double *t2, char *smem)
+                                                            const char *t2, char *smem)
 {
     const int warp = (int)(threadIdx.x >> 5);
     LcFast F;
@@ -139,14 +109,8 @@ __device__ __forceinline__ void lc_enc_phase_a_sparse_block(const LcCoderCfg &cf
             const uint32_t key = skeys[j0];
             // model after the first two visits: from the per-launch table, or computed (the first update is closed form)
             const int sa = codes[spos[j0]], sb = codes[spos[j0 + 1]];
-            if (t2) {
-                const double *e = t2 + ((size_t)sa * F.n + sb) * LCS_T2_STRIDE;
-                F.k = sa == sb ? 1 : 2;
-                F.u = e[0];
-                const int lo_s = sa < sb ? sa : sb, hi_s = sa < sb ? sb : sa;
-                F.my_sym = F.lane == 0 ? lo_s : (F.lane == 1 && F.k == 2 ? hi_s : 0x7fffffff);
-                F.my_val = F.lane < F.k ? e[1 + F.lane] : 0.0;
-            } else {
+            if (t2) lcv_record_load(F, t2 + ((size_t)sa * F.n + sb) * 64);
+            else {
                 lcf_state_first(F, sa);
                 lcf_update(F, sb); // k <= 2: cannot overflow
             }

@@ -219,21 +219,26 @@ extern "C" int hostsim_decode_fast(const unsigned char *bytes, const long long *
 }
 
 // decoder v2 (decoder warp + updater warps per block) followed by the generic redo pass, as the host does
-struct DecV2Args { DecArgs d; LcV2Cfg vc; double *tables; char *scratch2; };
+struct DecV2Args { DecArgs d; LcV2Cfg vc; double *tables; char *scratch2; char *t2; };
 static void decv2_tables_body(void *p)
 {
     DecV2Args *a = (DecV2Args *)p;
     lcv_tables_block(a->d.cfg, a->tables, a->d.smem);
+}
+static void decv2_t2_body(void *p)
+{
+    DecV2Args *a = (DecV2Args *)p;
+    lcv_t2_block(a->d.cfg, a->tables, a->t2, a->d.smem);
 }
 static void decv2_body(void *p)
 {
     DecV2Args *a = (DecV2Args *)p;
     if (a->d.cfg.n == 256 && a->d.cfg.C == 512 && a->d.cfg.R == 16 && a->d.cfg.imgs == 1)
         lcv_decode_block<256, 512, 16>(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table,
-                                       a->d.deq_out, a->d.status, a->d.fault, a->scratch2, a->tables, a->d.smem);
+                                       a->d.deq_out, a->d.status, a->d.fault, a->scratch2, a->tables, a->t2, a->d.smem);
     else
     lcv_decode_block<0, 0, 0>(a->d.cfg, a->vc, a->d.bytes, a->d.offsets, a->d.nbits, a->d.B, a->d.out, a->d.deq_table, a->d.deq_out,
-                     a->d.status, a->d.fault, a->scratch2, a->tables, a->d.smem);
+                     a->d.status, a->d.fault, a->scratch2, a->tables, a->t2, a->d.smem);
 }
 static void decv3_body(void *p)
 {
@@ -261,7 +266,15 @@ extern "C" int hostsim_decode_v2(const unsigned char *bytes, const long long *of
     a.d.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     a.tables = tables.data();
     a.scratch2 = (char *)(((uintptr_t)scratch2.data() + 255) & ~(uintptr_t)255);
+    std::vector<char> t2rec;
+    a.t2 = (char *)0;
     for (int b = 0; b < 3; b++) emu::run_warp(decv2_tables_body, &a, (unsigned)b, 3u);
+    if (g_decoder_version == 2 && n <= 64) { // small alphabets also exercise the two-visit records (updater copy path)
+        t2rec.assign((size_t)n * n * 64 + 64, (char)0xCD);
+        a.t2 = t2rec.data();
+        for (int b = 0; b < 2; b++)
+            for (int w = 0; w < 2; w++) emu::run_warp(decv2_t2_body, &a, (unsigned)b, 2u, (unsigned)w, 2u);
+    }
     if (g_decoder_version == 3)
         for (int b = 0; b < grid; b++) emu::run_block(decv3_body, &a, (unsigned)b, (unsigned)grid, LC3_WARPS);
     else
@@ -285,7 +298,7 @@ extern "C" void hostsim_stats(long long *out, int reset)
 // checked on the GPU), phases A and B run through the emulator
 struct ParAArgs { LcCoderCfg cfg; const int *codes; int B; const uint32_t *skeys; const unsigned short *spos;
                   const int *first_bad; double *ivs; char *smem; unsigned short *glist; int *ngroups; unsigned int *task_counter;
-                  double *tables; double *t2; };
+                  double *tables; char *t2; };
 static void para_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
@@ -307,7 +320,7 @@ static void para_lanes_body(void *p)
 static void para_t2_body(void *p)
 {
     ParAArgs *a = (ParAArgs *)p;
-    lcs_t2_block(a->cfg, a->tables, a->t2, a->smem);
+    lcv_t2_block(a->cfg, a->tables, a->t2, a->smem);
 }
 static void glist_body(void *p)
 {   // phase S part: group list + first-visit intervals (on the GPU this is done by lc_enc_sort_kernel)
@@ -382,10 +395,10 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
     std::vector<double> tables(lcv_tables_bytes(n) / 8 + 8, -777.0);
     ParAArgs a{cfg, codes, B, skeys.data(), spos.data(), first_bad.data(), ivs.data(),
                (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15), glist.data(), ngroups.data(), &task_counter,
-               tables.data(), (double *)0};
-    std::vector<double> t2;
-    if (nwarps == 0 && n <= 64) { // small alphabets also exercise the table of models after two visits
-        t2.assign((size_t)n * n * LCS_T2_STRIDE, -555.0);
+               tables.data(), (char *)0};
+    std::vector<char> t2;
+    if (nwarps == 0 && n <= 64) { // small alphabets also exercise the records of the models after two visits
+        t2.assign((size_t)n * n * 64, (char)0xCD);
         a.t2 = t2.data();
     }
     if (nwarps == 0) { // sparse variant: second visits from the table, one warp per context visited three times or more
