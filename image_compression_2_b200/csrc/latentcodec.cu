@@ -830,7 +830,9 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
         LC_CUDA_RET();
         // records of the models after two visits: the updater's job for a second visit becomes a copy
         char *t2 = (char *)0;
-        if (lc_decoder_choice() == 2 && (long long)B * 1000 >= (long long)cfg.n * cfg.n) {
+        // (measured neutral on the decode time -- the updater is not the bottleneck -- so only where the table's
+        // n^2 updates are small against the batch: >= 4096 streams at n = 256)
+        if (lc_decoder_choice() == 2 && (long long)B * 16 >= (long long)cfg.n * cfg.n) {
             t2 = (char *)tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255);
             lc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, (size_t)LCS_BLOCK_WARPS * cfg.n * 8, st>>>(cfg, tables, t2);
             LC_CUDA_RET();

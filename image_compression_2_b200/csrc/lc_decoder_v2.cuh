@@ -327,12 +327,25 @@ __device__ __forceinline__ void lcv_load_inline(LcFast &F, const LcV2 &V, uint32
 // j: this warp's next job (jobs are numbered through all streams of the block; warp u takes j = u mod LCV_NU)
 __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &j)
 {
+#ifdef LC_DEC_PROFILE // busy cycles and job counts per context state -> lc_prof_global[56..63]
+    unsigned long long lcu_busy[4] = {0ull, 0ull, 0ull, 0ull}, lcu_jobs[4] = {0ull, 0ull, 0ull, 0ull};
+    long long lcu_t = 0; int lcu_st = 0;
+#define LCU_BEGIN(st_) do { lcu_st = (st_); lcu_t = clock64(); } while (0)
+#define LCU_END() do { lcu_busy[lcu_st] += (unsigned long long)(clock64() - lcu_t); lcu_jobs[lcu_st] += 1ull; } while (0)
+#else
+#define LCU_BEGIN(st_)
+#define LCU_END()
+#endif
     for (;; j += LCV_NU) {
         const uint32_t slot = j & (LCV_RING - 1);
         lcv_bar_wait(V.ring_bar + slot, (j / LCV_RING) & 1u);
         const uint32_t key = lcv_ld_vol(V.ring_key + slot);
         const uint32_t pay = lcv_ld_vol(V.ring_pay + slot);
+        LCU_BEGIN(LCV_PAY_ST(pay));
         if (key == LCV_SENTINEL) {
+#ifdef LC_DEC_PROFILE
+            if (F.lane == 0) for (int i_ = 0; i_ < 4; i_++) { atomicAdd(&lc_prof_global[56 + i_], lcu_busy[i_]); atomicAdd(&lc_prof_global[60 + i_], lcu_jobs[i_]); }
+#endif
             __syncwarp();
             if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
             j += LCV_NU;
@@ -353,6 +366,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
                 __syncwarp();
                 LCV_FENCE();
                 if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+                LCU_END();
                 continue;
             }
             if (st == 1) lcf_state_first(F, LCV_PAY_S1(pay));
@@ -398,6 +412,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
         __syncwarp();
         LCV_FENCE();
         if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+        LCU_END();
     }
 }
 

@@ -59,3 +59,7 @@ for st in range(4):
     cnt = max(t[st, 0], 1)
     print("state %d: exact-search fallbacks %.2f%%, exact_at fallbacks %.2f%%, waits for a recent job %.2f%%" % (
         st, 100 * t[4, st] / cnt, 100 * t[5, st] / cnt, 100 * t[6, st] / cnt))
+if v2:
+    busy, jobs = t[7, 0:4], t[7, 4:8]
+    print("updater warp: busy cycles/job by state " + " ".join("%d: %.0f (%.1f%% of symbols)" % (i, busy[i] / max(jobs[i], 1), 100 * jobs[i] / nsym) for i in range(1, 4)))
+    print("updater warp: busy cycles/symbol %.0f" % (busy.sum() / nsym))
