@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--kind", default="enc_like")
     ap.add_argument("--cpu-sample-streams", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--large-batch", type=int, default=8192,
+                    help="streams per GPU of the supplementary throughput measurement (0 = skip); 8192 is config 4's "
+                         "share per GPU (65,536 latents over 8 GPUs)")
     return ap.parse_args()
 
 
@@ -343,6 +346,41 @@ def run_b200(args):
     # optional size gather (not timed; the only collective this framework has)
     sizes, _ = sharding.gather_shard_bytes(int(enc.offsets[-1]), device=dev)
 
+    # ---- supplementary: the same round trip at config 4's per-GPU share (several waves of blocks per launch instead
+    # of one), device-resident like `value`; reported beside the headline, never instead of it
+    large = None
+    if args.large_batch > B and args.kind == "enc_like" and args.bits == 8:
+        B2, steps2 = args.large_batch, 3
+        lat2 = synth(args.kind, B2, 1000 + 4 * 100000 + rank).to(dev)
+
+        def step_large():
+            idx2 = pipe.quantize(lat2)
+            enc2 = pipe.encode(idx2)
+            return idx2, enc2, pipe.decode(enc2.data, enc2.offsets, enc2.nbits, B2)
+
+        idx2, enc2, (dec2, _, dst2, _) = step_large()
+        torch.cuda.synchronize()
+        assert int(enc2.status.abs().sum()) == 0 and int(dst2.abs().sum()) == 0 and torch.equal(dec2.view(B2, R, C), idx2)
+        del idx2, enc2, dec2, dst2
+        barrier()
+        t2 = []
+        for _ in range(steps2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_large()
+            e1.record(stream)
+            e1.synchronize()
+            t2.append(e0.elapsed_time(e1))
+        barrier()
+        t2_total = torch.tensor([sum(t2)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2_total, op=dist.ReduceOp.MAX)
+        v2 = world * B2 * SYMS * steps2 / (float(t2_total) * 1e-3)
+        large = {"workload": "cfg4 share: %d synthetic W+ latents per GPU (65,536 over 8 GPUs), 8-bit round trip" % B2,
+                 "streams_per_gpu": B2, "value": v2, "unit": UNIT, "streams_per_s": v2 / SYMS, "steps": steps2,
+                 "ms_per_step": float(t2_total) / steps2, "parity": "round-trip identity on all streams"}
+
     if rank == 0:
         total_syms = world * B * SYMS
         value = total_syms * args.steps / (ms_total * 1e-3)
@@ -359,7 +397,7 @@ def run_b200(args):
         dec_ms = sum(t_dec) / len(t_dec)
         facts = {}
         try:
-            facts = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_facts.json"))).get("lc_decode_v2_kernel", {})
+            facts = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_facts.json"))).get("lc_decode_v2_w8_kernel" if (n == 256 and R == 16 and C == 512) else "lc_decode_v2_kernel", {})
         except Exception:
             pass
         same_cfg = facts.get("streams") == B and facts.get("n_symbols") == n
@@ -378,7 +416,7 @@ def run_b200(args):
             # per step: quantise, tables, two-visit table, sort, phase A, phase B1, B2, size scan, compaction,
             # tables, decode, redo pass
             "gpu_launches": 12 * args.steps,
-            "roofline": {"kernel": "lc_decode_v2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "lc_decode_v2_w8_kernel" if (n == 256 and R == 16 and C == 512) else "lc_decode_v2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": facts.get("dram_bytes_per_launch") if same_cfg else None,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
@@ -386,13 +424,15 @@ def run_b200(args):
                          "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms_total / args.steps),
                          "warp_inst_per_symbol": facts.get("warp_inst_per_symbol") if same_cfg else None,
                          "issue_slot_utilisation": facts.get("issue_slot_utilisation") if same_cfg else None,
-                         "ncu": "profiles/r01_ncu_all_kernels_v7.md",
+                         "ncu": "profiles/r01_ncu_all_kernels_v8.md",
                          "note": "decode = dependent chain per stream: latency/issue-bound, not HBM-bound "
                                  "(DESIGN.md section 5); traffic above the algorithmic bytes is the per-stream "
                                  "context words + 64-byte records"},
             "clocks": clocks,
             "rank_bytes": [int(x) for x in sizes.tolist()],
         }
+        if large is not None:
+            line["large_batch"] = large
         if not args.no_cpu_baseline:
             codes, threads = cpu_sample(args, n)
             cv, cdt, cs = cpu_roundtrip_rate(codes, n, threads, repeats=cpu_repeats(codes.shape[0], n, threads))
