@@ -136,6 +136,66 @@ static __device__ __forceinline__ void lcv_bar_wait(unsigned long long *b, uint3
 }
 #endif
 
+// Shared-memory accesses of the decoder warp's hot loop go through 32-bit shared-window addresses held in
+// registers (inline PTX), not through generic pointers: on sm_100a every access through a generic pointer to
+// dynamic shared memory re-derives the window base (S2UR CgaCtaId / ULEA / LDCU, three to four instructions per
+// access, measured 15 % of the decoder warp's instructions) and each pointer costs two registers.
+#ifdef LC_HOSTSIM
+typedef uintptr_t lcv_sa; // on the emulator a "shared address" is the host pointer
+static inline lcv_sa lcv_sa_of(const void *p) { return (lcv_sa)p; }
+static inline uint32_t lcv_sa_ld32(lcv_sa a) { return *(const volatile uint32_t *)a; }
+static inline void lcv_sa_st32(lcv_sa a, uint32_t v) { *(volatile uint32_t *)a = v; }
+static inline uint32_t lcv_sa_ld32_acq(lcv_sa a) { return *(const volatile uint32_t *)a; }
+static inline int lcv_sa_ld8(lcv_sa a) { return (int)*(const volatile unsigned char *)a; }
+static inline void lcv_sa_st8(lcv_sa a, int v) { *(volatile unsigned char *)a = (unsigned char)v; }
+static inline double lcv_sa_ldf64(lcv_sa a) { return *(const volatile double *)a; }
+static inline void lcv_sa_or32(lcv_sa a, uint32_t v) { atomicOr((uint32_t *)a, v); }
+static inline void lcv_sa_bar_arrive(lcv_sa b) { *(volatile unsigned long long *)b += 1ull; }
+#else
+typedef uint32_t lcv_sa;
+static __device__ __forceinline__ lcv_sa lcv_sa_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ uint32_t lcv_sa_ld32(lcv_sa a)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ void lcv_sa_st32(lcv_sa a, uint32_t v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
+}
+static __device__ __forceinline__ uint32_t lcv_sa_ld32_acq(lcv_sa a)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+static __device__ __forceinline__ int lcv_sa_ld8(lcv_sa a)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return (int)v;
+}
+static __device__ __forceinline__ void lcv_sa_st8(lcv_sa a, int v)
+{
+    asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v));
+}
+static __device__ __forceinline__ double lcv_sa_ldf64(lcv_sa a) // per-launch constants: plain load
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ void lcv_sa_or32(lcv_sa a, uint32_t v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+static __device__ __forceinline__ void lcv_sa_bar_arrive(lcv_sa b) // release.cta
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
+}
+#endif
+
 // ---- tables kernel body, one warp (block) per first symbol s1: u after the first update with s1 (its value
 // depends only on s1's accumulator-chain step; the block of the step's first symbol publishes it with its
 // reciprocal), and the exact np.cumsum (:346-347) of the model after that update.
@@ -238,7 +298,15 @@ struct LcV2 {
     const double *cum1;
     const char *t2;           // per-launch records of the models after two visits (lcv_t2_block), or null
     uint32_t pool_bytes, eps_k, lg_n;
+    // the same shared-memory areas as 32-bit shared addresses, for the decoder warp (lcv_view_sa)
+    lcv_sa sa_bits, sa_rows, sa_ring_bar, sa_ring_key, sa_ring_pay, sa_ring_done, sa_tab, sa_abort;
 };
+__device__ __forceinline__ void lcv_view_sa(LcV2 &V)
+{
+    V.sa_bits = lcv_sa_of(V.sbits); V.sa_rows = lcv_sa_of(V.rows); V.sa_ring_bar = lcv_sa_of(V.ring_bar);
+    V.sa_ring_key = lcv_sa_of(V.ring_key); V.sa_ring_pay = lcv_sa_of(V.ring_pay);
+    V.sa_ring_done = lcv_sa_of(V.ring_done); V.sa_tab = lcv_sa_of(V.u1tab); V.sa_abort = lcv_sa_of(V.abort_code);
+}
 
 #define LCV_PAY(s, st, s1) ((uint32_t)(s) | ((uint32_t)(st) << 10) | ((uint32_t)(s1) << 12))
 #define LCV_PAY_S(w) ((int)((w) & 0x3FFu))
@@ -429,10 +497,10 @@ __device__ __forceinline__ void lcv_post(const LcV2 &V, LcvPost &P, int lane, ui
 {
     const uint32_t j = P.njobs, slot = j & (LCV_RING - 1);
     // the job that used this slot must be finished before the slot is reused (ring_done starts at slot-RING+1)
-    while (lcv_ld_acq(V.ring_done + slot) != j - LCV_RING + 1u) LCV_SPIN();
+    while (lcv_sa_ld32_acq(V.sa_ring_done + 4u * slot) != j - LCV_RING + 1u) LCV_SPIN();
     if (lane == 0) {
-        lcv_st_vol(V.ring_key + slot, key); lcv_st_vol(V.ring_pay + slot, pay);
-        lcv_bar_arrive(V.ring_bar + slot);
+        lcv_sa_st32(V.sa_ring_key + 4u * slot, key); lcv_sa_st32(V.sa_ring_pay + 4u * slot, pay);
+        lcv_sa_bar_arrive(V.sa_ring_bar + 8u * slot);
     }
     if ((uint32_t)lane == slot) { P.my_key = key; P.my_job = j; }
     P.njobs = j + 1u;
@@ -453,6 +521,21 @@ __device__ __forceinline__ bool lcv_gap_search(double u, double ru, double dv, d
     if (!(v - lo > dv) || !(hi - v >= dv)) return false;
     out.sym = gfirst + m; out.clo = lo; out.chi = hi; out.exact = 0;
     return true;
+}
+
+// lane-distributed register model (LcFast) from an inline record held in registers by every lane: only the exact
+// paths need it
+__device__ __forceinline__ void lcv_record_to_lanes(LcFast &F, const double2 &q0, const double2 &q1, const double2 &q2,
+                                                    const double2 &q3)
+{
+    const unsigned long long sb = (unsigned long long)__double_as_longlong(q3.y);
+    int k = (int)((sb >> 48) & 0xffu);
+    if (k > LCV_INLINE_K) k = LCV_INLINE_K;
+    const double val[LCV_INLINE_K] = {q0.y, q1.x, q1.y, q2.x, q2.y, q3.x};
+    F.k = k; F.u = q0.x; F.my_sym = 0x7fffffff; F.my_val = 0.0;
+#pragma unroll
+    for (int j = 0; j < LCV_INLINE_K; j++)
+        if (F.lane == j && j < k) { F.my_sym = (int)((sb >> (8 * j)) & 0xffu); F.my_val = val[j]; }
 }
 
 // decode_symbol (:272-292) for one symbol: the symbol, and low/high after the interval update (before
@@ -497,7 +580,7 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
         if (pre_ok) { // model after one update: exact np.cumsum values from the per-launch table
             const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
             const int t = lcf_tab_index(F, s1);
-            const double u = V.u1tab[t], ru = V.ru1tab[t];
+            const double u = lcv_sa_ldf64(V.sa_tab + 8u * (uint32_t)t), ru = lcv_sa_ldf64(V.sa_tab + 256u + 8u * (uint32_t)t);
             const double va = nd * lc_rcp_fast(rd) - cfix;
             const double A0 = (double)s1 * u, B0 = A0 + F.P1;
             int sc;
@@ -519,59 +602,59 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
     } else if (st == 2) {
         const double u = q0.x;
         const unsigned long long sb = (unsigned long long)__double_as_longlong(q3.y);
-        int k = (int)((sb >> 48) & 0xffu);
+        const uint32_t sb_lo = (uint32_t)sb, sb_hi = (uint32_t)(sb >> 32);
+        int k = (int)((sb_hi >> 16) & 0xffu);
         if (k > LCV_INLINE_K) k = LCV_INLINE_K;
-        double val[LCV_INLINE_K] = {q0.y, q1.x, q1.y, q2.x, q2.y, q3.x};
-        int sym[LCV_INLINE_K];
-#pragma unroll
-        for (int j = 0; j < LCV_INLINE_K; j++) sym[j] = (int)((sb >> (8 * j)) & 0xffu);
         bool decided = false;
         LcInterval iv; iv.sym = 0; iv.clo = 0.0; iv.chi = 0.0; iv.exact = 0;
         const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
         if (pre_ok) {
             const double ru = lc_rcp_fast(u);
             const double va = nd * lc_rcp_fast(rd) - cfix;
-            // approximate cum before (A) and after (Bv) every entry
-            double A[LCV_INLINE_K], Bv[LCV_INLINE_K];
-            double S = 0.0, Bk = 0.0; // Bk/g0: end of the last valid entry (start of the tail gap)
-            int g0 = 0;
-#pragma unroll
-            for (int j = 0; j < LCV_INLINE_K; j++) {
-                A[j] = (double)(sym[j] - j) * u + S;
-                S += val[j];
-                Bv[j] = A[j] + val[j];
-                if (j < k) { Bk = Bv[j]; g0 = sym[j] + 1; }
-            }
-            // first entry whose upper bound reaches v (descending scan: the last assignment wins)
-            int l = k;
-            double Al = 0.0, Bl = 0.0, Bp = 0.0;
+            // entries in ascending symbol order; approximate cum before (A) and after (B) each: stop at the first entry
+            // whose upper bound reaches v.  Sequential with early exit -- a record holds 2-3 entries on average, and
+            // the fully unrolled select form of this scan was a quarter of the warp's instructions on these symbols.
+            double S = 0.0, Al = 0.0, Bl = 0.0, Bp = 0.0; // Bp/gf: end of the previous entry = start of the gap before l
             int sl = 0, gf = 0;
-#pragma unroll
-            for (int j = LCV_INLINE_K - 1; j >= 0; j--) {
-                if (j < k && Bv[j] >= va) {
-                    l = j; Al = A[j]; Bl = Bv[j]; sl = sym[j];
-                    Bp = j > 0 ? Bv[j > 0 ? j - 1 : 0] : 0.0;
-                    gf = j > 0 ? sym[j > 0 ? j - 1 : 0] + 1 : 0;
-                }
+            bool found = false;
+#define LCV_SCAN_STEP(j_, sym_expr_, val_)                                              \
+            if (k <= (j_)) break;                                                        \
+            {                                                                            \
+                const int sy_ = (int)(sym_expr_);                                        \
+                const double A_ = (double)(sy_ - (j_)) * u + S;                          \
+                const double B_ = A_ + (val_);                                           \
+                if (B_ >= va) { found = true; Al = A_; Bl = B_; sl = sy_; break; }       \
+                Bp = B_; gf = sy_ + 1; S += (val_);                                      \
             }
-            if (l < k) {
+            do {
+                LCV_SCAN_STEP(0, sb_lo & 0xffu, q0.y)
+                LCV_SCAN_STEP(1, (sb_lo >> 8) & 0xffu, q1.x)
+                LCV_SCAN_STEP(2, (sb_lo >> 16) & 0xffu, q1.y)
+                LCV_SCAN_STEP(3, sb_lo >> 24, q2.x)
+                LCV_SCAN_STEP(4, sb_hi & 0xffu, q2.y)
+                LCV_SCAN_STEP(5, (sb_hi >> 8) & 0xffu, q3.x)
+            } while (0);
+#undef LCV_SCAN_STEP
+            if (found) {
                 if (va - Al > F.delta_v) {
                     if (Bl - va >= F.delta_v) { iv.sym = sl; iv.clo = Al; iv.chi = Bl; decided = true; }
                 } else if (Al - va >= F.delta_v) {
                     decided = lcv_gap_search(u, ru, F.delta_v, va, Bp, gf, sl - gf, iv);
                 }
             } else {
-                decided = lcv_gap_search(u, ru, F.delta_v, va, Bk, g0, n - g0, iv);
+                decided = lcv_gap_search(u, ru, F.delta_v, va, Bp, gf, n - gf, iv);
             }
         }
-        // lane-distributed copy of the record for the exact paths
-        F.k = k; F.u = u; F.my_sym = 0x7fffffff; F.my_val = 0.0;
-#pragma unroll
-        for (int j = 0; j < LCV_INLINE_K; j++) if (lane == j && j < k) { F.my_sym = sym[j]; F.my_val = val[j]; }
         if (decided) {
             on_candidate(iv.sym);
-            lcf_apply_symbol(F, iv, nd, rd, lo, hi);
-            nlo = lo; nhi = hi; s = iv.sym; done = true;
+            long long low64 = lo, high64 = hi;
+            if (!lc_interval_apply(iv, F.delta, low64, high64)) {
+                // the symbol itself was decided with margin; only the exact bounds are missing (lcf_apply_symbol)
+                lcv_record_to_lanes(F, q0, q1, q2, q3);
+                lcf_exact_at(F, iv.sym, iv);
+                lc_interval_apply(iv, F.delta, low64, high64);
+            }
+            nlo = (uint32_t)low64; nhi = (uint32_t)high64; s = iv.sym; done = true;
         }
     } else {
         lcv_load_pool(F, V, gw);
@@ -579,6 +662,7 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
     if (!done) { // exact evaluation shared with the other kernels
         fallback = 1;
         if (st == 1) lcf_state_first(F, s1);
+        if (st == 2) lcv_record_to_lanes(F, q0, q1, q2, q3);
         LcInterval iv;
         double num, rdv;
         const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
@@ -621,6 +705,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     uint32_t code = lcv_br_take(br, 32); // start_decoding (:247-258)
     int status = LC_OK;
     int pos = 0, r = 0, c = 0;
+    lcv_sa row_cur = V.sa_rows, row_prev = V.sa_rows + (uint32_t)C; // the row being decoded and the one above it
     uint32_t key = 0u; // (left=-1, up=-1)
     int st = 0;        // its state; the data the state needs is requested one symbol ahead:
     uint32_t gw = 0u;  //   states 1, 3: the context's 4-byte word
@@ -632,10 +717,12 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         LCP_START();
         LCP_ROW(st); LCP_COUNT(st, 0);
         const uint32_t shift = (key & 15u) * 2u;
-        // next position and the symbol above it (written at least C-1 >= 3 symbols ago): requested early
-        int c2 = c + 1, r2 = r;
-        if (c2 == C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
-        const int up2 = r2 > 0 ? (int)V.rows[((r2 - 1) & 1) * C + c2] : -1;
+        // next position and the symbol above it (written at least C-1 >= 3 symbols ago): requested early.  At the
+        // end of a row the next position is column 0 of the next row, under column 0 of this one.
+        const bool last = c + 1 == C;
+        const int r_next = r + 1 == F.R ? 0 : r + 1; // (the next image of the stream starts without a row above)
+        const bool has_up2 = last ? r_next > 0 : r > 0;
+        const int up2 = has_up2 ? lcv_sa_ld8(last ? row_cur : row_prev + (uint32_t)(c + 1)) : -1;
         // ---- decode_symbol (:272-292).  The next position's context key needs only the symbol: as soon as a path
         // has its candidate, the state word of that context is requested from shared memory, so the load overlaps
         // the bounds arithmetic.
@@ -644,8 +731,8 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         {
             const int fs = lcv_decode_symbol(F, V, st, gw, q0, q1, q2, q3, lo, hi, code, s, s1, nlo, nhi, fell_back,
                                              [&](int sym_) {
-                                                 key2 = (uint32_t)((c2 > 0 ? sym_ : -1) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);
-                                                 w2 = lcv_ld_vol(V.sbits + (key2 >> 4));
+                                                 key2 = (uint32_t)((last ? -1 : sym_) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);
+                                                 w2 = lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4));
                                              });
             if (fs != LC_OK) { status = fs; break; }
             if (fell_back) LCP_COUNT(4, st);
@@ -654,7 +741,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         LCP_MARK(1);
         // ---- next position's context (get_context :78-117): the data its state needs is requested now (loaded
         // straight into the registers the next iteration reads) and arrives during renormalisation and write-back
-        if (lane == 0) V.rows[(r & 1) * C + c] = (unsigned char)s;
+        if (lane == 0) lcv_sa_st8(row_cur + (uint32_t)c, s);
         const uint32_t shift2 = (key2 & 15u) * 2u;
         int st2 = (int)((w2 >> shift2) & 3u);
         bool pend2 = key2 == key; // this symbol's own update of the same context comes first
@@ -686,27 +773,29 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         LCP_MARK(2);
         // ---- this context's model moves on
         if (st == 0) {
-            if (lane == 0) { __stcg(V.gword + key, (uint32_t)s); atomicOr(V.sbits + (key >> 4), 1u << shift); }
+            if (lane == 0) { __stcg(V.gword + key, (uint32_t)s); lcv_sa_or32(V.sa_bits + 4u * (key >> 4), 1u << shift); }
         } else {
             lcv_post(V, P, lane, key, LCV_PAY(s, st, s1));
         }
         __syncwarp(); // lane 0's writes (row, word, state bits) are ordered before the other lanes' next reads
-        if (c2 == 0) { // a row is complete: write it out
-            lcv_flush_row(V.rows + (r & 1) * C, 0, C, out + (pos - (C - 1)), deq_table,
+        if (last) { // a row is complete: write it out
+            lcv_flush_row(V.rows + (row_cur - V.sa_rows), 0, C, out + (pos - (C - 1)), deq_table,
                           deq_out ? deq_out + (pos - (C - 1)) : (float *)0, lane);
-            const uint32_t ab = lcv_ld_vol(V.abort_code);
+            const uint32_t ab = lcv_sa_ld32(V.sa_abort);
             if (ab) { status = (int)ab; pos++; c = C; break; }
-        }
+            const lcv_sa t_ = row_cur; row_cur = row_prev; row_prev = t_;
+            c = 0; r = r_next;
+        } else c++;
         if (pend2) {
             LCP_COUNT(6, st2);
             const bool mine = P.my_key == key2;
-            if (mine) while (lcv_ld_vol(V.ring_done + lane) != P.my_job + 1u) LCV_SPIN();
+            if (mine) while (lcv_sa_ld32(V.sa_ring_done + 4u * (uint32_t)lane) != P.my_job + 1u) LCV_SPIN();
             __syncwarp();
             LCV_FENCE();
-            st2 = (int)((lcv_ld_vol(V.sbits + (key2 >> 4)) >> shift2) & 3u);
+            st2 = (int)((lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4)) >> shift2) & 3u);
             LCV_PREFETCH(st2, key2, gw, q0, q1, q2, q3);
         }
-        key = key2; c = c2; r = r2; st = st2;
+        key = key2; st = st2;
         LCP_MARK(3);
     }
     LCP_FLUSH();
@@ -719,7 +808,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         // symbols of the unfinished row (c of them; none when the stream ended on a row boundary), zeros after a fault
         const int done = pos;
         const int part = (c < C) ? c : 0;
-        if (part > 0) lcv_flush_row(V.rows + (r & 1) * C, 0, part, out + (done - part), deq_table,
+        if (part > 0) lcv_flush_row(V.rows + (row_cur - V.sa_rows), 0, part, out + (done - part), deq_table,
                                     deq_out ? deq_out + (done - part) : (float *)0, lane);
         for (int z = done + lane; z < F.total; z += 32) { out[z] = 0; if (deq_out) deq_out[z] = 0.0f; }
     }
@@ -747,6 +836,7 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
     V.cum1 = tables + 64;
     V.t2 = t2;
     V.pool_bytes = vc.pool_bytes; V.eps_k = vc.eps_k; V.lg_n = vc.lg_n;
+    lcv_view_sa(V);
     LcFast F;
     F.n = cfg.n; F.C = cfg.C; F.R = cfg.R; F.total = cfg.total; F.lane = (int)(threadIdx.x & 31);
     F.rate = cfg.rate; F.delta = cfg.delta; F.u0 = LC_DDIV(1.0, (double)cfg.n);

@@ -223,6 +223,7 @@ __device__ __forceinline__ void lc3_decode_block(const LcCoderCfg &cfg, const Lc
     V.cum1 = tables + 64;
     V.t2 = (const char *)0;
     V.pool_bytes = vc.pool_bytes; V.eps_k = vc.eps_k; V.lg_n = vc.lg_n;
+    lcv_view_sa(V);
     LcV3Mail M;
     M.sym = (uint32_t *)(smem + vc.sm_mail); M.hdr = (unsigned long long *)(M.sym + 2); M.data = M.sym + 4;
     LcFast F;
