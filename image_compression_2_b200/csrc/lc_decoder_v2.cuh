@@ -43,7 +43,7 @@ struct LcV2Cfg {
     uint32_t eps_k;       // floor(1e-10 * n * 2^40): the -1e-10 of decode_symbol in units of range/2^40
     uint32_t pool_bytes;  // overflow-record pool per block
     // shared memory carve-up
-    uint32_t sm_bits, sm_rows, sm_ring, sm_tab, sm_dense, sm_misc, sm_mail, sm_bytes;
+    uint32_t sm_bits, sm_rows, sm_ring, sm_tab, sm_dense, sm_misc, sm_mail, sm_stage, sm_bytes;
     // per-block global scratch carve-up
     uint64_t g_word, g_rec, g_pool, g_stride;
 };
@@ -68,6 +68,7 @@ static inline void lcv_cfg_make(const LcCoderCfg &c, LcV2Cfg *v)
     v->sm_dense = off; off += LCV_NU * (uint32_t)c.n * 8;
     v->sm_misc = off;  off += 16;                      // pool_top | abort
     v->sm_mail = off;  off += 96;                      // decoder v3: symbol word | packet header | pad | 64 B packet data
+    v->sm_stage = off; off += 128;                     // decoder v2: two 64-byte slots the next context's record is copied into
     v->sm_bytes = lc_round_up(off, 16);
     uint64_t g = 0;
     v->g_word = g; g += ((uint64_t)v->nkeys * 4 + 255) & ~(uint64_t)255;
@@ -196,6 +197,37 @@ static __device__ __forceinline__ void lcv_sa_bar_arrive(lcv_sa b) // release.ct
 }
 #endif
 
+// Asynchronous 64-byte copy global -> shared by lanes 0..3 (cp.async, L2 only), and its completion.  The decoder
+// warp requests the next context's record with it one symbol ahead.  A register prefetch (four 128-bit loads into
+// loop-carried registers) made the compiler copy the loaded registers right behind the loads, which stalled the
+// warp for the full L2/HBM latency on every such symbol (10 % of its time in the ncu stall samples).
+#ifdef LC_HOSTSIM
+static inline void lcv_stage_copy(lcv_sa dst, const char *src, int lane)
+{
+    if (lane < 4) memcpy((char *)dst + 16 * lane, src + 16 * lane, 16);
+}
+static inline void lcv_stage_wait() {}
+static inline double2 lcv_sa_ld128(lcv_sa a)
+{
+    double2 v;
+    v.x = ((const volatile double *)a)[0]; v.y = ((const volatile double *)a)[1];
+    return v;
+}
+#else
+static __device__ __forceinline__ void lcv_stage_copy(lcv_sa dst, const char *src, int lane)
+{
+    if (lane < 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)lane), "l"(src + 16 * lane) : "memory");
+}
+static __device__ __forceinline__ void lcv_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+static __device__ __forceinline__ double2 lcv_sa_ld128(lcv_sa a)
+{
+    double2 v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+#endif
+
 // ---- tables kernel body, one warp (block) per first symbol s1: u after the first update with s1 (its value
 // depends only on s1's accumulator-chain step; the block of the step's first symbol publishes it with its
 // reciprocal), and the exact np.cumsum (:346-347) of the model after that update.
@@ -299,13 +331,14 @@ struct LcV2 {
     const char *t2;           // per-launch records of the models after two visits (lcv_t2_block), or null
     uint32_t pool_bytes, eps_k, lg_n;
     // the same shared-memory areas as 32-bit shared addresses, for the decoder warp (lcv_view_sa)
-    lcv_sa sa_bits, sa_rows, sa_ring_bar, sa_ring_key, sa_ring_pay, sa_ring_done, sa_tab, sa_abort;
+    lcv_sa sa_bits, sa_rows, sa_ring_bar, sa_ring_key, sa_ring_pay, sa_ring_done, sa_tab, sa_abort, sa_stage;
 };
 __device__ __forceinline__ void lcv_view_sa(LcV2 &V)
 {
     V.sa_bits = lcv_sa_of(V.sbits); V.sa_rows = lcv_sa_of(V.rows); V.sa_ring_bar = lcv_sa_of(V.ring_bar);
     V.sa_ring_key = lcv_sa_of(V.ring_key); V.sa_ring_pay = lcv_sa_of(V.ring_pay);
     V.sa_ring_done = lcv_sa_of(V.ring_done); V.sa_tab = lcv_sa_of(V.u1tab); V.sa_abort = lcv_sa_of(V.abort_code);
+    V.sa_stage = 0;
 }
 
 #define LCV_PAY(s, st, s1) ((uint32_t)(s) | ((uint32_t)(st) << 10) | ((uint32_t)(s1) << 12))
@@ -684,6 +717,13 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
         } else if ((st_) != 0) gw_ = __ldcg(V.gword + (key_));                              \
     } while (0)
 
+// decoder v2: the same request, the inline record going to the staging slot in shared memory instead of registers
+__device__ __forceinline__ void lcv_prefetch_staged(const LcV2 &V, int lane, int st, uint32_t key, uint32_t &gw, lcv_sa slot)
+{
+    if (st == 2) lcv_stage_copy(slot, V.grec + (size_t)key * 64, lane);
+    else if (st != 0) gw = __ldcg(V.gword + key);
+}
+
 // write decoded symbols [first, first+count) of the row held in shared memory (and their dequantised values)
 __device__ __forceinline__ void lcv_flush_row(const unsigned char *row, int first_col, int count, int *out,
                                               const float *deq_table, float *deq_out, int lane)
@@ -709,7 +749,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     uint32_t key = 0u; // (left=-1, up=-1)
     int st = 0;        // its state; the data the state needs is requested one symbol ahead:
     uint32_t gw = 0u;  //   states 1, 3: the context's 4-byte word
-    double2 q0 = {0.0, 0.0}, q1 = q0, q2 = q0, q3 = q0; // state 2: the inline record  u | val[6] | sym[6] k
+    //   state 2: the inline record  u | val[6] | sym[6] k, copied to staging slot (pos & 1) in shared memory
     P.my_key = LCV_SENTINEL; // contexts of the previous stream are not this stream's
     LCP_DECL
     LCP_INIT();
@@ -728,6 +768,13 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         // the bounds arithmetic.
         int s = 0, s1 = 0, fell_back = 0;
         uint32_t nlo = 0u, nhi = 0u, key2 = 0u, w2 = 0u;
+        double2 q0 = {0.0, 0.0}, q1 = q0, q2 = q0, q3 = q0;
+        if (st == 2) { // the record requested during the previous symbol
+            const lcv_sa slot = V.sa_stage + 64u * (uint32_t)(pos & 1);
+            lcv_stage_wait();
+            __syncwarp();
+            q0 = lcv_sa_ld128(slot); q1 = lcv_sa_ld128(slot + 16u); q2 = lcv_sa_ld128(slot + 32u); q3 = lcv_sa_ld128(slot + 48u);
+        }
         {
             const int fs = lcv_decode_symbol(F, V, st, gw, q0, q1, q2, q3, lo, hi, code, s, s1, nlo, nhi, fell_back,
                                              [&](int sym_) {
@@ -748,7 +795,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         if (st2 != 0 && !pend2) {
             // a job on that context among the last LCV_RING posted ones may still be running
             pend2 = __ballot_sync(LC_FULL_MASK, P.my_key == key2) != 0u;
-            if (!pend2) LCV_PREFETCH(st2, key2, gw, q0, q1, q2, q3);
+            if (!pend2) lcv_prefetch_staged(V, lane, st2, key2, gw, V.sa_stage + 64u * (uint32_t)((pos + 1) & 1));
         }
         // ---- renormalise (:295-303) and underflow (:306-309): closed form, the d+e new bits come straight from
         // the top of the bit window
@@ -793,7 +840,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             __syncwarp();
             LCV_FENCE();
             st2 = (int)((lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4)) >> shift2) & 3u);
-            LCV_PREFETCH(st2, key2, gw, q0, q1, q2, q3);
+            lcv_prefetch_staged(V, lane, st2, key2, gw, V.sa_stage + 64u * (uint32_t)((pos + 1) & 1));
         }
         key = key2; st = st2;
         LCP_MARK(3);
@@ -837,6 +884,7 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
     V.t2 = t2;
     V.pool_bytes = vc.pool_bytes; V.eps_k = vc.eps_k; V.lg_n = vc.lg_n;
     lcv_view_sa(V);
+    V.sa_stage = lcv_sa_of(smem + vc.sm_stage);
     LcFast F;
     F.n = cfg.n; F.C = cfg.C; F.R = cfg.R; F.total = cfg.total; F.lane = (int)(threadIdx.x & 31);
     F.rate = cfg.rate; F.delta = cfg.delta; F.u0 = LC_DDIV(1.0, (double)cfg.n);
