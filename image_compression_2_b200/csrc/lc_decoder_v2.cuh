@@ -270,20 +270,25 @@ struct LcvBits {
     uint32_t widx;
     uint32_t nextw;
 };
-__device__ __forceinline__ uint32_t lcv_br_word(const LcvBits &b, uint32_t wi)
+// word wi of the stream as loaded (little-endian memory order, garbage past the end) ...
+__device__ __forceinline__ uint32_t lcv_br_load(const LcvBits &b, uint32_t wi)
 {
+    return wi * 4u < b.nbytes ? __ldg(b.w + wi) : 0u;
+}
+// ... and as the next 32 bits of the stream, MSB first, zeros past the end (the reference reads zeros there, :260-270).
+// Split so that nothing touches the loaded register until the word is consumed one refill later.
+__device__ __forceinline__ uint32_t lcv_br_fix(const LcvBits &b, uint32_t raw, uint32_t wi)
+{
+    uint32_t w = __byte_perm(raw, 0, 0x0123);
     const uint32_t byte0 = wi * 4u;
-    if (byte0 >= b.nbytes) return 0u; // the reference reads zeros past the end (:260-270)
-    uint32_t w = __byte_perm(__ldg(b.w + wi), 0, 0x0123);
-    const uint32_t rem = b.nbytes - byte0;
-    if (rem < 4u) w &= 0xffffffffu << (8u * (4u - rem));
+    if (byte0 + 4u > b.nbytes) w = byte0 >= b.nbytes ? 0u : (w & (0xffffffffu << (8u * (4u - (b.nbytes - byte0)))));
     return w;
 }
 __device__ __forceinline__ void lcv_br_init(LcvBits &b, const unsigned char *src, long long nbytes)
 {
     b.w = (const uint32_t *)src; b.nbytes = (uint32_t)(nbytes > 0x7fffffffll ? 0x7fffffffll : nbytes);
-    b.win = ((unsigned long long)lcv_br_word(b, 0) << 32) | lcv_br_word(b, 1);
-    b.nwin = 64; b.widx = 2; b.nextw = lcv_br_word(b, 2);
+    b.win = ((unsigned long long)lcv_br_fix(b, lcv_br_load(b, 0), 0) << 32) | lcv_br_fix(b, lcv_br_load(b, 1), 1);
+    b.nwin = 64; b.widx = 2; b.nextw = lcv_br_load(b, 2);
 }
 // drop nb bits (0..32); the window keeps more than 32 valid bits at its top
 __device__ __forceinline__ void lcv_br_skip(LcvBits &b, int nb)
@@ -291,10 +296,10 @@ __device__ __forceinline__ void lcv_br_skip(LcvBits &b, int nb)
     b.win <<= nb;
     b.nwin -= nb;
     if (b.nwin <= 32) {
-        b.win |= (unsigned long long)b.nextw << (32 - b.nwin);
+        b.win |= (unsigned long long)lcv_br_fix(b, b.nextw, b.widx) << (32 - b.nwin);
         b.nwin += 32;
         b.widx++;
-        b.nextw = lcv_br_word(b, b.widx);
+        b.nextw = lcv_br_load(b, b.widx);
     }
 }
 // next nb bits (1..32), MSB first
@@ -600,8 +605,11 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
             const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
             const unsigned long long above = below + rng1 + 1ull;
             const unsigned long long a = ((unsigned long long)off + 1ull) << V.lg_n;
-            const unsigned long long e_lo = (unsigned long long)(__umulhi(rng1, V.eps_k) >> 8); // <= E < e_lo + 3
-            if (below + e_lo + 4ull <= a && a + 1ull <= above + e_lo) {
+            const uint32_t e_lo = __umulhi(rng1, V.eps_k) >> 8; // <= E < e_lo + 3
+            // below + e_lo + 4 <= a  and  a + 1 <= above + e_lo, i.e. e_lo + 4 <= a - below <= range + e_lo - 1, in 32
+            // bits (a - below >= 2^32 would need the full 2^32 range and a top symbol: left to the exact path)
+            const unsigned long long dlt = a - below;
+            if ((uint32_t)(dlt >> 32) == 0u && (uint32_t)dlt >= e_lo + 4u && (uint32_t)dlt - (e_lo + 4u) <= rng1 - 4u) {
                 s = cand; done = true;
                 nlo = lo + (uint32_t)(below >> V.lg_n);
                 nhi = lo + (uint32_t)(above >> V.lg_n) - 1u;
@@ -746,6 +754,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     int status = LC_OK;
     int pos = 0, r = 0, c = 0;
     lcv_sa row_cur = V.sa_rows, row_prev = V.sa_rows + (uint32_t)C; // the row being decoded and the one above it
+    bool up_ok = false, next_ok = F.R > 1; // a row above this row / above the next row (same image)
     uint32_t key = 0u; // (left=-1, up=-1)
     int st = 0;        // its state; the data the state needs is requested one symbol ahead:
     uint32_t gw = 0u;  //   states 1, 3: the context's 4-byte word
@@ -760,8 +769,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         // next position and the symbol above it (written at least C-1 >= 3 symbols ago): requested early.  At the
         // end of a row the next position is column 0 of the next row, under column 0 of this one.
         const bool last = c + 1 == C;
-        const int r_next = r + 1 == F.R ? 0 : r + 1; // (the next image of the stream starts without a row above)
-        const bool has_up2 = last ? r_next > 0 : r > 0;
+        const bool has_up2 = last ? next_ok : up_ok;
         const int up2 = has_up2 ? lcv_sa_ld8(last ? row_cur : row_prev + (uint32_t)(c + 1)) : -1;
         // ---- decode_symbol (:272-292).  The next position's context key needs only the symbol: as soon as a path
         // has its candidate, the state word of that context is requested from shared memory, so the load overlaps
@@ -831,7 +839,8 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             const uint32_t ab = lcv_sa_ld32(V.sa_abort);
             if (ab) { status = (int)ab; pos++; c = C; break; }
             const lcv_sa t_ = row_cur; row_cur = row_prev; row_prev = t_;
-            c = 0; r = r_next;
+            c = 0; r = r + 1 == F.R ? 0 : r + 1; // (the next image of the stream starts without a row above)
+            up_ok = r > 0; next_ok = r + 1 != F.R;
         } else c++;
         if (pend2) {
             LCP_COUNT(6, st2);
