@@ -94,7 +94,7 @@ static inline uint32_t lcv_ld_acq(const uint32_t *p) { return *(const volatile u
 static inline void lcv_st_rel(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
 static inline void lcv_bar_init(unsigned long long *b) { *(volatile unsigned long long *)b = 0ull; } // completed phases
 static inline void lcv_bar_arrive(unsigned long long *b) { *(volatile unsigned long long *)b += 1ull; }
-static inline void lcv_bar_wait(unsigned long long *b, uint32_t parity)
+static inline void lcv_bar_wait(uintptr_t b, uint32_t parity)
 {
     while (((uint32_t)*(volatile unsigned long long *)b & 1u) == parity) emu::spin_yield();
 }
@@ -123,17 +123,20 @@ static __device__ __forceinline__ void lcv_bar_arrive(unsigned long long *b) // 
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
 }
-static __device__ __forceinline__ void lcv_bar_wait(unsigned long long *b, uint32_t parity) // acquire.cta
+// b: shared-window address.  The suspend-time hint lets the hardware keep the warp asleep until the phase completes
+// instead of returning every ~80 cycles (the retry loop was 17 instructions per symbol on the updater warp, competing
+// for issue slots with the decoder warps of the same sub-partition).
+static __device__ __forceinline__ void lcv_bar_wait(uint32_t b, uint32_t parity) // acquire.cta
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "LCV_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra LCV_DONE;\n"
         "bra LCV_WAIT;\n"
         "LCV_DONE:\n"
-        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+        "}\n" ::"r"(b), "r"(parity), "r"(0x989680u) : "memory");
 }
 #endif
 
@@ -444,20 +447,20 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
 #endif
     for (;; j += LCV_NU) {
         const uint32_t slot = j & (LCV_RING - 1);
-        lcv_bar_wait(V.ring_bar + slot, (j / LCV_RING) & 1u);
-        const uint32_t key = lcv_ld_vol(V.ring_key + slot);
-        const uint32_t pay = lcv_ld_vol(V.ring_pay + slot);
+        lcv_bar_wait(V.sa_ring_bar + 8u * slot, (j / LCV_RING) & 1u);
+        const uint32_t key = lcv_sa_ld32(V.sa_ring_key + 4u * slot);
+        const uint32_t pay = lcv_sa_ld32(V.sa_ring_pay + 4u * slot);
         LCU_BEGIN(LCV_PAY_ST(pay));
         if (key == LCV_SENTINEL) {
 #ifdef LC_DEC_PROFILE
             if (F.lane == 0) for (int i_ = 0; i_ < 4; i_++) { atomicAdd(&lc_prof_global[56 + i_], lcu_busy[i_]); atomicAdd(&lc_prof_global[60 + i_], lcu_jobs[i_]); }
 #endif
             __syncwarp();
-            if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+            if (F.lane == 0) lcv_sa_st32(V.sa_ring_done + 4u * slot, j + 1u);
             j += LCV_NU;
             break;
         }
-        if (lcv_ld_vol(V.abort_code) == 0u) {
+        if (lcv_sa_ld32(V.sa_abort) == 0u) {
             const int s = LCV_PAY_S(pay), st = LCV_PAY_ST(pay);
             const uint32_t shift = (key & 15u) * 2u;
             uint32_t word = 0u;
@@ -471,7 +474,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
                 if (F.lane == 0) atomicXor(V.sbits + (key >> 4), 3u << shift); // 01 -> 10
                 __syncwarp();
                 LCV_FENCE();
-                if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+                if (F.lane == 0) lcv_sa_st32(V.sa_ring_done + 4u * slot, j + 1u);
                 LCU_END();
                 continue;
             }
@@ -517,7 +520,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
         }
         __syncwarp();
         LCV_FENCE();
-        if (F.lane == 0) lcv_st_vol(V.ring_done + slot, j + 1u);
+        if (F.lane == 0) lcv_sa_st32(V.sa_ring_done + 4u * slot, j + 1u);
         LCU_END();
     }
 }
