@@ -54,6 +54,8 @@ v2 = open(os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v2.
 l0 = next(i for i, t in enumerate(v2) if "void lcv_decode_stream(" in t) + 1
 l1 = next(i for i, t in enumerate(v2) if "// Block entry:" in t) + 1
 addrs = [a for a, t, c in ins if c and c[0] == "lc_decoder_v2.cuh" and l0 <= c[1] < l1]
+if os.environ.get("DEC_RANGE") == "all" or not addrs:  # any other kernel: one range
+    addrs = [a for a, t, c in ins]
 lo, hi = min(addrs), max(addrs)
 tot_s = sum(float(r[si] or 0) for r in data)
 agg = {True: collections.defaultdict(lambda: [0.0, 0.0]), False: collections.defaultdict(lambda: [0.0, 0.0])}
