@@ -377,9 +377,30 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t2_total, op=dist.ReduceOp.MAX)
         v2 = world * B2 * SYMS * steps2 / (float(t2_total) * 1e-3)
+        # ... and end to end with host buffers (chunked over four streams, copies under the kernels)
+        lat2_host = lat2.cpu().pin_memory()
+        for _ in range(2):
+            pipe.roundtrip_host(lat2_host)
+        barrier()
+        te = []
+        for _ in range(steps2):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res2 = pipe.roundtrip_host(lat2_host)
+            te.append(time.perf_counter() - t0)
+        barrier()
+        assert not res2["enc_status"].numpy().any() and not res2["dec_status"].numpy().any()
+        te_total = torch.tensor([sum(te)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te_total, op=dist.ReduceOp.MAX)
+        v2e = world * B2 * SYMS * steps2 / float(te_total)
         large = {"workload": "cfg4 share: %d synthetic W+ latents per GPU (65,536 over 8 GPUs), 8-bit round trip" % B2,
                  "streams_per_gpu": B2, "value": v2, "unit": UNIT, "streams_per_s": v2 / SYMS, "steps": steps2,
-                 "ms_per_step": float(t2_total) / steps2, "parity": "round-trip identity on all streams"}
+                 "ms_per_step": float(t2_total) / steps2, "parity": "round-trip identity on all streams",
+                 "e2e": {"value": v2e, "unit": UNIT, "ms_per_step": 1e3 * float(te_total) / steps2,
+                         "h2d_bytes_per_step": int(res2["h2d_bytes"]), "d2h_bytes_per_step": int(res2["d2h_bytes"]),
+                         "host_chunks": int(res2["chunks"])}}
 
     if rank == 0:
         total_syms = world * B * SYMS

@@ -112,9 +112,10 @@ def test_pipeline_host_roundtrip():
     from tests.helpers import synth_latents
     B = 32
     lat = synth_latents("enc_like", B, 77).pin_memory()
-    for quantizer in ("codebook", "affine"):
+    for quantizer, chunks in (("codebook", None), ("affine", None), ("codebook", 3)):  # 3: uneven chunks on 3 streams
         pipe = LatentPipeline(n_symbols=256, quantizer=quantizer)
-        res = pipe.roundtrip_host(lat)
+        res = pipe.roundtrip_host(lat, chunks=chunks)
+        assert res["chunks"] == (chunks or 1)
         assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any()
         if quantizer == "codebook":
             cb = pipe.codebook.cpu().numpy()
