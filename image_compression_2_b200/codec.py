@@ -219,10 +219,13 @@ def encode_batch(idx, layout, n_symbols, mode="repaired", adaptation_rate=0.05, 
 
 
 def decode_batch(data, offsets, nbits, layout, n_symbols, mode="repaired", adaptation_rate=0.05, codebook=None,
-                 workspace=None):
+                 workspace=None, deq_out=None):
     """cabac_decode for layout.B independent streams (cabac_compression.py:363-406).
     data uint8 CUDA (stream b = ceil(nbits[b]/8) bytes at offsets[b], offsets multiples of 4, buffer padded to a
     multiple of 4); offsets int64 [>=B]; nbits int32 [B].
+    deq_out: optional destination of the dequantised values instead of a fresh CUDA tensor -- fp32, contiguous,
+    B*total elements, either on the device or in PINNED host memory (the kernel then writes the rows straight over
+    PCIe as it decodes them: no separate device-to-host copy afterwards).
     Returns (idx int32 [B,total], deq fp32 [B,total] | None, status int32 [B], fault_index int32 [B])."""
     lib = _native.load()
     data = _need_cuda(data, "data", torch.uint8)
@@ -240,7 +243,14 @@ def decode_batch(data, offsets, nbits, layout, n_symbols, mode="repaired", adapt
         cb = _need_cuda(codebook.to(dev), "codebook", torch.float32)
         if cb.numel() < n:
             raise ValueError("codebook has %d entries, need %d" % (cb.numel(), n))
-        deq = torch.empty((B, layout.total), dtype=torch.float32, device=dev)
+        if deq_out is not None:
+            if deq_out.dtype != torch.float32 or not deq_out.is_contiguous() or deq_out.numel() != B * layout.total:
+                raise ValueError("deq_out must be contiguous fp32 with %d elements" % (B * layout.total))
+            if not (deq_out.is_cuda or deq_out.is_pinned()):
+                raise RuntimeError("deq_out must be a CUDA tensor or pinned host memory")
+            deq = deq_out.view(B, layout.total)
+        else:
+            deq = torch.empty((B, layout.total), dtype=torch.float32, device=dev)
     if B == 0:
         return idx, deq, status, fault
     scratch_bytes = lib.lc_coder_scratch_bytes(B, layout.imgs, layout.R, layout.C, n, layout.has_ctx)

@@ -55,10 +55,10 @@ class LatentPipeline:
         return codec.encode_batch(idx.reshape(-1), layout, self.n, mode=self.mode, adaptation_rate=self.rate,
                                   workspace=ws or self.ws)
 
-    def decode(self, data, offsets, nbits, B, ws=None):
+    def decode(self, data, offsets, nbits, B, ws=None, deq_out=None):
         layout = codec.StreamLayout(B, 1, self.R, self.C, 1)
         return codec.decode_batch(data, offsets, nbits, layout, self.n, mode=self.mode, adaptation_rate=self.rate,
-                                  codebook=self.deq_table, workspace=ws or self.ws)
+                                  codebook=self.deq_table, workspace=ws or self.ws, deq_out=deq_out)
 
     # ---- whole path ---------------------------------------------------------------------------
     def roundtrip_device(self, latents):
@@ -130,8 +130,8 @@ class LatentPipeline:
                 data_dev = bytes_host[base:base + max(used, 16)].to(self.device, non_blocking=True)
                 offs_dev = meta_host[:Bc + 1].to(self.device, non_blocking=True)
                 nbits_dev = meta_host[Bc + 1:2 * Bc + 1].to(self.device, non_blocking=True).int()
-                dec_idx, deq, dstatus, dfault = self.decode(data_dev, offs_dev, nbits_dev, Bc, ws)
-                deq_host[c0:c1].copy_(deq.view((Bc,) + tuple(latents_host.shape[1:])), non_blocking=True)
+                # (the decoder writes the dequantised rows straight into the pinned host buffer as it goes)
+                dec_idx, deq, dstatus, dfault = self.decode(data_dev, offs_dev, nbits_dev, Bc, ws, deq_out=deq_host[c0:c1])
                 st_host[c0:c1].copy_(dstatus, non_blocking=True)
             base += (used + 15) // 16 * 16
             used_total += used
