@@ -287,7 +287,11 @@ __global__ void __launch_bounds__(32 * LC3_WARPS, 7) lc_decode_v3_kernel(LcCoder
 #ifndef LC_SORT_THREADS
 #define LC_SORT_THREADS 1024
 #endif
-typedef cub::BlockRadixSort<uint32_t, LC_SORT_THREADS, LC_PAR_MAX_SYMBOLS / LC_SORT_THREADS, unsigned short> LcBlockSort;
+#ifndef LC_SORT_RADIX_BITS
+#define LC_SORT_RADIX_BITS 4
+#endif
+typedef cub::BlockRadixSort<uint32_t, LC_SORT_THREADS, LC_PAR_MAX_SYMBOLS / LC_SORT_THREADS, unsigned short, LC_SORT_RADIX_BITS>
+    LcBlockSort;
 typedef cub::BlockScan<int, LC_SORT_THREADS> LcBlockScan;
 
 // Also emits what needs no model: the closed-form interval of every first visit (uniform model: cum[i] = i/n) and,
@@ -406,7 +410,10 @@ __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, con
 }
 
 #define LCS_BLOCK_WARPS 4
-__global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS) lc_enc_phase_a_sparse_kernel(
+#ifndef LCS_BLOCKS_PER_SM
+#define LCS_BLOCKS_PER_SM 12
+#endif
+__global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS, LCS_BLOCKS_PER_SM) lc_enc_phase_a_sparse_kernel(
     LcCoderCfg cfg, const int *__restrict__ codes, int B, const uint32_t *__restrict__ skeys,
     const unsigned short *__restrict__ spos, const int *__restrict__ first_bad, const unsigned short *__restrict__ glist,
     const int *__restrict__ ngroups, double *ivs, unsigned int *task_counter, const double *__restrict__ tables,
@@ -755,7 +762,7 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
             if (sparse_variant) {
                 const size_t sp_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;
                 int blocks_per_sm = (int)((200u * 1024u) / (sp_smem + 1024u));
-                if (blocks_per_sm > 32 / LCS_BLOCK_WARPS) blocks_per_sm = 32 / LCS_BLOCK_WARPS;
+                if (blocks_per_sm > LCS_BLOCKS_PER_SM) blocks_per_sm = LCS_BLOCKS_PER_SM;
                 cudaMemsetAsync(task_counter, 0, 4, st);
                 lc_enc_phase_a_sparse_kernel<<<lc_num_sms() * blocks_per_sm, 32 * LCS_BLOCK_WARPS, sp_smem, st>>>(
                     cfg, codes, nb, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables, t2);
