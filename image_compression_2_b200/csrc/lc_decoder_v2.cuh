@@ -28,7 +28,7 @@
 #pragma once
 #include "lc_decoder_fast.cuh"
 
-#define LCV_NU 1
+#define LCV_NU 1 // (the single completed-jobs counter of the ring assumes jobs finish in order: one updater warp)
 #define LCV_WARPS (1 + LCV_NU)
 #define LCV_RING 32
 #define LCV_INLINE_K 6
@@ -456,7 +456,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
             if (F.lane == 0) for (int i_ = 0; i_ < 4; i_++) { atomicAdd(&lc_prof_global[56 + i_], lcu_busy[i_]); atomicAdd(&lc_prof_global[60 + i_], lcu_jobs[i_]); }
 #endif
             __syncwarp();
-            if (F.lane == 0) lcv_sa_st32(V.sa_ring_done + 4u * slot, j + 1u);
+            if (F.lane == 0) lcv_sa_st32(V.sa_ring_done, j + 1u);
             j += LCV_NU;
             break;
         }
@@ -474,7 +474,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
                 if (F.lane == 0) atomicXor(V.sbits + (key >> 4), 3u << shift); // 01 -> 10
                 __syncwarp();
                 LCV_FENCE();
-                if (F.lane == 0) lcv_sa_st32(V.sa_ring_done + 4u * slot, j + 1u);
+                if (F.lane == 0) lcv_sa_st32(V.sa_ring_done, j + 1u);
                 LCU_END();
                 continue;
             }
@@ -520,7 +520,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
         }
         __syncwarp();
         LCV_FENCE();
-        if (F.lane == 0) lcv_sa_st32(V.sa_ring_done + 4u * slot, j + 1u);
+        if (F.lane == 0) lcv_sa_st32(V.sa_ring_done, j + 1u);
         LCU_END();
     }
 }
@@ -529,6 +529,7 @@ __device__ __forceinline__ void lcv_updater(LcFast &F, const LcV2 &V, uint32_t &
 // DECODER warp
 // =================================================================================================
 struct LcvPost {
+    uint32_t done_seen;  // a value of the updater's completed-jobs counter read earlier (it only grows)
     uint32_t njobs;      // jobs posted so far in this stream
     uint32_t my_key;     // lane l: key of the last job posted into ring slot l
     uint32_t my_job;     // ... and its index
@@ -537,8 +538,16 @@ struct LcvPost {
 __device__ __forceinline__ void lcv_post(const LcV2 &V, LcvPost &P, int lane, uint32_t key, uint32_t pay)
 {
     const uint32_t j = P.njobs, slot = j & (LCV_RING - 1);
-    // the job that used this slot must be finished before the slot is reused (ring_done starts at slot-RING+1)
-    while (lcv_sa_ld32_acq(V.sa_ring_done + 4u * slot) != j - LCV_RING + 1u) LCV_SPIN();
+    // the job that used this slot (j - RING) must be finished before the slot is reused.  The updater warp finishes
+    // jobs in order and publishes their count in one word (ring_done[0]); the decoder warp only re-reads it when the
+    // value it saw last no longer proves that -- the updater is ahead nearly always, so the common case is a compare.
+    if (j - P.done_seen >= (uint32_t)LCV_RING) {
+        for (;;) {
+            P.done_seen = lcv_sa_ld32_acq(V.sa_ring_done);
+            if (j - P.done_seen < (uint32_t)LCV_RING) break;
+            LCV_SPIN();
+        }
+    }
     if (lane == 0) {
         lcv_sa_st32(V.sa_ring_key + 4u * slot, key); lcv_sa_st32(V.sa_ring_pay + 4u * slot, pay);
         lcv_sa_bar_arrive(V.sa_ring_bar + 8u * slot);
@@ -848,7 +857,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         if (pend2) {
             LCP_COUNT(6, st2);
             const bool mine = P.my_key == key2;
-            if (mine) while (lcv_sa_ld32(V.sa_ring_done + 4u * (uint32_t)lane) != P.my_job + 1u) LCV_SPIN();
+            if (mine) while ((int)(lcv_sa_ld32(V.sa_ring_done) - (P.my_job + 1u)) < 0) LCV_SPIN();
             __syncwarp();
             LCV_FENCE();
             st2 = (int)((lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4)) >> shift2) & 3u);
@@ -916,8 +925,8 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
         V.eps_k = (uint32_t)(1e-10 * (double)FN * 1099511627776.0);
     }
     if (threadIdx.x < 64) V.u1tab[threadIdx.x] = tables[threadIdx.x];
-    if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = threadIdx.x - LCV_RING + 1u; }
-    LcvPost P; P.njobs = 0u; P.my_key = LCV_SENTINEL; P.my_job = 0u;
+    if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = 0u; }
+    LcvPost P; P.njobs = 0u; P.done_seen = 0u; P.my_key = LCV_SENTINEL; P.my_job = 0u;
     uint32_t ujob = (uint32_t)(warp > 0 ? warp - 1 : 0);
     const uint32_t nwords = (vc.nkeys + 15u) / 16u;
     for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {

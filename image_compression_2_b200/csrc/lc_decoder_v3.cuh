@@ -167,7 +167,7 @@ __device__ __forceinline__ void lc3_context(const LcFast &F, const LcV2 &V, cons
             if (st2 != 0) {
                 const bool mine = P.my_key == key2; // a job on it among the last LCV_RING posted ones may still be running
                 if (__ballot_sync(LC_FULL_MASK, mine)) {
-                    if (mine) while (lcv_ld_acq(V.ring_done + lane) != P.my_job + 1u) LCV_SPIN();
+                    if (mine) while ((int)(lcv_ld_acq(V.ring_done) - (P.my_job + 1u)) < 0) LCV_SPIN();
                     __syncwarp();
                     LCV_FENCE();
                     st2 = (int)((lcv_ld_vol(V.sbits + (key2 >> 4)) >> shift2) & 3u);
@@ -238,8 +238,8 @@ __device__ __forceinline__ void lc3_decode_block(const LcCoderCfg &cfg, const Lc
     F.u1tab = V.u1tab; F.rows = (unsigned short *)0;
     F.k = 0; F.u = F.u0; F.my_sym = 0x7fffffff; F.my_val = 0.0;
     if (threadIdx.x < 64) V.u1tab[threadIdx.x] = tables[threadIdx.x];
-    if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = threadIdx.x - LCV_RING + 1u; }
-    LcvPost P; P.njobs = 0u; P.my_key = LCV_SENTINEL; P.my_job = 0u;
+    if (threadIdx.x < LCV_RING) { lcv_bar_init(V.ring_bar + threadIdx.x); V.ring_done[threadIdx.x] = 0u; }
+    LcvPost P; P.njobs = 0u; P.done_seen = 0u; P.my_key = LCV_SENTINEL; P.my_job = 0u;
     uint32_t ujob = 0u;
     const uint32_t nwords = (vc.nkeys + 15u) / 16u;
     for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
