@@ -200,6 +200,14 @@ static __device__ __forceinline__ void lcv_sa_bar_arrive(lcv_sa b) // release.ct
 }
 #endif
 
+// Scheduling fence for one value: `v` cannot be touched before `after` exists.  ptxas otherwise places the first
+// consumer of an early shared-memory load right behind it, where the in-order warp waits out the load's latency.
+#ifdef LC_HOSTSIM
+#define LCV_USE_AFTER(v, after) ((void)0)
+#else
+#define LCV_USE_AFTER(v, after) asm volatile("" : "+r"(v) : "r"(after))
+#endif
+
 // Asynchronous 64-byte copy global -> shared by lanes 0..3 (cp.async, L2 only), and its completion.  The decoder
 // warp requests the next context's record with it one symbol ahead.  A register prefetch (four 128-bit loads into
 // loop-carried registers) made the compiler copy the loaded registers right behind the loads, which stalled the
@@ -798,7 +806,9 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         {
             const int fs = lcv_decode_symbol(F, V, st, gw, q0, q1, q2, q3, lo, hi, code, s, s1, nlo, nhi, fell_back,
                                              [&](int sym_) {
-                                                 key2 = (uint32_t)((last ? -1 : sym_) + 1) * (uint32_t)(n + 1) + (uint32_t)(up2 + 1);
+                                                 int up_ = up2;
+                                                 LCV_USE_AFTER(up_, sym_); // keeps the consumer of the early load here
+                                                 key2 = (uint32_t)((last ? -1 : sym_) + 1) * (uint32_t)(n + 1) + (uint32_t)(up_ + 1);
                                                  w2 = lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4));
                                              });
             if (fs != LC_OK) { status = fs; break; }
