@@ -236,34 +236,29 @@ __global__ void __launch_bounds__(32) lc_v2_tables_kernel(LcCoderCfg cfg, double
     lcv_tables_block(cfg, tables, lc_smem);
 }
 
-__global__ void __launch_bounds__(32 * LCV_WARPS, 8) lc_decode_v2_kernel(LcCoderCfg cfg, LcV2Cfg vc,
-                                                                          const unsigned char *__restrict__ bytes,
-                                                                          const long long *__restrict__ offsets,
-                                                                          const int *__restrict__ nbits, int B, int *out,
-                                                                          const float *__restrict__ deq_table,
-                                                                          float *deq_out, int *status, int *fault,
-                                                                          char *scratch, const double *tables,
-                                                                          const char *t2)
-{
-    extern __shared__ __align__(16) char lc_smem[];
-    lcv_decode_block<0, 0, 0>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables,
-                              t2, lc_smem);
-}
-
-// the W+ latent shape of the reference (8-bit codes of a [16,512] latent, one image per stream), fixed at compile time
-__global__ void __launch_bounds__(32 * LCV_WARPS, 8) lc_decode_v2_w8_kernel(LcCoderCfg cfg, LcV2Cfg vc,
-                                                                             const unsigned char *__restrict__ bytes,
-                                                                             const long long *__restrict__ offsets,
-                                                                             const int *__restrict__ nbits, int B, int *out,
-                                                                             const float *__restrict__ deq_table,
-                                                                             float *deq_out, int *status, int *fault,
-                                                                             char *scratch, const double *tables,
-                                                                             const char *t2)
-{
-    extern __shared__ __align__(16) char lc_smem[];
-    lcv_decode_block<256, 512, 16>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch,
-                                   tables, t2, lc_smem);
-}
+// The decoder kernels exist in two register budgets.  Registers are allocated per warp in units that make 97..128
+// registers per thread cost the same, so 8 blocks of 64 threads fill an SM's register file at <= 128 registers and 10
+// blocks need <= 96.  LATENCY build (8 resident streams per SM, 106 registers): the dependent chain per symbol is
+// shortest; used while every stream gets its own block in one wave (<= 8 x SMs streams: 6.1 ms for the benchmark).
+// THROUGHPUT build (10 per SM, 90 registers, no spills): the chain is ~7 % slower but 25 % more streams are resident;
+// used for larger batches (+3 % symbols/s at 8192 streams).  FN/FC/FR: generic shape, or the W+ latent shape of the
+// reference (8-bit codes of a [16,512] latent, one image per stream) fixed at compile time.
+#define LC_V2_LAT_PER_SM 8
+#define LC_V2_THR_PER_SM 10
+#define LC_V2_KERNEL(NAME, FN, FC, FR, PER_SM)                                                                         \
+    __global__ void __launch_bounds__(32 * LCV_WARPS, PER_SM)                                                          \
+        NAME(LcCoderCfg cfg, LcV2Cfg vc, const unsigned char *__restrict__ bytes, const long long *__restrict__ offsets, \
+             const int *__restrict__ nbits, int B, int *out, const float *__restrict__ deq_table, float *deq_out,      \
+             int *status, int *fault, char *scratch, const double *tables, const char *t2)                             \
+    {                                                                                                                  \
+        extern __shared__ __align__(16) char lc_smem[];                                                                \
+        lcv_decode_block<FN, FC, FR>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault,        \
+                                     scratch, tables, t2, lc_smem);                                                    \
+    }
+LC_V2_KERNEL(lc_decode_v2_kernel, 0, 0, 0, LC_V2_LAT_PER_SM)
+LC_V2_KERNEL(lc_decode_v2_w8_kernel, 256, 512, 16, LC_V2_LAT_PER_SM)
+LC_V2_KERNEL(lc_decode_v2_thr_kernel, 0, 0, 0, LC_V2_THR_PER_SM)
+LC_V2_KERNEL(lc_decode_v2_w8_thr_kernel, 256, 512, 16, LC_V2_THR_PER_SM)
 
 // Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream
 __global__ void __launch_bounds__(32 * LC3_WARPS, 7) lc_decode_v3_kernel(LcCoderCfg cfg, LcV2Cfg vc,
@@ -581,12 +576,21 @@ static int lc_decoder_choice()
     return choice;
 }
 static bool lc_use_decoder_v2(const LcCoderCfg &cfg) { return lc_decoder_choice() != 0 && lcv_eligible(cfg); }
+// resident streams per SM for a batch of B: the latency build while one wave of it holds the batch
+static int lc_v2_per_sm(const LcV2Cfg &vc, int B)
+{
+    int fit = (int)((227u * 1024u) / (vc.sm_bytes + 1024u));
+    if (fit < 1) fit = 1;
+    const int lat = fit < LC_V2_LAT_PER_SM ? fit : LC_V2_LAT_PER_SM;
+    const int thr = fit < LC_V2_THR_PER_SM ? fit : LC_V2_THR_PER_SM;
+    const char *e = getenv("LC_DECODER_BUILD"); // debug switch: "lat" / "thr"
+    if (e && e[0] == 'l') return lat;
+    if (e && e[0] == 't') return thr;
+    return (long long)B <= (long long)lc_num_sms() * lat ? lat : thr;
+}
 static int lc_v2_grid(const LcV2Cfg &vc, int B)
 {
-    int per_sm = (int)((227u * 1024u) / (vc.sm_bytes + 1024u));
-    if (per_sm > 8) per_sm = 8; // two warps of <= 128 registers per block
-    if (per_sm < 1) per_sm = 1;
-    long long g = (long long)lc_num_sms() * per_sm;
+    long long g = (long long)lc_num_sms() * lc_v2_per_sm(vc, B);
     if (g > B) g = B;
     return g < 1 ? 1 : (int)g;
 }
@@ -830,6 +834,8 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
             cudaFuncSetAttribute(lc_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             cudaFuncSetAttribute(lc_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             cudaFuncSetAttribute(lc_decode_v2_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(lc_decode_v2_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(lc_decode_v2_w8_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
             v2_attr = true;
         }
         if (vc.sm_bytes > 64 * 1024) return -22;
@@ -848,14 +854,15 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
             lc_decode_v3_kernel<<<g2, 32 * LC3_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
                                                                          B, idx_out, deq_table, deq_out, status,
                                                                          fault_index, (char *)scratch, tables);
-        else if (cfg.n == 256 && cfg.C == 512 && cfg.R == 16 && cfg.imgs == 1 && !getenv("LC_DECODER_GENERIC"))
-            lc_decode_v2_w8_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets,
-                                                                            nbits, B, idx_out, deq_table, deq_out, status,
-                                                                            fault_index, (char *)scratch, tables, t2);
-        else
-            lc_decode_v2_kernel<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
-                                                                         B, idx_out, deq_table, deq_out, status,
-                                                                         fault_index, (char *)scratch, tables, t2);
+        else {
+            const bool w8 = cfg.n == 256 && cfg.C == 512 && cfg.R == 16 && cfg.imgs == 1 && !getenv("LC_DECODER_GENERIC");
+            const bool thr = lc_v2_per_sm(vc, B) > LC_V2_LAT_PER_SM;
+            auto kern = thr ? (w8 ? lc_decode_v2_w8_thr_kernel : lc_decode_v2_thr_kernel)
+                            : (w8 ? lc_decode_v2_w8_kernel : lc_decode_v2_kernel);
+            kern<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits, B, idx_out,
+                                                          deq_table, deq_out, status, fault_index, (char *)scratch, tables,
+                                                          t2);
+        }
         LC_CUDA_RET();
         lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
                                                          deq_table, deq_out, status, fault_index, (char *)scratch,

@@ -281,11 +281,14 @@ def test_cfg4_large_batch_roundtrip():
     assert np.array_equal(out["deq"][:8].cpu().numpy().view(np.uint32), want.view(np.uint32))
 
 
-def test_decoder_v2_and_sparse_encoder_special_paths():
-    """The paths the synthetic latents rarely reach: contexts with 7..32 distinct symbols (pool records) and more
+@pytest.mark.parametrize("build", ["lat", "thr"])
+def test_decoder_v2_and_sparse_encoder_special_paths(build, monkeypatch):
+    """(build: the decoder kernel's two register budgets -- 8 or 10 resident streams per SM; the host picks by batch
+    size, LC_DECODER_BUILD forces one.)  The paths the synthetic latents rarely reach: contexts with 7..32 distinct symbols (pool records) and more
     than 32 (decoder: stream redone by the generic kernel; encoder phase A: dense continuation), small alphabets,
     short rows, several images sharing a model -- bitstreams and decoded symbols equal the oracle's."""
     from image_compression_2_b200 import coder
+    monkeypatch.setenv("LC_DECODER_BUILD", build)
     rng = np.random.default_rng(31)
     cases = []
     wide = np.zeros((3, 4, 400), np.int32)
@@ -320,3 +323,17 @@ def test_decoder_v2_and_sparse_encoder_special_paths():
     idx = torch.from_numpy(rng.integers(0, 256, (2, 4, 64)).astype(np.int32)).cuda()
     enc = codec.encode_batch(idx.reshape(-1), codec.layout_independent((2, 4, 64)), 256, slot_bytes=64)
     assert enc.status.cpu().tolist() == [5, 5]
+
+
+def test_decoder_throughput_build_more_streams_than_blocks():
+    """1480 + 7 streams of the W+ shape: the host picks the 10-streams-per-SM build and its blocks loop over streams;
+    same symbols as the encoder input, and as the 8-per-SM build."""
+    from image_compression_2_b200 import codec
+    B = 148 * 10 + 7
+    g = torch.Generator().manual_seed(5)
+    codes = torch.clamp(torch.round(torch.randn(B, 16, 512, generator=g) * 18 + 128), 0, 255).to(torch.int32).cuda()
+    layout = codec.layout_independent((B, 16, 512))
+    enc = codec.encode_batch(codes.reshape(-1), layout, 256)
+    assert not enc.status.any()
+    idx, _, status, fault = codec.decode_batch(enc.data, enc.offsets, enc.nbits, layout, 256)
+    assert not status.any() and torch.equal(idx.reshape(codes.shape), codes)
