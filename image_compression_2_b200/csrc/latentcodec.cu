@@ -439,7 +439,8 @@ __global__ void __launch_bounds__(32) lc_enc_phase_b_kernel(LcCoderCfg cfg, int 
 __global__ void __launch_bounds__(32) lc_enc_phase_b1_kernel(LcCoderCfg cfg, int B, const int *__restrict__ first_bad,
                                                              double *ivs, int *first_out)
 {
-    lc_enc_phase_b1_block(cfg, B, first_bad, ivs, first_out);
+    __shared__ __align__(16) char b1_ring[LC_B1_SMEM];
+    lc_enc_phase_b1_block(cfg, B, first_bad, ivs, first_out, b1_ring);
 }
 
 __global__ void __launch_bounds__(LC_B2_THREADS) lc_enc_phase_b2_kernel(LcCoderCfg cfg, int B,

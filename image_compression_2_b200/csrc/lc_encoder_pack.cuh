@@ -17,18 +17,43 @@
 // The bitstream is bit-identical to the serial writer's by construction (same bits, same order).
 #pragma once
 #include "lc_encoder_par.cuh"
+#include "lc_decoder_v2.cuh" // shared-window address helpers (lcv_sa_*)
 
 #define LC_B2_THREADS 256
 #define LC_B2_ITEMS (LC_PAR_MAX_SYMBOLS / LC_B2_THREADS)
 
 // ---- B1: the (low, high) recurrence.  `pairs`: in (cum[s], cum[s+1]) per position; out: record in the first 8 bytes.
 // Returns the first bit of finish_encoding (low's second-highest bit).
-__device__ __forceinline__ int lc_enc_b1_stream(int lane, double *pairs, int limit)
+//
+// The pairs are streamed through a shared-memory ring with cp.async: every lane copies one pair, so one instruction
+// moves 32 symbols (512 contiguous bytes), LC_B1_AHEAD chunks ahead of the chunk being coded.  The first version loaded
+// each symbol's pair into registers one group of four symbols ahead (every lane the same 16 bytes); the register
+// rotation at the end of a group then waited for loads that had had only ~0.5 us to arrive -- 18 % of the kernel's
+// stall samples were that one MOV (long scoreboard).
+#define LC_B1_CHUNK 32
+#define LC_B1_AHEAD 2
+#define LC_B1_SMEM ((LC_B1_AHEAD + 1) * LC_B1_CHUNK * 16)
+#ifdef LC_HOSTSIM
+static inline void lc_b1_async16(lcv_sa dst, const void *src) { memcpy((void *)dst, src, 16); }
+static inline void lc_b1_commit() {}
+static inline void lc_b1_wait_ahead() {}
+#else
+static __device__ __forceinline__ void lc_b1_async16(lcv_sa dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+static __device__ __forceinline__ void lc_b1_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+static __device__ __forceinline__ void lc_b1_wait_ahead() // all but the LC_B1_AHEAD most recent groups have landed
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(LC_B1_AHEAD) : "memory");
+}
+#endif
+__device__ __forceinline__ int lc_enc_b1_stream(int lane, double *pairs, int limit, char *smem)
 {
     uint32_t lo = 0u, hi = 0xffffffffu;
-    const double2 *iv2 = (const double2 *)pairs;
     unsigned long long *rec = (unsigned long long *)pairs;
-    const double2 zero2 = {0.0, 0.0};
+    const lcv_sa ring = lcv_sa_of(smem);
+    const int nchunks = (limit + LC_B1_CHUNK - 1) / LC_B1_CHUNK;
     // one symbol of the recurrence
 #define LC_B1_STEP(iv_, pos_)                                                                                       \
     do {                                                                                                            \
@@ -47,19 +72,31 @@ __device__ __forceinline__ int lc_enc_b1_stream(int lane, double *pairs, int lim
         lo = __funnelshift_lc(0u, lo_d_, e_) & ~em_;                                                                \
         hi = __funnelshift_lc(0xffffffffu, hi_d_, e_) | em_;                                                        \
     } while (0)
-    // groups of four symbols: the next group's intervals are requested before the current group is coded, so no
-    // instruction of the chain waits for a load
-    double2 c0 = limit > 0 ? iv2[0] : zero2, c1 = limit > 1 ? iv2[1] : zero2;
-    double2 c2 = limit > 2 ? iv2[2] : zero2, c3 = limit > 3 ? iv2[3] : zero2;
-    for (int g = 0; g < limit; g += 4) {
-        const double2 n0 = g + 4 < limit ? iv2[g + 4] : zero2, n1 = g + 5 < limit ? iv2[g + 5] : zero2;
-        const double2 n2 = g + 6 < limit ? iv2[g + 6] : zero2, n3 = g + 7 < limit ? iv2[g + 7] : zero2;
-        LC_B1_STEP(c0, g);
-        if (g + 1 < limit) LC_B1_STEP(c1, g + 1);
-        if (g + 2 < limit) LC_B1_STEP(c2, g + 2);
-        if (g + 3 < limit) LC_B1_STEP(c3, g + 3);
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+#define LC_B1_ISSUE(k_)                                                                                             \
+    do {                                                                                                            \
+        const int idx_ = (k_) * LC_B1_CHUNK + lane;                                                                 \
+        if ((k_) < nchunks && idx_ < limit)                                                                         \
+            lc_b1_async16(ring + (uint32_t)((((k_) % (LC_B1_AHEAD + 1)) * LC_B1_CHUNK + lane) * 16), pairs + 2 * (size_t)idx_); \
+        lc_b1_commit(); /* (an empty group when there is nothing left: the group count stays uniform) */           \
+    } while (0)
+    for (int k = 0; k < LC_B1_AHEAD; k++) LC_B1_ISSUE(k);
+    for (int k = 0; k < nchunks; k++) {
+        LC_B1_ISSUE(k + LC_B1_AHEAD);
+        lc_b1_wait_ahead();
+        __syncwarp(); // every lane's copy of chunk k is visible to the warp
+        const lcv_sa base = ring + (uint32_t)((k % (LC_B1_AHEAD + 1)) * LC_B1_CHUNK * 16);
+        const int p0 = k * LC_B1_CHUNK;
+        const int cnt = limit - p0 < LC_B1_CHUNK ? limit - p0 : LC_B1_CHUNK;
+        double2 cur = lcv_sa_ld128(base);
+        for (int i = 0; i < cnt; i++) {
+            // the next pair is requested before this one is coded (shared memory: ~30 cycles against ~230)
+            const double2 nxt = lcv_sa_ld128(base + (uint32_t)((i + 1 < cnt ? i + 1 : i) * 16));
+            LC_B1_STEP(cur, p0 + i);
+            cur = nxt;
+        }
+        __syncwarp(); // the slot is refilled LC_B1_AHEAD + 1 chunks later, after every lane has read it
     }
+#undef LC_B1_ISSUE
 #undef LC_B1_STEP
     return (lo & 0x40000000u) != 0u ? 1 : 0;
 }
@@ -195,13 +232,15 @@ __device__ __forceinline__ void lc_enc_b2_block(const double *pairs, int limit, 
 
 // ---- block entry points
 // B1: one warp per stream (blockDim.x = 32); first_out[b] = first bit of finish_encoding
+// smem: LC_B1_SMEM bytes, 16-byte aligned
 __device__ __forceinline__ void lc_enc_phase_b1_block(const LcCoderCfg &cfg, int B, const int *first_bad, double *ivs,
-                                                      int *first_out)
+                                                      int *first_out, char *smem)
 {
     const int lane = (int)(threadIdx.x & 31);
     for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
         const int fb = first_bad[sidx];
-        const int first = lc_enc_b1_stream(lane, ivs + 2 * (size_t)sidx * LC_PAR_MAX_SYMBOLS, fb < cfg.total ? fb : cfg.total);
+        const int first = lc_enc_b1_stream(lane, ivs + 2 * (size_t)sidx * LC_PAR_MAX_SYMBOLS, fb < cfg.total ? fb : cfg.total,
+                                           smem);
         if (lane == 0) first_out[sidx] = first;
         __syncwarp();
     }

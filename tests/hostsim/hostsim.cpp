@@ -347,7 +347,8 @@ struct ParB2Args { ParBArgs b; char *smem; };
 static void parb1_body(void *p)
 {
     ParB2Args *a = (ParB2Args *)p;
-    lc_enc_phase_b1_block(a->b.cfg, a->b.B, a->b.first_bad, const_cast<double *>(a->b.ivs), a->b.nbits);
+    alignas(16) static thread_local char ring[LC_B1_SMEM];
+    lc_enc_phase_b1_block(a->b.cfg, a->b.B, a->b.first_bad, const_cast<double *>(a->b.ivs), a->b.nbits, ring);
 }
 static void parb2_body(void *p)
 {
