@@ -450,7 +450,7 @@ def run_b200(args):
                          "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms_total / args.steps),
                          "warp_inst_per_symbol": facts.get("warp_inst_per_symbol") if same_cfg else None,
                          "issue_slot_utilisation": facts.get("issue_slot_utilisation") if same_cfg else None,
-                         "ncu": facts.get("_source", "profiles/r01_ncu_all_kernels_v10.md"),
+                         "ncu": facts.get("_source", "profiles/r01_ncu_all_kernels_v11.md"),
                          "note": "decode = dependent chain per stream: latency/issue-bound, not HBM-bound "
                                  "(DESIGN.md section 5); traffic above the algorithmic bytes is the per-stream "
                                  "context words + 64-byte records"},
