@@ -393,12 +393,50 @@ __device__ __forceinline__ void lcf_apply_symbol(const LcFast &F, LcInterval &iv
     lo = (uint32_t)low64; hi = (uint32_t)high64;
 }
 
+// decode_symbol (:272-292) in a context never seen before, in integer arithmetic (same derivation as decoder v2's
+// state-0 path): the uniform model's bounds i/n are exact for a power-of-two n, so with a = (code-low+1)*n and
+// E = 1e-10*n*range the symbol is the s with s*range < a - E <= (s+1)*range.  Candidate from a float quotient, decided
+// only with integer margins (the reference's float64 evaluation is within 1e-3 of these units); returns false when
+// they do not decide, and the caller takes the exact path.  lg_n = log2 n, eps_k = floor(1e-10 * n * 2^40).
+#ifdef LC_HOSTSIM
+static inline float lcf_rcp_f32(float x) { return 1.0f / x; }
+#else
+static __device__ __forceinline__ float lcf_rcp_f32(float x) // x >= 65535 here: no range handling needed
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#endif
+__device__ __forceinline__ bool lcf_uniform_symbol(int n, uint32_t lg_n, uint32_t eps_k, uint32_t lo, uint32_t hi,
+                                                   uint32_t code, int &s, uint32_t &nlo, uint32_t &nhi)
+{
+    const uint32_t rng1 = hi - lo, off = code - lo; // range-1, (code-low+1)-1
+    if (!(hi >= lo && off <= rng1 && rng1 >= 0xffffu)) return false;
+    int cand = (int)((float)off * lcf_rcp_f32((float)rng1) * (float)n);
+    cand = cand > n - 1 ? n - 1 : cand;
+    const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
+    const unsigned long long above = below + rng1 + 1ull;
+    const unsigned long long a = ((unsigned long long)off + 1ull) << lg_n;
+    const uint32_t e_lo = __umulhi(rng1, eps_k) >> 8; // <= E < e_lo + 3
+    const unsigned long long dlt = a - below;         // e_lo + 4 <= a - below <= range + e_lo - 1, in 32 bits
+    if (!((uint32_t)(dlt >> 32) == 0u && (uint32_t)dlt >= e_lo + 4u && (uint32_t)dlt - (e_lo + 4u) <= rng1 - 4u)) return false;
+    s = cand;
+    nlo = lo + (uint32_t)(below >> lg_n);
+    nhi = lo + (uint32_t)(above >> lg_n) - 1u;
+    return true;
+}
+
 // =================================================================================================
 __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned char *src, long long nbytes, int *out,
                                                       const float *deq_table, float *deq_out, int *status_out,
                                                       int *fault_index)
 {
     const uint32_t mask = F.slot_cap - 1;
+    uint32_t lg_n = 0u;
+    while ((1 << lg_n) < F.n) lg_n++;
+    const bool pow2 = (1 << lg_n) == F.n;
+    const uint32_t eps_k = (uint32_t)(1e-10 * (double)F.n * 1099511627776.0);
     LCP_DECL
     LCP_INIT();
     for (uint32_t i = F.lane; i < F.slot_cap; i += 32) __stcg(&F.slots[i], 0ull);
@@ -448,15 +486,19 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         LCP_MARK(2);
         // ---- decode_symbol (:272-292)
         LcInterval iv;
-        double num, rdv;
-        {
+        double num = 0.0, rdv = 0.0;
+        int s = 0;
+        uint32_t nlo = 0u, nhi = 0u;
+        // a context never seen before (91 % of the symbols at 10 bits): integer path first
+        const bool fresh = state == 0 && pow2 && lcf_uniform_symbol(F.n, lg_n, eps_k, lo, hi, code, s, nlo, nhi);
+        if (!fresh) {
             const int fs = lcf_find_symbol(F, state, LCF_S1(word), lo, hi, code, iv, num, rdv);
 #ifdef LC_DEC_PROFILE
             if (fs & 0x100) LCP_COUNT(4, state);
 #endif
             if ((fs & 0xff) != LC_OK) { status = fs & 0xff; break; }
+            s = iv.sym;
         }
-        const int s = iv.sym;
         LCP_MARK(3);
         // ---- the symbol is known: request the table window of the NEXT position's context now, so
         // its latency overlaps the interval update, renormalisation and write-back below
@@ -470,9 +512,10 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         unsigned long long w2 = __ldcg(&F.slots[(start2 + (uint32_t)F.lane) & mask]);
 
 #ifdef LC_DEC_PROFILE
-        { long long l_ = lo, h_ = hi; if (!lc_interval_apply(iv, F.delta, l_, h_)) LCP_COUNT(5, state); }
+        if (!fresh) { long long l_ = lo, h_ = hi; if (!lc_interval_apply(iv, F.delta, l_, h_)) LCP_COUNT(5, state); }
 #endif
-        lcf_apply_symbol(F, iv, num, rdv, lo, hi);
+        if (fresh) { lo = nlo; hi = nhi; }
+        else lcf_apply_symbol(F, iv, num, rdv, lo, hi);
         LCP_MARK(4);
         // ---- renormalise (:295-303) and underflow (:306-309), closed form
         {
