@@ -70,6 +70,78 @@ struct LcFast {
     double u, my_val;
 };
 
+// Shared-memory accesses of the decoder warp's hot loop go through 32-bit shared-window addresses held in
+// registers (inline PTX), not through generic pointers: on sm_100a every access through a generic pointer to
+// dynamic shared memory re-derives the window base (S2UR CgaCtaId / ULEA / LDCU, three to four instructions per
+// access, measured 15 % of the decoder warp's instructions) and each pointer costs two registers.
+#ifdef LC_HOSTSIM
+typedef uintptr_t lcv_sa; // on the emulator a "shared address" is the host pointer
+static inline lcv_sa lcv_sa_of(const void *p) { return (lcv_sa)p; }
+static inline uint32_t lcv_sa_ld32(lcv_sa a) { return *(const volatile uint32_t *)a; }
+static inline void lcv_sa_st32(lcv_sa a, uint32_t v) { *(volatile uint32_t *)a = v; }
+static inline uint32_t lcv_sa_ld32_acq(lcv_sa a) { return *(const volatile uint32_t *)a; }
+static inline int lcv_sa_ld8(lcv_sa a) { return (int)*(const volatile unsigned char *)a; }
+static inline void lcv_sa_st8(lcv_sa a, int v) { *(volatile unsigned char *)a = (unsigned char)v; }
+static inline int lcv_sa_ld16(lcv_sa a) { return (int)*(const volatile unsigned short *)a; }
+static inline void lcv_sa_st16(lcv_sa a, int v) { *(volatile unsigned short *)a = (unsigned short)v; }
+static inline double lcv_sa_ldf64(lcv_sa a) { return *(const volatile double *)a; }
+static inline void lcv_sa_or32(lcv_sa a, uint32_t v) { atomicOr((uint32_t *)a, v); }
+static inline void lcv_sa_bar_arrive(lcv_sa b) { *(volatile unsigned long long *)b += 1ull; }
+#else
+typedef uint32_t lcv_sa;
+static __device__ __forceinline__ lcv_sa lcv_sa_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ uint32_t lcv_sa_ld32(lcv_sa a)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ void lcv_sa_st32(lcv_sa a, uint32_t v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
+}
+static __device__ __forceinline__ uint32_t lcv_sa_ld32_acq(lcv_sa a)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+static __device__ __forceinline__ int lcv_sa_ld8(lcv_sa a)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return (int)v;
+}
+static __device__ __forceinline__ void lcv_sa_st8(lcv_sa a, int v)
+{
+    asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v));
+}
+static __device__ __forceinline__ int lcv_sa_ld16(lcv_sa a)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return (int)v;
+}
+static __device__ __forceinline__ void lcv_sa_st16(lcv_sa a, int v)
+{
+    asm volatile("st.volatile.shared.u16 [%0], %1;" ::"r"(a), "r"(v));
+}
+static __device__ __forceinline__ double lcv_sa_ldf64(lcv_sa a) // per-launch constants: plain load
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ void lcv_sa_or32(lcv_sa a, uint32_t v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+static __device__ __forceinline__ void lcv_sa_bar_arrive(lcv_sa b) // release.cta
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
+}
+#endif
+
 __device__ __forceinline__ int lcf_tab_index(const LcFast &F, int s)
 {
     return F.pw_chains == 0 ? s : ((s & (F.pw_len - 1)) >> 3);
@@ -448,6 +520,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
     int status = LC_OK;
     int left = -1, my_out = 0;
     int pos = 0, r = 0, c = 0;
+    lcv_sa row_cur = lcv_sa_of(F.rows), row_prev = row_cur + 2u * (uint32_t)F.C; // the row being decoded / the one above
     // software-pipelined probe: window of 32 slots for the context of position 0
     uint32_t key = 0u; // (left=-1, up=-1)
     uint32_t start = ((key * 2654435761u) >> F.slot_shift) & ~15u;
@@ -502,11 +575,13 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         LCP_MARK(3);
         // ---- the symbol is known: request the table window of the NEXT position's context now, so
         // its latency overlaps the interval update, renormalisation and write-back below
-        if (F.lane == 0) F.rows[(r & 1) * F.C + c] = (unsigned short)s;
-        int c2 = c + 1, r2 = r;
-        if (c2 == F.C) { c2 = 0; if (++r2 == F.R) r2 = 0; }
+        // (rows through shared-window addresses, base addresses swapped at row ends: see the note at lcv_sa_*)
+        if (F.lane == 0) lcv_sa_st16(row_cur + 2u * (uint32_t)c, s);
+        const bool last = c + 1 == F.C;
+        const int c2 = last ? 0 : c + 1;
+        const int r2 = last ? (r + 1 == F.R ? 0 : r + 1) : r;
         int up2 = -1;
-        if (r2 > 0) up2 = (F.C == 1) ? s : (int)F.rows[((r2 - 1) & 1) * F.C + c2]; // C==1: the element just written
+        if (r2 > 0) up2 = (F.C == 1) ? s : lcv_sa_ld16(last ? row_cur : row_prev + 2u * (uint32_t)c2); // C==1: the element just written
         const uint32_t key2 = (uint32_t)((c2 > 0 ? s : -1) + 1) * (uint32_t)(F.n + 1) + (uint32_t)(up2 + 1);
         const uint32_t start2 = ((key2 * 2654435761u) >> F.slot_shift) & ~15u;
         unsigned long long w2 = __ldcg(&F.slots[(start2 + (uint32_t)F.lane) & mask]);
@@ -570,6 +645,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         __syncwarp();
         key = key2; start = start2; w = w2;
         left = s; c = c2; r = r2;
+        if (last) { const lcv_sa t_ = row_cur; row_cur = row_prev; row_prev = t_; }
         LCP_MARK(6);
     }
     LCP_FLUSH();

@@ -140,66 +140,6 @@ static __device__ __forceinline__ void lcv_bar_wait(uint32_t b, uint32_t parity)
 }
 #endif
 
-// Shared-memory accesses of the decoder warp's hot loop go through 32-bit shared-window addresses held in
-// registers (inline PTX), not through generic pointers: on sm_100a every access through a generic pointer to
-// dynamic shared memory re-derives the window base (S2UR CgaCtaId / ULEA / LDCU, three to four instructions per
-// access, measured 15 % of the decoder warp's instructions) and each pointer costs two registers.
-#ifdef LC_HOSTSIM
-typedef uintptr_t lcv_sa; // on the emulator a "shared address" is the host pointer
-static inline lcv_sa lcv_sa_of(const void *p) { return (lcv_sa)p; }
-static inline uint32_t lcv_sa_ld32(lcv_sa a) { return *(const volatile uint32_t *)a; }
-static inline void lcv_sa_st32(lcv_sa a, uint32_t v) { *(volatile uint32_t *)a = v; }
-static inline uint32_t lcv_sa_ld32_acq(lcv_sa a) { return *(const volatile uint32_t *)a; }
-static inline int lcv_sa_ld8(lcv_sa a) { return (int)*(const volatile unsigned char *)a; }
-static inline void lcv_sa_st8(lcv_sa a, int v) { *(volatile unsigned char *)a = (unsigned char)v; }
-static inline double lcv_sa_ldf64(lcv_sa a) { return *(const volatile double *)a; }
-static inline void lcv_sa_or32(lcv_sa a, uint32_t v) { atomicOr((uint32_t *)a, v); }
-static inline void lcv_sa_bar_arrive(lcv_sa b) { *(volatile unsigned long long *)b += 1ull; }
-#else
-typedef uint32_t lcv_sa;
-static __device__ __forceinline__ lcv_sa lcv_sa_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-static __device__ __forceinline__ uint32_t lcv_sa_ld32(lcv_sa a)
-{
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-static __device__ __forceinline__ void lcv_sa_st32(lcv_sa a, uint32_t v)
-{
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
-}
-static __device__ __forceinline__ uint32_t lcv_sa_ld32_acq(lcv_sa a)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-static __device__ __forceinline__ int lcv_sa_ld8(lcv_sa a)
-{
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return (int)v;
-}
-static __device__ __forceinline__ void lcv_sa_st8(lcv_sa a, int v)
-{
-    asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v));
-}
-static __device__ __forceinline__ double lcv_sa_ldf64(lcv_sa a) // per-launch constants: plain load
-{
-    double v;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-static __device__ __forceinline__ void lcv_sa_or32(lcv_sa a, uint32_t v)
-{
-    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-static __device__ __forceinline__ void lcv_sa_bar_arrive(lcv_sa b) // release.cta
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
-}
-#endif
-
 // Scheduling fence for one value: `v` cannot be touched before `after` exists.  ptxas otherwise places the first
 // consumer of an early shared-memory load right behind it, where the in-order warp waits out the load's latency.
 #ifdef LC_HOSTSIM
