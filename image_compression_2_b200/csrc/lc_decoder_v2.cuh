@@ -22,7 +22,11 @@
 //    (the truncation guard of the previous version tripped on a third of these symbols).
 //  * Records of at most LCV_INLINE_K entries (94 % of the deeper visits) are searched as scalar code
 //    from registers; larger ones use the lane-parallel search of lc_decoder_fast.cuh.
-//  * The bit reader is warp-uniform (every lane loads the same word, one refill ahead).
+//  * The bit reader is warp-uniform (every lane loads the same word, one refill ahead, kept raw until consumed).
+//  * What the next symbol needs is requested one symbol ahead: the context's 4-byte word into a register, its
+//    64-byte inline record with cp.async into a shared-memory staging slot.  The hot loop addresses shared memory
+//    through 32-bit shared-window addresses (lcv_sa_*, lc_decoder_fast.cuh).  Both came out of the per-instruction
+//    profile of this loop (tools/dec_lines.py, tools/dec_stalls.py).
 // Whenever a fast path cannot decide with its margins it falls back to lcf_find_symbol /
 // lcf_apply_symbol, the same exact evaluation the other kernels use.
 #pragma once
