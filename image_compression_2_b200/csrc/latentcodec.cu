@@ -245,20 +245,20 @@ __global__ void __launch_bounds__(32) lc_v2_tables_kernel(LcCoderCfg cfg, double
 // reference (8-bit codes of a [16,512] latent, one image per stream) fixed at compile time.
 #define LC_V2_LAT_PER_SM 8
 #define LC_V2_THR_PER_SM 10
-#define LC_V2_KERNEL(NAME, FN, FC, FR, PER_SM)                                                                         \
+#define LC_V2_KERNEL(NAME, FN, FC, FR, PER_SM, OUTLINE)                                                                         \
     __global__ void __launch_bounds__(32 * LCV_WARPS, PER_SM)                                                          \
         NAME(LcCoderCfg cfg, LcV2Cfg vc, const unsigned char *__restrict__ bytes, const long long *__restrict__ offsets, \
              const int *__restrict__ nbits, int B, int *out, const float *__restrict__ deq_table, float *deq_out,      \
              int *status, int *fault, char *scratch, const double *tables, const char *t2)                             \
     {                                                                                                                  \
         extern __shared__ __align__(16) char lc_smem[];                                                                \
-        lcv_decode_block<FN, FC, FR>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault,        \
-                                     scratch, tables, t2, lc_smem);                                                    \
+        lcv_decode_block<FN, FC, FR, OUTLINE>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status,     \
+                                              fault, scratch, tables, t2, lc_smem);                                    \
     }
-LC_V2_KERNEL(lc_decode_v2_kernel, 0, 0, 0, LC_V2_LAT_PER_SM)
-LC_V2_KERNEL(lc_decode_v2_w8_kernel, 256, 512, 16, LC_V2_LAT_PER_SM)
-LC_V2_KERNEL(lc_decode_v2_thr_kernel, 0, 0, 0, LC_V2_THR_PER_SM)
-LC_V2_KERNEL(lc_decode_v2_w8_thr_kernel, 256, 512, 16, LC_V2_THR_PER_SM)
+LC_V2_KERNEL(lc_decode_v2_kernel, 0, 0, 0, LC_V2_LAT_PER_SM, false)
+LC_V2_KERNEL(lc_decode_v2_w8_kernel, 256, 512, 16, LC_V2_LAT_PER_SM, false)
+LC_V2_KERNEL(lc_decode_v2_thr_kernel, 0, 0, 0, LC_V2_THR_PER_SM, true)
+LC_V2_KERNEL(lc_decode_v2_w8_thr_kernel, 256, 512, 16, LC_V2_THR_PER_SM, true)
 
 // Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream
 __global__ void __launch_bounds__(32 * LC3_WARPS, 7) lc_decode_v3_kernel(LcCoderCfg cfg, LcV2Cfg vc,

@@ -540,11 +540,52 @@ __device__ __forceinline__ void lcv_record_to_lanes(LcFast &F, const double2 &q0
         if (F.lane == j && j < k) { F.my_sym = (int)((sb >> (8 * j)) & 0xffu); F.my_val = val[j]; }
 }
 
+// The exact evaluation of one symbol (lcf_find_symbol / lcf_apply_symbol on the lane-distributed model) for whatever
+// the fast paths could not decide, and for pool records (state 3).  About 3 % of the benchmark's symbols come here;
+// inlined, this code made the decoder warp's loop 28 KB long and 5 % of its stall samples were instruction fetches, so
+// it is a real function: the call costs ~100 cycles on those symbols only.
+// Measured: as a call it helps the 10-streams-per-SM build (twenty warps at different program counters per SM:
+// decode of 8192 streams 41.0 -> 40.3 ms) and costs the 8-per-SM build 2 % (the call and the copy of the model on 3 % of
+// the symbols), so only the throughput build calls it; the latency build inlines the same body.
+struct LcvCold { int status, s; uint32_t nlo, nhi; };
+__device__ __forceinline__ LcvCold lcv_exact_symbol(LcFast &F, const char *pool, int st, int s1, uint32_t gw, const double2 &q0,
+                                                    const double2 &q1, const double2 &q2, const double2 &q3, uint32_t lo,
+                                                    uint32_t hi, uint32_t code)
+{
+    LcvCold r; r.status = LC_OK; r.s = 0; r.nlo = 0u; r.nhi = 0u;
+    if (st == 1) lcf_state_first(F, s1);
+    else if (st == 2) lcv_record_to_lanes(F, q0, q1, q2, q3);
+    else if (st == 3) { // lane-distributed register model from the pool record (lcv_load_pool)
+        F.k = LCV_WORD_K(gw);
+        if (F.k > 32) F.k = 32; // only reachable on a stream already flagged for the generic kernel
+        const char *rec = pool + (size_t)LCV_WORD_OFF(gw) * 16;
+        int cl = 1; while ((1 << cl) < F.k) cl++;
+        F.u = __ldcg((const double *)rec);
+        const bool valid = F.lane < F.k;
+        F.my_val = valid ? __ldcg((const double *)(rec + 8) + F.lane) : 0.0;
+        F.my_sym = valid ? (int)__ldcg((const unsigned short *)(rec + 8 + (8 << cl)) + F.lane) : 0x7fffffff;
+    }
+    LcInterval iv;
+    double num, rdv;
+    const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
+    if (fs != LC_OK) { r.status = fs; return r; }
+    lcf_apply_symbol(F, iv, num, rdv, lo, hi);
+    r.s = iv.sym; r.nlo = lo; r.nhi = hi;
+    return r;
+}
+static __device__ __noinline__ LcvCold lcv_cold_symbol(LcFast *Fp, const char *pool, int st, int s1, uint32_t gw, double2 q0,
+                                                       double2 q1, double2 q2, double2 q3, uint32_t lo, uint32_t hi,
+                                                       uint32_t code)
+{
+    return lcv_exact_symbol(*Fp, pool, st, s1, gw, q0, q1, q2, q3, lo, hi, code);
+}
+
 // decode_symbol (:272-292) for one symbol: the symbol, and low/high after the interval update (before
 // renormalisation), from the context's state st and the data that state needs (gw: the context word for states 1
 // and 3; q0..q3: the inline record for state 2).  on_candidate(sym) is called as soon as a path has its candidate
 // symbol (again with the final symbol if the exact evaluation was needed).  Returns LC_OK or the fault status.
-template <class OnCandidate>
+// OUTLINE: the exact evaluation as a real function call (lcv_cold_symbol) instead of inlined code.
+template <bool OUTLINE, class OnCandidate>
 __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int st, uint32_t gw, const double2 &q0,
                                                  const double2 &q1, const double2 &q2, const double2 &q3, uint32_t lo,
                                                  uint32_t hi, uint32_t code, int &s, int &s1, uint32_t &nlo, uint32_t &nhi,
@@ -653,28 +694,44 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
         if (decided) {
             on_candidate(iv.sym);
             long long low64 = lo, high64 = hi;
-            if (!lc_interval_apply(iv, F.delta, low64, high64)) {
-                // the symbol itself was decided with margin; only the exact bounds are missing (lcf_apply_symbol)
-                lcv_record_to_lanes(F, q0, q1, q2, q3);
-                lcf_exact_at(F, iv.sym, iv);
-                lc_interval_apply(iv, F.delta, low64, high64);
+            if (OUTLINE) {
+                // when the truncations are not stable under the bounds' error (4 % of these symbols) the exact
+                // evaluation below redoes the symbol: same result, exact sums, no inlined copy of lcf_exact_at here
+                if (lc_interval_apply(iv, F.delta, low64, high64)) {
+                    nlo = (uint32_t)low64; nhi = (uint32_t)high64; s = iv.sym; done = true;
+                }
+            } else {
+                if (!lc_interval_apply(iv, F.delta, low64, high64)) {
+                    // the symbol itself was decided with margin; only the exact bounds are missing (lcf_apply_symbol)
+                    lcv_record_to_lanes(F, q0, q1, q2, q3);
+                    lcf_exact_at(F, iv.sym, iv);
+                    lc_interval_apply(iv, F.delta, low64, high64);
+                }
+                nlo = (uint32_t)low64; nhi = (uint32_t)high64; s = iv.sym; done = true;
             }
-            nlo = (uint32_t)low64; nhi = (uint32_t)high64; s = iv.sym; done = true;
         }
     } else {
-        lcv_load_pool(F, V, gw);
+        if (!OUTLINE) lcv_load_pool(F, V, gw);
     }
     if (!done) { // exact evaluation shared with the other kernels
         fallback = 1;
-        if (st == 1) lcf_state_first(F, s1);
-        if (st == 2) lcv_record_to_lanes(F, q0, q1, q2, q3);
-        LcInterval iv;
-        double num, rdv;
-        const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
-        if (fs != LC_OK) return fs;
-        on_candidate(iv.sym);
-        lcf_apply_symbol(F, iv, num, rdv, lo, hi);
-        nlo = lo; nhi = hi; s = iv.sym;
+        if (OUTLINE) {
+            LcFast Fc = F; // only the copy's address is taken: F itself stays in registers
+            const LcvCold r = lcv_cold_symbol(&Fc, V.pool, st, s1, gw, q0, q1, q2, q3, lo, hi, code);
+            if (r.status != LC_OK) return r.status;
+            on_candidate(r.s);
+            nlo = r.nlo; nhi = r.nhi; s = r.s;
+        } else {
+            if (st == 1) lcf_state_first(F, s1);
+            if (st == 2) lcv_record_to_lanes(F, q0, q1, q2, q3);
+            LcInterval iv;
+            double num, rdv;
+            const int fs = lcf_find_symbol(F, st == 3 ? 2 : st, s1, lo, hi, code, iv, num, rdv) & 0xff;
+            if (fs != LC_OK) return fs;
+            on_candidate(iv.sym);
+            lcf_apply_symbol(F, iv, num, rdv, lo, hi);
+            nlo = lo; nhi = hi; s = iv.sym;
+        }
     }
     return LC_OK;
 }
@@ -707,6 +764,7 @@ __device__ __forceinline__ void lcv_flush_row(const unsigned char *row, int firs
     }
 }
 
+template <bool OUTLINE>
 __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvPost &P, const unsigned char *src,
                                                   long long nbytes, int *out, const float *deq_table, float *deq_out,
                                                   int *status_out, int *fault_index)
@@ -748,7 +806,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             q0 = lcv_sa_ld128(slot); q1 = lcv_sa_ld128(slot + 16u); q2 = lcv_sa_ld128(slot + 32u); q3 = lcv_sa_ld128(slot + 48u);
         }
         {
-            const int fs = lcv_decode_symbol(F, V, st, gw, q0, q1, q2, q3, lo, hi, code, s, s1, nlo, nhi, fell_back,
+            const int fs = lcv_decode_symbol<OUTLINE>(F, V, st, gw, q0, q1, q2, q3, lo, hi, code, s, s1, nlo, nhi, fell_back,
                                              [&](int sym_) {
                                                  int up_ = up2;
                                                  LCV_USE_AFTER(up_, sym_); // keeps the consumer of the early load here
@@ -838,7 +896,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
 
 // Block entry: LCV_WARPS warps, persistent over streams.  FN/FC/FR > 0 fix the alphabet size and the image shape at
 // compile time (one image per stream): keys, shifts, margins and loop bounds become immediates on the serial chain.
-template <int FN, int FC, int FR>
+template <int FN, int FC, int FR, bool OUTLINE = false>
 __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const LcV2Cfg &vc, const unsigned char *bytes,
                                                  const long long *offsets, const int *nbits, int B, int *out,
                                                  const float *deq_table, float *deq_out, int *status, int *fault,
@@ -891,7 +949,7 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
         if (warp == 0) {
             int fi = 0, st = 0;
             const long long nby = ((long long)nbits[sidx] + 7) >> 3;
-            lcv_decode_stream(F, V, P, bytes + offsets[sidx], nby, out + (size_t)sidx * cfg.total, deq_table,
+            lcv_decode_stream<OUTLINE>(F, V, P, bytes + offsets[sidx], nby, out + (size_t)sidx * cfg.total, deq_table,
                               deq_out ? deq_out + (size_t)sidx * cfg.total : (float *)0, &st, &fi);
             if (F.lane == 0) { status[sidx] = st; fault[sidx] = fi; }
         } else {
