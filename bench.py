@@ -400,6 +400,7 @@ def run_b200(args):
                 res2 = pipe.roundtrip_host(lat2_host)
                 local[1] += time.perf_counter() - t0
             assert not res2["enc_status"].numpy().any() and not res2["dec_status"].numpy().any()
+            assert torch.equal(res2["deq"], pipe.codebook.cpu()[pipe.quantize(lat2).cpu().long()]), "e2e result differs"
             info = {"h2d_bytes_per_step": int(res2["h2d_bytes"]), "d2h_bytes_per_step": int(res2["d2h_bytes"]),
                     "host_chunks": int(res2["chunks"])}
         except Exception as e:  # noqa: BLE001 -- reported, never fatal
