@@ -81,15 +81,15 @@ class LatentPipeline:
         offsets, nbits, enc_status, deq = pinned fp32 [B,R,C], dec_status, h2d_bytes, d2h_bytes).  Synchronises at
         the end.
 
-        The batch is cut into `chunks` contiguous sub-batches (default 4 from 2048 streams up), each with its own CUDA
+        The batch is cut into `chunks` contiguous sub-batches (default: about 2048 streams each, from 1536 streams up), each with its own CUDA
         stream and workspace, so that the host<->device copies of one chunk run under the kernels of the others.
         Every chunk still makes the full trip: latents up, compressed bytes down to the host and up again, dequantised
         fp32 down.  Measured on a B200: 8192 streams 73.0 -> 63.5 ms; at 1024 streams (one latency-bound wave per
         kernel, encoder blocks of one chunk waiting for registers held by the decoder blocks of another) chunking
         gains nothing, so small batches stay in one piece."""
         B = latents_host.shape[0]
-        if chunks is None:
-            chunks = 4 if B >= 2048 else 1
+        if chunks is None:  # chunks of about 2048 streams, from 1536 streams up (measured: 1536 -6 %, 2048 -8 %, 4096 -6 %)
+            chunks = max(2, min(4, (B + 1024) // 2048)) if B >= 1536 else 1
         chunks = max(1, min(int(chunks), B))
         bounds = [(B * c) // chunks for c in range(chunks + 1)]
         main = torch.cuda.current_stream()
