@@ -2,11 +2,13 @@
 """bench.py -- latent symbols/s, encode + decode, bit-exact (BASELINE.json metric).
 
 A step = one pass of the whole hot path over one batch of synthetic W+ latents:
-  quantise (codebook argmin) -> encode -> compact -> decode (+ fused dequantise).
-Default workload = BASELINE.json configs[1]: 1024 latents of 16x512 at 8 bits per GPU
-("enc_like" synthetic latents).  With N GPUs every rank codes its own 1024
-streams (weak scaling, no collective on the hot path; the only NCCL traffic is the optional size
-gather after the timed region).
+  quantise -> encode -> compact -> decode (+ fused dequantise).
+Headline workload = BASELINE.json configs[1]: 1024 latents of 16x512 at 8 bits per GPU ("enc_like" synthetic
+latents).  With N GPUs every rank codes its own shard (no collective on the hot path; the
+only NCCL traffic is the optional size gather after the timed region).  The same run then measures the other
+BASELINE.json configs (`sweep`: cfg3 at 4/8/10 bits, cfg4 as stated = 65,536 latents over the N GPUs, cfg5 =
+hierarchical latents through quantiser B), each gated on bit-exact parity with the CPU oracle, and the HBM-bound
+quantiser kernels standalone at cfg4 size (`hbm_kernels`).
 
   python bench.py [--gpus N --steps K --warmup W]          this framework
   python bench.py --impl reference [...]                    the CPU coder on the host cores
@@ -14,6 +16,7 @@ gather after the timed region).
 One JSON line on stdout (rank 0).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,6 +32,7 @@ METRIC = "latent symbols/sec enc+dec (bit-exact)"
 UNIT = "symbols/s"
 R, C = 16, 512
 SYMS = R * C
+SM_CLOCK_HZ = 1.965e9  # clocks.max.sm of the B200 (profiling guide); the issue-slot peak is 148 SMs x 4 schedulers x this
 
 
 def parse():
@@ -37,15 +41,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="streams per GPU")
+    ap.add_argument("--batch", type=int, default=1024, help="streams per GPU of the headline workload")
     ap.add_argument("--bits", type=int, default=8)
     ap.add_argument("--kind", default="enc_like")
     ap.add_argument("--cpu-sample-streams", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--large-batch", type=int, default=8192,
-                    help="streams per GPU of the supplementary throughput measurement (0 = skip); 8192 is config 4's "
-                         "share per GPU (65,536 latents over 8 GPUs)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the cfg3/cfg4/cfg5 workloads and the HBM kernels")
+    ap.add_argument("--sweep-steps", type=int, default=10)
     return ap.parse_args()
+
+
+HIER_SIGMA = [0.115] * 5 + [0.158] * 7 + [0.131] * 4  # measured random-init per-level stds
 
 
 def synth(kind, B, seed):
@@ -57,6 +63,8 @@ def synth(kind, B, seed):
         return torch.randn(B, R, C, generator=g) * 0.4
     if kind == "uniform":
         return torch.rand(B, R, C, generator=g) * 2 - 1
+    if kind == "hier":
+        return torch.randn(B, R, C, generator=g) * torch.tensor(HIER_SIGMA).view(1, R, 1)
     raise ValueError(kind)
 
 
@@ -240,6 +248,177 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # this framework
 # ------------------------------------------------------------------------------------------------
+def kernel_source_hash():
+    """Identifies the kernel sources a set of ncu-derived facts belongs to (profiles/*_kernel_facts.json)."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "image_compression_2_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_kernel_facts():
+    """ncu-derived per-kernel facts (instructions per symbol, DRAM bytes): they cannot be measured outside a profiler,
+    so they come from the newest committed capture; `current` says whether that capture was taken from exactly the
+    kernel sources this run uses."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if f.endswith("_kernel_facts.json"):
+            best = os.path.join(pdir, f)
+    if best is None:
+        return {}, None
+    try:
+        return json.load(open(best)), os.path.relpath(best, ROOT)
+    except Exception:
+        return {}, None
+
+
+def oracle_parity(idx_host, streams, nbits_h, n, sample):
+    """Bit-for-bit comparison of `sample` bitstreams with the CPU oracle; returns (count, oracle bits/symbol)."""
+    from oracle import oracle as orc
+    B = idx_host.shape[0]
+    picks = sorted(set(int(round(i * (B - 1) / max(sample - 1, 1))) for i in range(min(sample, B))))
+    obits = 0
+    for b in picks:
+        ref = orc.encode_stream(idx_host[b:b + 1].astype("int32"), n, "repaired")
+        assert ref["status"] == 0, "oracle encoder fault on stream %d" % b
+        assert int(nbits_h[b]) == ref["nbits"], "stream %d: %d coded bits, oracle %d" % (b, int(nbits_h[b]), ref["nbits"])
+        assert streams[b] == ref["packed"], "stream %d: bitstream differs from the oracle" % b
+        obits += ref["nbits"]
+    return picks, obits / (len(picks) * idx_host.shape[1] * idx_host.shape[2])
+
+
+def run_workload(pipe, lat_host, dev, steps, warmup, flush, barrier, want_e2e, rank, tag):
+    """Parity gate + device-resident timing (+ optional end-to-end timing) of one workload on this rank.
+    Returns a dict of LOCAL numbers: ms_total, e2e_s, launches, coded_bits, parity strings."""
+    import torch
+    from image_compression_2_b200 import _native
+    lib = _native.load()
+    B = lat_host.shape[0]
+    n = pipe.n
+    lat = lat_host.to(dev)
+    stream = torch.cuda.current_stream()
+
+    def step(events=None):
+        idx = pipe.quantize(lat)
+        enc = pipe.encode(idx, reuse_output=True)
+        if events is not None:
+            events[0].record(stream)
+        dec_idx, deq, dstatus, _ = pipe.decode(enc.data, enc.offsets, enc.nbits, B, reuse_output=True)
+        if events is not None:
+            events[1].record(stream)
+        return idx, enc, dec_idx, deq, dstatus
+
+    # ---- parity gate on this rank's actual workload before any timing
+    idx, enc, dec_idx, deq, dstatus = step()
+    torch.cuda.synchronize()
+    assert int(enc.status.abs().sum()) == 0 and int(dstatus.abs().sum()) == 0, "%s: coder fault" % tag
+    assert torch.equal(dec_idx.view(B, R, C), idx), "%s: round trip is not the identity" % tag
+    assert torch.equal(deq.view(B, R, C), pipe.deq_table[idx.long()]), "%s: dequantised latents differ" % tag
+    coded_bits = float(enc.nbits.double().mean()) / SYMS
+    out = {"streams": B, "coded_bits_per_symbol": coded_bits, "parity": "round-trip identity on all %d streams" % B,
+           "enc_bytes": int(enc.offsets[-1])}
+    if rank == 0:
+        streams, nbits_h, _, _ = enc.to_host()
+        from oracle import oracle as orc
+        # the coder against the oracle on 8 sampled streams, the quantiser on the same streams' latents
+        picks, obits = oracle_parity(idx.cpu().numpy(), streams, nbits_h, n, 8)
+        sub = lat_host[picks].numpy()
+        want_idx = (orc.quantize_codebook(sub, pipe.codebook.cpu().numpy()) if pipe.quantizer == "codebook"
+                    else orc.quantize_affine(sub, pipe.bits)[0].clip(0, n - 1))
+        assert (idx[picks].cpu().numpy().astype("int64") == want_idx).all(), "%s: quantiser differs from the oracle" % tag
+        out["parity"] += "; quantised indices and bitstreams of %d sampled streams bit-identical to the CPU oracle" % len(picks)
+        out["oracle_coded_bits_per_symbol_sample"] = obits
+        out["coded_bits_per_symbol_sample"] = float(sum(int(nbits_h[b]) for b in picks)) / (len(picks) * SYMS)
+    del idx, enc, dec_idx, deq, dstatus
+
+    # ---- device-resident metric
+    for _ in range(max(warmup, 3)):
+        step()
+        flush.zero_()
+    barrier()
+    lib.lc_debug_launch_count(1)
+    t_steps, t_dec = [], []
+    for _ in range(steps):
+        flush.zero_()  # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step((d0, d1))
+        e1.record(stream)
+        e1.synchronize()
+        t_steps.append(e0.elapsed_time(e1))
+        t_dec.append(d0.elapsed_time(d1))
+    out["launches"] = int(lib.lc_debug_launch_count(1))
+    barrier()
+    out["ms_total"] = sum(t_steps)
+    out["dec_ms"] = sum(t_dec) / len(t_dec)
+    out["steps"] = steps
+
+    # ---- end-to-end metric: host buffers in, host buffers out, copies inside the timed region
+    if want_e2e:
+        for _ in range(2):
+            res = pipe.roundtrip_host(lat_host)
+        barrier()
+        e_times = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = pipe.roundtrip_host(lat_host)
+            e_times.append(time.perf_counter() - t0)
+        barrier()
+        assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any(), "%s: e2e coder fault" % tag
+        want = pipe.deq_table.cpu()[pipe.quantize(lat).cpu().long()]
+        assert torch.equal(res["deq"], want), "%s: e2e result differs" % tag
+        out["e2e_s"] = sum(e_times)
+        out["h2d"] = int(res["h2d_bytes"]); out["d2h"] = int(res["d2h_bytes"]); out["chunks"] = int(res["chunks"])
+    del lat
+    return out
+
+
+def hbm_kernels(dev, peak_gbs, flush):
+    """K1 / K2 / dequantisers standalone at cfg4 size (65,536 latents = 2 GiB of fp32 in): HBM-bound kernels against
+    the measured copy bandwidth.  Algorithmic bytes = fp32 read + index written (+ fp32 written)."""
+    import torch
+    from image_compression_2_b200 import codec
+    Bk = 65536
+    n_elem = Bk * SYMS
+    out = {}
+    lat = torch.empty(Bk, R, C, dtype=torch.float32, device=dev).uniform_(-0.5, 0.5)
+    cb = torch.linspace(-1, 1, 256).float().to(dev)
+    cases = [
+        ("lc_quant_codebook_kernel<u8> (K2, 8 bit)", lambda: codec.quantize_codebook(lat, cb, sorted_ascending=True, idx_dtype=torch.uint8), 5),
+        ("lc_quant_codebook_kernel<i32> (K2, reference's int32 indices)", lambda: codec.quantize_codebook(lat, cb, sorted_ascending=True), 8),
+        ("lc_quant_affine_kernel<u8> idx only (K1, 8 bit)", lambda: codec.quantize_affine(lat, 8, want_wq=False, idx_dtype=torch.uint8), 5),
+        ("lc_quant_affine_kernel fp32 dequantised only (K1, StyleGAN3Compressor.compress)", lambda: codec.quantize_affine(lat, 8, want_idx=False), 8),
+        ("lc_quant_affine_kernel<u8> idx + fp32 (K1)", lambda: codec.quantize_affine(lat, 8, idx_dtype=torch.uint8), 9),
+    ]
+    idx8 = codec.quantize_codebook(lat, cb, sorted_ascending=True, idx_dtype=torch.uint8)[0]
+    cases.append(("lc_dequant_codebook_kernel<u8> (dequantiser B)", lambda: codec.dequantize_codebook(idx8, cb), 5))
+    cases.append(("lc_dequant_affine_kernel<u8> (dequantiser A)", lambda: codec.dequantize_affine(idx8, 8), 5))
+    stream = torch.cuda.current_stream()
+    for name, fn, bytes_per_sym in cases:
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        gbs = n_elem * bytes_per_sym / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": n_elem * bytes_per_sym, "bytes_per_symbol": bytes_per_sym,
+                     "achieved_gbs": gbs, "frac_of_measured_hbm_peak": gbs / peak_gbs}
+    return {"size": "%d latents 16x512 (2 GiB fp32 in, cfg4)" % Bk, "peak_gbs": peak_gbs, "kernels": out}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -276,204 +455,159 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # every rank codes its own shard of the global batch (world*B streams), inputs generated on the
-    # CPU so the oracle and the kernels see the same bits
-    lo, hi = sharding.shard_range(world * B, rank, world)
-    lat_host = synth(args.kind, B, 1000 + 2 * 100000 + rank).pin_memory()
-    lat = lat_host.to(dev)
-    pipe = LatentPipeline(n_symbols=n, R=R, C=C, quantizer="codebook")
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
 
-    stream = torch.cuda.current_stream()
-
-    def step_device(events=None):
-        idx = pipe.quantize(lat)
-        enc = pipe.encode(idx)
-        if events is not None:
-            events[0].record(stream)
-        dec_idx, deq, dstatus, dfault = pipe.decode(enc.data, enc.offsets, enc.nbits, B)
-        if events is not None:
-            events[1].record(stream)
-        return idx, enc, dec_idx, deq, dstatus
-
-    # ---- parity gate on this rank's actual workload before any timing
-    idx, enc, dec_idx, deq, dstatus = step_device()
-    torch.cuda.synchronize()
-    assert int(enc.status.abs().sum()) == 0 and int(dstatus.abs().sum()) == 0, "coder fault in the bench workload"
-    assert torch.equal(dec_idx.view(B, R, C), idx), "round trip is not the identity"
-    assert torch.equal(deq.view(B, R, C), pipe.codebook[idx.long()]), "dequantised latents differ"
-    coded_bits = float(enc.nbits.double().mean())
-    parity_note = "round-trip identity on all streams"
-    if rank == 0:
-        from oracle import oracle as orc
-        streams, nbits_h, _, _ = enc.to_host()
-        idx_h = idx.cpu().numpy()
-        for b in range(0, B, max(1, B // 8)):
-            ref = orc.encode_stream(idx_h[b:b + 1], n, "repaired")
-            assert nbits_h[b] == ref["nbits"] and streams[b] == ref["packed"], "bitstream differs from the oracle"
-        parity_note += "; %d sampled bitstreams bit-identical to the CPU oracle" % len(range(0, B, max(1, B // 8)))
-
-    # ---- device-resident metric
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-        flush.zero_()
+    # ---- headline: every rank codes its shard [lo, hi) of the global batch of world*B streams; inputs are generated
+    # on the CPU (seeded by the shard's first stream) so the oracle and the kernels see the same bits
+    lo, hi = sharding.shard_range(world * B, rank, world)
+    lat_host = synth(args.kind, hi - lo, 1000 + 2 * 100000 + lo).pin_memory()
+    pipe = LatentPipeline(n_symbols=n, R=R, C=C, quantizer="codebook")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    t_steps, t_dec = [], []
-    for _ in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (untimed)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step_device((d0, d1))
-        e1.record(stream)
-        e1.synchronize()
-        t_steps.append(e0.elapsed_time(e1))
-        t_dec.append(d0.elapsed_time(d1))
-    barrier()
-    t_total = torch.tensor([sum(t_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
-    ms_total = float(t_total)
-
-    # ---- end-to-end metric: host buffers in, host buffers out, copies inside the timed region
-    for _ in range(2):
-        res = pipe.roundtrip_host(lat_host)
-    barrier()
-    e_times = []
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = pipe.roundtrip_host(lat_host)
-        e_times.append(time.perf_counter() - t0)
-    barrier()
-    assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any()
-    assert torch.equal(res["deq"], pipe.codebook.cpu()[idx.cpu().long()]), "e2e result differs"
-    e_total = torch.tensor([sum(e_times)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_total, op=dist.ReduceOp.MAX)
+    head = run_workload(pipe, lat_host, dev, args.steps, args.warmup, flush, barrier, True, rank, "cfg2")
     clocks = sampler.stop() if rank == 0 else None
-
+    ms_total, e_total = reduce_max([head["ms_total"], head["e2e_s"]])
     # optional size gather (not timed; the only collective this framework has)
-    sizes, _ = sharding.gather_shard_bytes(int(enc.offsets[-1]), device=dev)
+    sizes, _ = sharding.gather_shard_bytes(head["enc_bytes"], device=dev)
+    del lat_host
 
-    # ---- supplementary: the same round trip at config 4's per-GPU share (several waves of blocks per launch instead
-    # of one), device-resident like `value`; reported beside the headline, never instead of it
-    large = None
-    if args.large_batch > B and args.kind == "enc_like" and args.bits == 8:
-        B2, steps2 = args.large_batch, 3
-        # Each rank measures locally inside try/except and the ranks then meet in ONE all-reduce, so a failure here
-        # (e.g. memory on a shared box) cannot hang the job or cost the headline line above.
-        local = [0.0, 0.0, 0.0]  # device ms, e2e s, failed
-        info = {}
+    # ---- the other BASELINE.json configs, same gate, same timing rules
+    sweep = []
+    if not args.no_sweep:
+        cfg4_total, cfg5_total = 65536, 16384
+        c4 = sharding.shard_range(cfg4_total, rank, world) if world > 1 else (0, 8192)
+        c5 = sharding.shard_range(cfg5_total, rank, world)
+        specs = [
+            # (name, description, quantiser, bits, kind, [lo,hi) of this rank, seed base, global streams, e2e)
+            ("cfg3_4bit", "cfg3: 4096 latents per GPU, quantization_bits=4 (affine quantiser A), 'wide' latents", "affine", 4,
+             "wide", (rank * 4096, rank * 4096 + 4096), 3 * 100000 + 4000, world * 4096, False),
+            ("cfg3_8bit", "cfg3: 4096 latents per GPU, quantization_bits=8 (affine quantiser A), 'enc_like' latents", "affine", 8,
+             "enc_like", (rank * 4096, rank * 4096 + 4096), 3 * 100000 + 8000, world * 4096, False),
+            ("cfg3_10bit", "cfg3: 4096 latents per GPU, quantization_bits=10 (affine quantiser A), 'enc_like' latents", "affine", 10,
+             "enc_like", (rank * 4096, rank * 4096 + 4096), 3 * 100000 + 10000, world * 4096, False),
+            ("cfg4", ("cfg4 as stated: 65,536 latents batch-sharded over %d GPUs (%d per GPU), 8-bit" % (world, c4[1] - c4[0]))
+             if world > 1 else "cfg4 share of one of 8 GPUs: 8192 of the 65,536 latents, 8-bit (run with --gpus 2/4/8 for the config as stated)",
+             "codebook", 8, "enc_like", c4, 4 * 100000, cfg4_total if world > 1 else 8192, True),
+            ("cfg5", "cfg5: 16,384 hierarchical multi-scale latents (per-level sigma) over %d GPU(s), Gumbel-softmax codebook "
+             "quantiser B (argmin, n=256)" % world, "codebook", 8, "hier", c5, 5 * 100000, cfg5_total, False),
+        ]
+        for name, desc, quant, bits, kind, (s_lo, s_hi), seed, global_streams, want_e2e in specs:
+            local = [0.0, 0.0, 0.0, 0.0]  # device ms, e2e s, failed, launches
+            info = {}
+            # each rank measures locally inside try/except and the ranks then meet in ONE all-reduce, so a failure here
+            # (e.g. memory on a shared box) cannot hang the job or cost the headline line above
+            try:
+                p2 = LatentPipeline(n_symbols=1 << bits, R=R, C=C, quantizer=quant)
+                lat2 = synth(kind, s_hi - s_lo, 1000 + seed + s_lo)
+                if want_e2e:
+                    lat2 = lat2.pin_memory()
+                r = run_workload(p2, lat2, dev, args.sweep_steps, args.warmup, flush, barrier, want_e2e, rank, name)
+                local = [r["ms_total"], r.get("e2e_s", 0.0), 0.0, float(r["launches"])]
+                info = r
+                del lat2, p2
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001 -- reported, never fatal
+                local[2] = 1.0
+                info = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            t_ms, te_s, failed, launches = reduce_max(local)
+            entry = {"name": name, "workload": desc, "streams_total": global_streams, "streams_per_gpu": s_hi - s_lo,
+                     "n_symbols": 1 << bits, "quantizer": quant, "latents": kind}
+            if failed:
+                entry["failed"] = info.get("error", "on another rank")
+            else:
+                steps2 = args.sweep_steps
+                v = global_streams * SYMS * steps2 / (t_ms * 1e-3)
+                entry.update({"value": v, "unit": UNIT, "streams_per_s": v / SYMS, "steps": steps2,
+                              "ms_per_step": t_ms / steps2, "decode_ms": info.get("dec_ms"),
+                              "coded_bits_per_symbol": info.get("coded_bits_per_symbol"),
+                              "coded_bits_per_symbol_sample": info.get("coded_bits_per_symbol_sample"),
+                              "oracle_coded_bits_per_symbol_sample": info.get("oracle_coded_bits_per_symbol_sample"),
+                              "parity": info.get("parity"), "gpu_launches": int(launches)})
+                if want_e2e:
+                    ve = global_streams * SYMS * steps2 / te_s
+                    entry["e2e"] = {"value": ve, "unit": UNIT, "streams_per_s": ve / SYMS, "ms_per_step": 1e3 * te_s / steps2,
+                                    "h2d_bytes_per_step": info.get("h2d"), "d2h_bytes_per_step": info.get("d2h"),
+                                    "host_chunks": info.get("chunks")}
+            sweep.append(entry)
+
+    hbm = None
+    if not args.no_sweep and rank == 0 and world == 1:
         try:
-            lat2 = synth(args.kind, B2, 1000 + 4 * 100000 + rank).to(dev)
-
-            def step_large():
-                idx2 = pipe.quantize(lat2)
-                enc2 = pipe.encode(idx2)
-                return idx2, enc2, pipe.decode(enc2.data, enc2.offsets, enc2.nbits, B2)
-
-            idx2, enc2, (dec2, _, dst2, _) = step_large()
-            torch.cuda.synchronize()
-            assert int(enc2.status.abs().sum()) == 0 and int(dst2.abs().sum()) == 0 and torch.equal(dec2.view(B2, R, C), idx2)
-            del idx2, enc2, dec2, dst2
-            for _ in range(steps2):
-                flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                step_large()
-                e1.record(stream)
-                e1.synchronize()
-                local[0] += e0.elapsed_time(e1)
-            # ... and end to end with host buffers (chunked over four streams, copies under the kernels)
-            lat2_host = lat2.cpu().pin_memory()
-            for _ in range(2):
-                pipe.roundtrip_host(lat2_host)
-            for _ in range(steps2):
-                flush.zero_()
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                res2 = pipe.roundtrip_host(lat2_host)
-                local[1] += time.perf_counter() - t0
-            assert not res2["enc_status"].numpy().any() and not res2["dec_status"].numpy().any()
-            assert torch.equal(res2["deq"], pipe.codebook.cpu()[pipe.quantize(lat2).cpu().long()]), "e2e result differs"
-            info = {"h2d_bytes_per_step": int(res2["h2d_bytes"]), "d2h_bytes_per_step": int(res2["d2h_bytes"]),
-                    "host_chunks": int(res2["chunks"])}
-        except Exception as e:  # noqa: BLE001 -- reported, never fatal
-            local[2] = 1.0
-            info = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
-        agg = torch.tensor(local, dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(agg, op=dist.ReduceOp.MAX)
-        t2_ms, te_s, failed = (float(x) for x in agg)
-        if failed:
-            large = {"streams_per_gpu": B2, "failed": info.get("error", "on another rank")}
-        else:
-            v2 = world * B2 * SYMS * steps2 / (t2_ms * 1e-3)
-            v2e = world * B2 * SYMS * steps2 / te_s
-            large = {"workload": "cfg4 share: %d synthetic W+ latents per GPU (65,536 over 8 GPUs), 8-bit round trip" % B2,
-                     "streams_per_gpu": B2, "value": v2, "unit": UNIT, "streams_per_s": v2 / SYMS, "steps": steps2,
-                     "ms_per_step": t2_ms / steps2, "parity": "round-trip identity on all streams",
-                     "e2e": dict({"value": v2e, "unit": UNIT, "ms_per_step": 1e3 * te_s / steps2}, **info)}
+            hbm = hbm_kernels(dev, peak, flush)
+        except Exception as e:  # noqa: BLE001
+            hbm = {"failed": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank == 0:
         total_syms = world * B * SYMS
         value = total_syms * args.steps / (ms_total * 1e-3)
-        e2e_value = total_syms * args.steps / float(e_total)
-        # roofline of the dominant kernel (the decoder).  Algorithmic bytes per symbol of that
-        # launch: coded bits/8 read + 4 B int32 index + 4 B fp32 dequantised value written
-        # (DESIGN.md section 5).  It is NOT an HBM-bound kernel; the fraction is reported as is.
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        dec_ms = sum(t_dec) / len(t_dec)
-        facts = {}
-        try:
-            facts = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_facts.json"))).get("lc_decode_v2_w8_kernel" if (n == 256 and R == 16 and C == 512) else "lc_decode_v2_kernel", {})
-        except Exception:
-            pass
-        if B > 8 * 148 and n == 256 and R == 16 and C == 512:  # the host picks the throughput build there
-            facts = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_facts.json"))).get("lc_decode_v2_w8_thr_kernel", {})
+        e2e_value = total_syms * args.steps / e_total
+        w8 = n == 256 and R == 16 and C == 512
+        kname = ("lc_decode_v2_w8_thr_kernel" if B > 8 * 148 else "lc_decode_v2_w8_kernel") if w8 else "lc_decode_v2_kernel"
+        facts_all, facts_file = load_kernel_facts()
+        facts = facts_all.get(kname, {})
         same_cfg = facts.get("streams") == B and facts.get("n_symbols") == n
-        bytes_per_launch = B * SYMS * (coded_bits / SYMS / 8.0 + 8.0)
-        achieved = bytes_per_launch / (dec_ms * 1e-3) / 1e9
+        facts_current = facts_all.get("_kernel_source_sha16") == kernel_source_hash()
+        dec_ms = head["dec_ms"]
+        coded_bits = head["coded_bits_per_symbol"]
+        # Algorithmic HBM bytes of the decode launch per symbol: coded bits/8 read + index written + 4 B fp32 written
+        idx_bytes = 1 if n <= 256 else 2
+        bytes_per_launch = B * SYMS * (coded_bits / 8.0 + idx_bytes + 4.0)
+        hbm_achieved = bytes_per_launch / (dec_ms * 1e-3) / 1e9
+        # ... but the decoder is a dependent chain per stream: its roofline is the SM issue rate
+        slots_peak = 148 * 4 * SM_CLOCK_HZ
+        ips = facts.get("warp_inst_per_symbol") if same_cfg else None
+        inst_rate = (ips * B * SYMS / (dec_ms * 1e-3)) if ips else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "streams_per_gpu": B, "symbols_per_stream": SYMS,
-                       "n_symbols": n, "coder_mode": "repaired", "coded_bits_per_symbol": coded_bits / SYMS,
+                       "n_symbols": n, "coder_mode": "repaired", "coded_bits_per_symbol": coded_bits,
+                       "oracle_coded_bits_per_symbol_sample": head.get("oracle_coded_bits_per_symbol_sample"),
+                       "coded_bits_per_symbol_sample": head.get("coded_bits_per_symbol_sample"),
+                       "index_dtype": "uint8" if n <= 256 else "uint16",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)", "parallelism": "streams sharded by image, no collective",
-                       "parity": parity_note, "streams_per_s": value / SYMS},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(res["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(res["d2h_bytes"]), "ms_per_step": 1e3 * float(e_total) / args.steps},
-            # per step: quantise, tables, two-visit table, sort, phase A, phase B1, B2, size scan, compaction,
-            # tables, decode, redo pass
-            "gpu_launches": 12 * args.steps,
-            "roofline": {"kernel": ("lc_decode_v2_w8_thr_kernel" if B > 8 * 148 else "lc_decode_v2_w8_kernel") if (n == 256 and R == 16 and C == 512) else "lc_decode_v2_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak,
+                       "parity": head["parity"], "streams_per_s": value / SYMS},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": head["h2d"],
+                    "d2h_bytes_per_step": head["d2h"], "ms_per_step": 1e3 * e_total / args.steps,
+                    "frac_of_device_value": e2e_value / value},
+            # counted by the library (lc_debug_launch_count) over the timed steps of the headline workload
+            "gpu_launches": head["launches"],
+            "roofline": {"kernel": kname, "bound": "issue_slots",
+                         "achieved": inst_rate / 1e9 if inst_rate else None, "peak": slots_peak / 1e9,
+                         "unit": "G warp-instructions/s", "frac": inst_rate / slots_peak if inst_rate else None,
+                         "peak_source": "148 SMs x 4 schedulers x %.3f GHz (clocks.max.sm)" % (SM_CLOCK_HZ / 1e9),
+                         "warp_inst_per_symbol": ips, "kernel_ms": dec_ms,
+                         "kernel_share_of_step": dec_ms / (ms_total / args.steps),
+                         "cycles_per_symbol_per_stream": dec_ms * 1e-3 * SM_CLOCK_HZ / SYMS if B <= 8 * 148 else None,
                          "traffic": facts.get("dram_bytes_per_launch") if same_cfg else None,
-                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
-                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms_total / args.steps),
-                         "warp_inst_per_symbol": facts.get("warp_inst_per_symbol") if same_cfg else None,
-                         "issue_slot_utilisation": facts.get("issue_slot_utilisation") if same_cfg else None,
-                         "ncu": facts.get("_source", "profiles/r01_ncu_all_kernels_v11.md"),
-                         "note": "decode = dependent chain per stream: latency/issue-bound, not HBM-bound "
-                                 "(DESIGN.md section 5); traffic above the algorithmic bytes is the per-stream "
-                                 "context words + 64-byte records"},
+                         "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s",
+                                 "frac": hbm_achieved / peak, "algorithmic_bytes_per_launch": bytes_per_launch,
+                                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"},
+                         "ncu": facts.get("_source", facts_file), "ncu_facts_match_these_kernel_sources": facts_current,
+                         "note": "decode = one dependent chain per stream: latency/issue-bound, not HBM-bound (DESIGN.md "
+                                 "section 5); instructions per symbol and DRAM traffic come from the committed ncu capture "
+                                 "(they cannot be measured outside a profiler), kernel_ms is measured live with CUDA events"},
             "clocks": clocks,
             "rank_bytes": [int(x) for x in sizes.tolist()],
         }
-        if large is not None:
-            line["large_batch"] = large
+        if sweep:
+            line["sweep"] = sweep
+        if hbm is not None:
+            line["hbm_kernels"] = hbm
         if not args.no_cpu_baseline:
             codes, threads = cpu_sample(args, n)
             cv, cdt, cs = cpu_roundtrip_rate(codes, n, threads, repeats=cpu_repeats(codes.shape[0], n, threads))

@@ -14,6 +14,15 @@ _vp, _i32, _i64, _dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_
 
 SIGNATURES = {
     "lc_version": (ctypes.c_int, []),
+    "lc_debug_launch_count": (_i64, [_i32]),
+    "lc_quantize_affine_t": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
+    "lc_dequantize_affine_t": (ctypes.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
+    "lc_quantize_codebook_t": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "lc_dequantize_codebook_t": (ctypes.c_int, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "lc_encode_batch_t": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64, _vp, _i64,
+                                         _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "lc_decode_batch_t": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64,
+                                         _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "lc_quantize_affine": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "lc_dequantize_affine": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "lc_quantize_codebook": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
@@ -23,6 +32,7 @@ SIGNATURES = {
     "lc_coder_grid": (ctypes.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "lc_encode_batch": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64, _vp, _i64,
                                        _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "lc_model_update": (ctypes.c_int, [_vp, _i32, _i32, _dbl, _vp]),
     "lc_stateful_table_bytes": (_i64, [_i32, _i32]),
     "lc_stateful_table_offset": (_i64, [_i32, _i32, _i32]),
     "lc_stateful_encode": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp,
@@ -32,6 +42,13 @@ SIGNATURES = {
     "lc_decode_batch": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _dbl, _i32, _i32, _vp, _i64,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
 }
+
+
+ABI_VERSION = 2
+
+# `flags` of the _t entry points (include/latentcodec.h)
+FLAG_DEC_LATENCY_BUILD, FLAG_DEC_THROUGHPUT_BUILD, FLAG_DEC_GENERIC_SHAPE = 1, 2, 4
+FLAG_DEC_REGISTER_MODEL, FLAG_DEC_SERIAL, FLAG_ENC_SERIAL, FLAG_DEC_NO_SMALL = 8, 16, 32, 64
 
 
 class NativeLibraryError(RuntimeError):
@@ -64,8 +81,8 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.lc_version() != 1:
-        raise NativeLibraryError("liblatentcodec.so ABI version %d, expected 1" % lib.lc_version())
+    if lib.lc_version() != ABI_VERSION:
+        raise NativeLibraryError("liblatentcodec.so ABI version %d, expected %d" % (lib.lc_version(), ABI_VERSION))
     _lib = lib
     return lib
 

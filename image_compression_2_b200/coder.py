@@ -28,7 +28,12 @@ class DecodeFault(IndexError):
 
 
 class ContextModel:
-    """Parameter holder with the reference constructor (cabac_compression.py:66-76)."""
+    """The reference's model object (cabac_compression.py:60-162): same constructor, same two state containers,
+    same three methods.  The coder kernels keep their own device-side model while a stream is being coded; this
+    object is the host view of it -- read by a stateful call (import), filled in after it (export).  The methods
+    work on that view: `get_context` and `get_probability` are index arithmetic and a dictionary lookup,
+    `update_model` runs ContextModel.update_model on the GPU (lc_model_update: the same exact float64 update,
+    NumPy pairwise-sum order, the coder kernels apply) -- there is no CPU arithmetic path here either."""
 
     def __init__(self, n_symbols=256, context_size=5, adaptation_rate=0.05, track_state=False):
         self.n_symbols = n_symbols
@@ -40,6 +45,40 @@ class ContextModel:
 
     def is_fresh(self):
         return len(self.context_models) == 0 and len(self.context_counts) == 0
+
+    def get_context(self, data, pos, shape):
+        """(:78-117) (left, up) neighbours with -1 sentinels for a 3-D shape, () otherwise."""
+        if len(shape) != 3:
+            return ()
+        batch, ws, dim = np.unravel_index(pos, shape)
+        left = int(data[batch, ws, dim - 1]) if dim > 0 else -1
+        up = int(data[batch, ws - 1, dim]) if ws > 0 else -1
+        return (left, up)
+
+    def get_probability(self, context, symbol=None):
+        """(:146-162) the context's vector (a missing context is ones(n)/n and exists from now on, :73)."""
+        context = tuple(int(c) for c in context)
+        probs = self.context_models.get(context)
+        if probs is None:
+            probs = self.context_models[context] = np.ones(self.n_symbols) / self.n_symbols
+        return probs if symbol is None else probs[symbol]
+
+    def update_model(self, context, symbol, device=None):
+        """(:119-144) EMA on `symbol`, the others rescaled by the pairwise-sum factor; counts += 1."""
+        from . import _native
+        lib = _native.load()
+        dev = _device(device)
+        context = tuple(int(c) for c in context)
+        n = int(self.n_symbols)
+        symbol = int(symbol)
+        if not (-n <= symbol < n):
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (symbol, n))
+        vec = torch.from_numpy(np.ascontiguousarray(self.get_probability(context), np.float64)).to(dev)
+        with codec._On(vec) as on:
+            _native.check(lib.lc_model_update(vec.data_ptr(), n, symbol, float(self.adaptation_rate), on.stream),
+                          "lc_model_update")
+        self.context_models[context] = vec.cpu().numpy()
+        self.context_counts[context] = self.context_counts.get(context, 0) + 1
 
 
 def _wants_state(context_model):
@@ -149,22 +188,20 @@ def cabac_encode_packed(data, context_model, mode=None, device=None):
         slot_bytes = (layout.total * 12 + 256 + 15) // 16 * 16
         slot = torch.empty(slot_bytes, dtype=torch.uint8, device=dev)
         res = torch.zeros(3, dtype=torch.int32, device=dev)
-        _native.check(lib.lc_stateful_encode(idx.data_ptr(), layout.imgs, layout.R, layout.C, int(context_model.n_symbols),
-                                             float(context_model.adaptation_rate), codec.MODES[mode or DEFAULT_MODE],
-                                             layout.has_ctx, table.buf.data_ptr(), table.buf.numel(), slot.data_ptr(),
-                                             slot_bytes, res[0:].data_ptr(), res[1:].data_ptr(), res[2:].data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream), "lc_stateful_encode")
+        with codec._On(idx, table.buf, slot, res) as on:
+            _native.check(lib.lc_stateful_encode(idx.data_ptr(), layout.imgs, layout.R, layout.C,
+                                                 int(context_model.n_symbols), float(context_model.adaptation_rate),
+                                                 codec.MODES[mode or DEFAULT_MODE], layout.has_ctx, table.buf.data_ptr(),
+                                                 table.buf.numel(), slot.data_ptr(), slot_bytes, res[0:].data_ptr(),
+                                                 res[1:].data_ptr(), res[2:].data_ptr(), on.stream), "lc_stateful_encode")
         nb, st, fi = (int(x) for x in res.cpu())
         table.export(context_model)  # the reference has mutated the model up to the fault before it raises
         raise_for_status(st, fi, "cabac_encode")
         return slot[:(nb + 7) // 8].cpu().numpy().tobytes(), nb
-    enc = codec.encode_batch(idx, layout, context_model.n_symbols, mode=mode or DEFAULT_MODE,
-                             adaptation_rate=context_model.adaptation_rate)
-    streams, nbits, status, fault = enc.to_host()
-    if int(status[0]) == 5:  # slot too small for this stream: retry with the worst case
-        enc = codec.encode_batch(idx, layout, context_model.n_symbols, mode=mode or DEFAULT_MODE,
-                                 adaptation_rate=context_model.adaptation_rate, slot_bytes=layout.total * 12 + 256)
-        streams, nbits, status, fault = enc.to_host()
+    # (a stream that overflows the default slot is coded again with the worst-case slot)
+    _, (streams, nbits, status, fault) = codec.encode_batch_checked(idx, layout, context_model.n_symbols,
+                                                                    mode=mode or DEFAULT_MODE,
+                                                                    adaptation_rate=context_model.adaptation_rate)
     raise_for_status(status[0], fault[0], "cabac_encode")
     return streams[0], int(nbits[0])
 
@@ -182,11 +219,12 @@ def cabac_decode(encoded_bytes, context_model, shape, mode=None, device=None):
         table = _StatefulTable(context_model, layout, dev)
         out = torch.empty(layout.total, dtype=torch.int32, device=dev)
         res = torch.zeros(2, dtype=torch.int32, device=dev)
-        _native.check(lib.lc_stateful_decode(data.data_ptr(), len(bytes(encoded_bytes)), layout.imgs, layout.R, layout.C,
-                                             int(context_model.n_symbols), float(context_model.adaptation_rate),
-                                             codec.MODES[mode or DEFAULT_MODE], layout.has_ctx, table.buf.data_ptr(),
-                                             table.buf.numel(), out.data_ptr(), res[0:].data_ptr(), res[1:].data_ptr(),
-                                             torch.cuda.current_stream().cuda_stream), "lc_stateful_decode")
+        with codec._On(data, table.buf, out, res) as on:
+            _native.check(lib.lc_stateful_decode(data.data_ptr(), len(bytes(encoded_bytes)), layout.imgs, layout.R,
+                                                 layout.C, int(context_model.n_symbols),
+                                                 float(context_model.adaptation_rate), codec.MODES[mode or DEFAULT_MODE],
+                                                 layout.has_ctx, table.buf.data_ptr(), table.buf.numel(), out.data_ptr(),
+                                                 res[0:].data_ptr(), res[1:].data_ptr(), on.stream), "lc_stateful_decode")
         st, fi = (int(x) for x in res.cpu())
         table.export(context_model)
         raise_for_status(st, fi, "cabac_decode")
@@ -210,9 +248,9 @@ def cabac_encode_batch(data, n_symbols=256, adaptation_rate=0.05, mode=None, dev
     else:
         arr = np.ascontiguousarray(np.asarray(data), dtype=np.int32)
         idx, shape = torch.from_numpy(arr).to(dev), arr.shape
-    enc = codec.encode_batch(idx, codec.layout_independent(shape), n_symbols, mode=mode or DEFAULT_MODE,
-                             adaptation_rate=adaptation_rate)
-    return enc.to_host()
+    _, host = codec.encode_batch_checked(idx, codec.layout_independent(shape), n_symbols, mode=mode or DEFAULT_MODE,
+                                         adaptation_rate=adaptation_rate)
+    return host
 
 
 def cabac_decode_batch(streams, shape, n_symbols=256, adaptation_rate=0.05, mode=None, device=None):

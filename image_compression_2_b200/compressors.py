@@ -89,9 +89,15 @@ class StyleGAN3Compressor(nn.Module):
 
 
 class GumbelSoftmaxDiscretization(nn.Module):
-    """Codebook quantiser (quantiser B).  Only the inference path of the reference layer is
-    provided: nearest-codebook indices and the codebook lookup.  The Gumbel sampling, temperature
-    annealing and usage statistics are training code and out of scope."""
+    """Codebook quantiser (quantiser B), gumbel_softmax_compression.py:26-137.
+
+    Same constructor, parameters and buffers as the reference layer (`codebook`, `log_temperature` -- a Parameter
+    when learnable_temp --, `usage`), so a reference `discretization_state_dict` loads (cabac_compression.py:642-675),
+    and the same accessors (`temperature`, `update_temp`, `get_code_usage`).  forward() provides the inference
+    result the compressors consume: nearest-codebook indices (argmin, :118) and their codebook values, computed by
+    the CUDA kernel without the [N,n] distance matrix.  The random Gumbel-softmax sample of the reference's
+    training forward (:103-108) is training code and out of scope: `discretized` here is always codebook[argmin],
+    the deterministic value `compress`/`decompress` use."""
 
     def __init__(self, latent_dim=512, n_embeddings=256, temperature=1.0, straight_through=True, learnable_temp=True):
         super().__init__()
@@ -102,15 +108,37 @@ class GumbelSoftmaxDiscretization(nn.Module):
         # the table comes from the host's torch.linspace, exactly as in the reference (:49-52);
         # the kernels take it as an argument and never rebuild it
         self.register_buffer("codebook", torch.linspace(-1, 1, n_embeddings).float())
+        if learnable_temp:  # (:54-58)
+            self.log_temperature = nn.Parameter(torch.ones(1) * np.log(temperature))
+        else:
+            self.register_buffer("log_temperature", torch.ones(1) * np.log(temperature))
+        self.register_buffer("usage", torch.zeros(n_embeddings))  # (:61)
 
-    def forward(self, z, hard=True):
+    @property
+    def temperature(self):
+        return torch.exp(self.log_temperature)
+
+    def update_temp(self, anneal_rate=0.00003, min_temp=0.5):
+        """(:67-71)"""
+        with torch.no_grad():
+            self.log_temperature.clamp_(min=np.log(min_temp))
+            self.log_temperature -= anneal_rate
+
+    def forward(self, z, hard=None):
         """-> (codebook[idx] shaped like z, perplexity of the hard assignment, idx int64 flat)."""
         idx, deq = codec.quantize_codebook(z.detach().float().contiguous(), self.codebook, want_deq=True)
         flat = idx.reshape(-1).long()
         counts = torch.bincount(flat, minlength=self.n_embeddings).float()
+        if self.training:  # usage statistics (:121-123)
+            self.usage += counts[: self.n_embeddings].to(self.usage.device)
         probs = counts / counts.sum().clamp(min=1)
         perplexity = torch.exp(-torch.sum(probs * torch.log(probs + 1e-10)))
         return deq, perplexity, flat
+
+    def get_code_usage(self):
+        """(:131-137)"""
+        total = self.usage.sum().float()
+        return self.usage / total if total > 0 else self.usage
 
 
 class GumbelSoftmaxCompressor(nn.Module):
@@ -220,9 +248,9 @@ class CABACCompressor:
                        if self.container == "reference" else packed)
         elif use_cabac:
             layout = codec.layout_reference(shape)
-            enc = codec.encode_batch(idx.reshape(-1), layout, n, mode=self.mode or coder.DEFAULT_MODE,
-                                     adaptation_rate=self.context_model.adaptation_rate)
-            streams, nbits, status, fault = enc.to_host()
+            _, (streams, nbits, status, fault) = codec.encode_batch_checked(
+                idx.reshape(-1), layout, n, mode=self.mode or coder.DEFAULT_MODE,
+                adaptation_rate=self.context_model.adaptation_rate)
             coder.raise_for_status(status[0], fault[0], "CABACCompressor.compress")
             if self.container == "reference":
                 encoded = np.unpackbits(np.frombuffer(streams[0], dtype=np.uint8))[: int(nbits[0])].tobytes()

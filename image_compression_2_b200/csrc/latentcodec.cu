@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 
@@ -13,33 +15,58 @@
 #include "lc_encoder_par.cuh"
 #include "lc_decoder_fast.cuh"
 #include "lc_decoder_v2.cuh"
+#ifdef LC_DEBUG_VARIANTS
 #include "lc_decoder_v3.cuh"
+#endif
 #include "lc_encoder_sparse.cuh"
 #include "lc_encoder_pack.cuh"
 #include "lc_stateful.cuh"
 
-#define LC_CUDA_RET()                                                     \
-    do {                                                                  \
-        cudaError_t e__ = cudaGetLastError();                             \
-        if (e__ != cudaSuccess) return -1000 - (int)e__;                  \
-    } while (0)
+// ---- per-device facts (immutable once read, so caching them is not mutable library state): SM count, and whether
+// the kernels' opt-in attributes (more than 48 KB of dynamic shared memory) have been set on that device.  Keyed by
+// cudaGetDevice(); atomics make concurrent first calls from several host threads benign (both write the same value).
+#define LC_MAX_DEVICES 64
+static std::atomic<int> g_sm_count[LC_MAX_DEVICES];
+static std::atomic<int> g_attrs_set[LC_MAX_DEVICES];
+
+static int lc_cur_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
 
 static int lc_num_sms()
 {
-    static int cached = 0;
-    if (cached) return cached;
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    const int dev = lc_cur_device();
+    if (dev >= 0 && dev < LC_MAX_DEVICES) {
+        const int c = g_sm_count[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return 148; // B200; keeps the sizing helpers usable on a machine without a GPU
     }
-    cached = n;
+    if (dev < LC_MAX_DEVICES) g_sm_count[dev].store(n, std::memory_order_relaxed);
     return n;
 }
 
+// launches issued by the calling host thread (diagnostic: bench.py reports it as gpu_launches)
+static thread_local long long t_launches = 0;
+#define LC_LAUNCHED()                                                     \
+    do {                                                                  \
+        cudaError_t e__ = cudaGetLastError();                             \
+        if (e__ != cudaSuccess) return -1000 - (int)e__;                  \
+        t_launches++;                                                     \
+    } while (0)
+
 // =================================================================================================
-// K1: quantiser A / dequantiser A  (stylegan3_hvae_full.py:313-316).  HBM-bound, 128-bit accesses.
+// K1: quantiser A / dequantiser A  (stylegan3_hvae_full.py:313-316).  HBM-bound: 128-bit loads, four
+// of them in flight per thread, streaming (evict-first) accesses; the index array leaves as int32,
+// uint16 or uint8 (4 / 2 / 1 bytes per symbol of write traffic).
 // =================================================================================================
+#define LC_EW_UNROLL 4
 __device__ __forceinline__ float lc_qa_round(float w, float scale)
 {
     const float a = __fadd_rn(w, 1.0f);
@@ -58,48 +85,101 @@ __device__ __forceinline__ int lc_qa_int(float q)
     return (q == q && fabsf(q) < 2.0e9f) ? (int)q : (int)0x80000000;
 }
 
+// four indices -> one vector store.  int32 keeps the unclamped value (the reference's quantiser A does not clamp);
+// the narrow types hold what the coder consumes: the index clamped to the alphabet [0, hi].
+template <typename T> struct LcIdx4;
+template <> struct LcIdx4<int> {
+    typedef int4 V;
+    static __device__ __forceinline__ int fix(int v, int) { return v; }
+    static __device__ __forceinline__ V pack(int a, int b, int c, int d) { return make_int4(a, b, c, d); }
+    static __device__ __forceinline__ int4 unpack(V v) { return v; }
+};
+template <> struct LcIdx4<unsigned short> {
+    typedef ushort4 V;
+    static __device__ __forceinline__ int fix(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+    static __device__ __forceinline__ V pack(int a, int b, int c, int d)
+    {
+        return make_ushort4((unsigned short)a, (unsigned short)b, (unsigned short)c, (unsigned short)d);
+    }
+    static __device__ __forceinline__ int4 unpack(V v) { return make_int4(v.x, v.y, v.z, v.w); }
+};
+template <> struct LcIdx4<unsigned char> {
+    typedef uchar4 V;
+    static __device__ __forceinline__ int fix(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+    static __device__ __forceinline__ V pack(int a, int b, int c, int d)
+    {
+        return make_uchar4((unsigned char)a, (unsigned char)b, (unsigned char)c, (unsigned char)d);
+    }
+    static __device__ __forceinline__ int4 unpack(V v) { return make_int4(v.x, v.y, v.z, v.w); }
+};
+
+template <typename T>
 __global__ void __launch_bounds__(256) lc_quant_affine_kernel(const float *__restrict__ w, long long n_elem, float scale,
-                                                              int *__restrict__ idx_out, float *__restrict__ wq_out)
+                                                              int hi, T *__restrict__ idx_out, float *__restrict__ wq_out)
 {
+    typedef typename LcIdx4<T>::V IV;
     const long long n4 = n_elem >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 v = __ldcs(reinterpret_cast<const float4 *>(w) + i);
-        float4 q;
-        q.x = lc_qa_round(v.x, scale); q.y = lc_qa_round(v.y, scale);
-        q.z = lc_qa_round(v.z, scale); q.w = lc_qa_round(v.w, scale);
-        if (idx_out) {
-            int4 o; o.x = lc_qa_int(q.x); o.y = lc_qa_int(q.y); o.z = lc_qa_int(q.z); o.w = lc_qa_int(q.w);
-            __stcs(reinterpret_cast<int4 *>(idx_out) + i, o);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * LC_EW_UNROLL) {
+        float4 v[LC_EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i < n4) v[u] = __ldcs(reinterpret_cast<const float4 *>(w) + i);
         }
-        if (wq_out) {
-            float4 o; o.x = lc_qa_deq(q.x, scale); o.y = lc_qa_deq(q.y, scale);
-            o.z = lc_qa_deq(q.z, scale); o.w = lc_qa_deq(q.w, scale);
-            __stcs(reinterpret_cast<float4 *>(wq_out) + i, o);
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i >= n4) break;
+            float4 q;
+            q.x = lc_qa_round(v[u].x, scale); q.y = lc_qa_round(v[u].y, scale);
+            q.z = lc_qa_round(v[u].z, scale); q.w = lc_qa_round(v[u].w, scale);
+            if (idx_out)
+                __stcs(reinterpret_cast<IV *>(idx_out) + i,
+                       LcIdx4<T>::pack(LcIdx4<T>::fix(lc_qa_int(q.x), hi), LcIdx4<T>::fix(lc_qa_int(q.y), hi),
+                                       LcIdx4<T>::fix(lc_qa_int(q.z), hi), LcIdx4<T>::fix(lc_qa_int(q.w), hi)));
+            if (wq_out) {
+                float4 o; o.x = lc_qa_deq(q.x, scale); o.y = lc_qa_deq(q.y, scale);
+                o.z = lc_qa_deq(q.z, scale); o.w = lc_qa_deq(q.w, scale);
+                __stcs(reinterpret_cast<float4 *>(wq_out) + i, o);
+            }
         }
     }
     // tail (n_elem not a multiple of 4)
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
         const float q = lc_qa_round(w[i], scale);
-        if (idx_out) idx_out[i] = lc_qa_int(q);
+        if (idx_out) idx_out[i] = (T)LcIdx4<T>::fix(lc_qa_int(q), hi);
         if (wq_out) wq_out[i] = lc_qa_deq(q, scale);
     }
 }
 
-__global__ void __launch_bounds__(256) lc_dequant_affine_kernel(const int *__restrict__ idx, long long n_elem, float scale,
+template <typename T>
+__global__ void __launch_bounds__(256) lc_dequant_affine_kernel(const T *__restrict__ idx, long long n_elem, float scale,
                                                                 float *__restrict__ w_out)
 {
+    typedef typename LcIdx4<T>::V IV;
     const long long n4 = n_elem >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const int4 v = __ldcs(reinterpret_cast<const int4 *>(idx) + i);
-        float4 o;
-        o.x = lc_qa_deq((float)v.x, scale); o.y = lc_qa_deq((float)v.y, scale);
-        o.z = lc_qa_deq((float)v.z, scale); o.w = lc_qa_deq((float)v.w, scale);
-        __stcs(reinterpret_cast<float4 *>(w_out) + i, o);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * LC_EW_UNROLL) {
+        IV v[LC_EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i < n4) v[u] = __ldcs(reinterpret_cast<const IV *>(idx) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i >= n4) break;
+            const int4 x = LcIdx4<T>::unpack(v[u]);
+            float4 o;
+            o.x = lc_qa_deq((float)x.x, scale); o.y = lc_qa_deq((float)x.y, scale);
+            o.z = lc_qa_deq((float)x.z, scale); o.w = lc_qa_deq((float)x.w, scale);
+            __stcs(reinterpret_cast<float4 *>(w_out) + i, o);
+        }
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride)
-        w_out[i] = lc_qa_deq((float)idx[i], scale);
+        w_out[i] = lc_qa_deq((float)(int)idx[i], scale);
 }
 
 // =================================================================================================
@@ -143,10 +223,12 @@ __device__ __forceinline__ int lc_argmin_scan(const float *cb, int n, float z)
     return bi;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) lc_quant_codebook_kernel(const float *__restrict__ z, long long n_elem,
                                                                 const float *__restrict__ codebook, int n, int sorted,
-                                                                int *__restrict__ idx_out, float *__restrict__ deq_out)
+                                                                T *__restrict__ idx_out, float *__restrict__ deq_out)
 {
+    typedef typename LcIdx4<T>::V IV;
     extern __shared__ float cb[];
     for (int i = threadIdx.x; i < n; i += blockDim.x) cb[i] = codebook[i];
     __syncthreads();
@@ -154,54 +236,79 @@ __global__ void __launch_bounds__(256) lc_quant_codebook_kernel(const float *__r
     const float guess_scale = (sorted && span > 0.0f) ? (float)(n - 1) / span : 0.0f;
     const long long n4 = n_elem >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 v = __ldcs(reinterpret_cast<const float4 *>(z) + i);
-        int4 o;
-        if (sorted) {
-            o.x = lc_argmin_sorted(cb, n, v.x, guess_scale); o.y = lc_argmin_sorted(cb, n, v.y, guess_scale);
-            o.z = lc_argmin_sorted(cb, n, v.z, guess_scale); o.w = lc_argmin_sorted(cb, n, v.w, guess_scale);
-        } else {
-            o.x = lc_argmin_scan(cb, n, v.x); o.y = lc_argmin_scan(cb, n, v.y);
-            o.z = lc_argmin_scan(cb, n, v.z); o.w = lc_argmin_scan(cb, n, v.w);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * LC_EW_UNROLL) {
+        float4 v[LC_EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i < n4) v[u] = __ldcs(reinterpret_cast<const float4 *>(z) + i);
         }
-        __stcs(reinterpret_cast<int4 *>(idx_out) + i, o);
-        if (deq_out) {
-            float4 d; d.x = cb[o.x]; d.y = cb[o.y]; d.z = cb[o.z]; d.w = cb[o.w];
-            __stcs(reinterpret_cast<float4 *>(deq_out) + i, d);
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i >= n4) break;
+            int4 o;
+            if (sorted) {
+                o.x = lc_argmin_sorted(cb, n, v[u].x, guess_scale); o.y = lc_argmin_sorted(cb, n, v[u].y, guess_scale);
+                o.z = lc_argmin_sorted(cb, n, v[u].z, guess_scale); o.w = lc_argmin_sorted(cb, n, v[u].w, guess_scale);
+            } else {
+                o.x = lc_argmin_scan(cb, n, v[u].x); o.y = lc_argmin_scan(cb, n, v[u].y);
+                o.z = lc_argmin_scan(cb, n, v[u].z); o.w = lc_argmin_scan(cb, n, v[u].w);
+            }
+            __stcs(reinterpret_cast<IV *>(idx_out) + i, LcIdx4<T>::pack(o.x, o.y, o.z, o.w));
+            if (deq_out) {
+                float4 d; d.x = cb[o.x]; d.y = cb[o.y]; d.z = cb[o.z]; d.w = cb[o.w];
+                __stcs(reinterpret_cast<float4 *>(deq_out) + i, d);
+            }
         }
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
         const int o = sorted ? lc_argmin_sorted(cb, n, z[i], guess_scale) : lc_argmin_scan(cb, n, z[i]);
-        idx_out[i] = o;
+        idx_out[i] = (T)o;
         if (deq_out) deq_out[i] = cb[o];
     }
 }
 
-__global__ void __launch_bounds__(256) lc_dequant_codebook_kernel(const int *__restrict__ idx, long long n_elem,
+template <typename T>
+__global__ void __launch_bounds__(256) lc_dequant_codebook_kernel(const T *__restrict__ idx, long long n_elem,
                                                                   const float *__restrict__ codebook, int n,
                                                                   float *__restrict__ w_out)
 {
+    typedef typename LcIdx4<T>::V IV;
     extern __shared__ float cb[];
     for (int i = threadIdx.x; i < n; i += blockDim.x) cb[i] = codebook[i];
     __syncthreads();
     const float nanv = __int_as_float(0x7fc00000);
     const long long n4 = n_elem >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const int4 v = __ldcs(reinterpret_cast<const int4 *>(idx) + i);
-        float4 o;
-        o.x = (unsigned)v.x < (unsigned)n ? cb[v.x] : nanv; o.y = (unsigned)v.y < (unsigned)n ? cb[v.y] : nanv;
-        o.z = (unsigned)v.z < (unsigned)n ? cb[v.z] : nanv; o.w = (unsigned)v.w < (unsigned)n ? cb[v.w] : nanv;
-        __stcs(reinterpret_cast<float4 *>(w_out) + i, o);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * LC_EW_UNROLL) {
+        IV v[LC_EW_UNROLL];
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i < n4) v[u] = __ldcs(reinterpret_cast<const IV *>(idx) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < LC_EW_UNROLL; u++) {
+            const long long i = i0 + u * stride;
+            if (i >= n4) break;
+            const int4 x = LcIdx4<T>::unpack(v[u]);
+            float4 o;
+            o.x = (unsigned)x.x < (unsigned)n ? cb[x.x] : nanv; o.y = (unsigned)x.y < (unsigned)n ? cb[x.y] : nanv;
+            o.z = (unsigned)x.z < (unsigned)n ? cb[x.z] : nanv; o.w = (unsigned)x.w < (unsigned)n ? cb[x.w] : nanv;
+            __stcs(reinterpret_cast<float4 *>(w_out) + i, o);
+        }
     }
-    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride)
-        w_out[i] = (unsigned)idx[i] < (unsigned)n ? cb[idx[i]] : nanv;
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
+        const int x = (int)idx[i];
+        w_out[i] = (unsigned)x < (unsigned)n ? cb[x] : nanv;
+    }
 }
 
 // =================================================================================================
 // K3 / K5: the coder kernels (one warp per block, persistent over streams) -- lc_coder.cuh
 // =================================================================================================
-__global__ void __launch_bounds__(32) lc_encode_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
+__global__ void __launch_bounds__(32) lc_encode_kernel(LcCoderCfg cfg, LcCodes codes, int B,
                                                        unsigned char *slots, uint32_t slot_bytes, int *nbits, int *status,
                                                        int *fault, char *scratch)
 {
@@ -211,7 +318,7 @@ __global__ void __launch_bounds__(32) lc_encode_kernel(LcCoderCfg cfg, const int
 
 __global__ void __launch_bounds__(32) lc_decode_kernel(LcCoderCfg cfg, const unsigned char *__restrict__ bytes,
                                                        const long long *__restrict__ offsets, const int *__restrict__ nbits,
-                                                       int B, int *out, const float *__restrict__ deq_table, float *deq_out,
+                                                       int B, LcIdxOut out, const float *__restrict__ deq_table, float *deq_out,
                                                        int *status, int *fault, char *scratch, int only_flagged)
 {
     extern __shared__ __align__(16) char lc_smem[];
@@ -220,7 +327,7 @@ __global__ void __launch_bounds__(32) lc_decode_kernel(LcCoderCfg cfg, const uns
 
 __global__ void __launch_bounds__(32) lc_fast_decode_kernel(LcCoderCfg cfg, const unsigned char *__restrict__ bytes,
                                                             const long long *__restrict__ offsets,
-                                                            const int *__restrict__ nbits, int B, int *out,
+                                                            const int *__restrict__ nbits, int B, LcIdxOut out,
                                                             const float *__restrict__ deq_table, float *deq_out,
                                                             int *status, int *fault, char *scratch)
 {
@@ -248,7 +355,7 @@ __global__ void __launch_bounds__(32) lc_v2_tables_kernel(LcCoderCfg cfg, double
 #define LC_V2_KERNEL(NAME, FN, FC, FR, PER_SM, OUTLINE)                                                                         \
     __global__ void __launch_bounds__(32 * LCV_WARPS, PER_SM)                                                          \
         NAME(LcCoderCfg cfg, LcV2Cfg vc, const unsigned char *__restrict__ bytes, const long long *__restrict__ offsets, \
-             const int *__restrict__ nbits, int B, int *out, const float *__restrict__ deq_table, float *deq_out,      \
+             const int *__restrict__ nbits, int B, LcIdxOut out, const float *__restrict__ deq_table, float *deq_out, \
              int *status, int *fault, char *scratch, const double *tables, const char *t2)                             \
     {                                                                                                                  \
         extern __shared__ __align__(16) char lc_smem[];                                                                \
@@ -260,7 +367,9 @@ LC_V2_KERNEL(lc_decode_v2_w8_kernel, 256, 512, 16, LC_V2_LAT_PER_SM, false)
 LC_V2_KERNEL(lc_decode_v2_thr_kernel, 0, 0, 0, LC_V2_THR_PER_SM, true)
 LC_V2_KERNEL(lc_decode_v2_w8_thr_kernel, 256, 512, 16, LC_V2_THR_PER_SM, true)
 
-// Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream
+#ifdef LC_DEBUG_VARIANTS
+// Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream -- measured slower than v2
+// (the two hand-overs per symbol cost what the decoder warp saves); debug builds only
 __global__ void __launch_bounds__(32 * LC3_WARPS, 7) lc_decode_v3_kernel(LcCoderCfg cfg, LcV2Cfg vc,
                                                                           const unsigned char *__restrict__ bytes,
                                                                           const long long *__restrict__ offsets,
@@ -272,6 +381,7 @@ __global__ void __launch_bounds__(32 * LC3_WARPS, 7) lc_decode_v3_kernel(LcCoder
     extern __shared__ __align__(16) char lc_smem[];
     lc3_decode_block(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, scratch, tables, lc_smem);
 }
+#endif
 
 // =================================================================================================
 // K3-parallel: the encoder split by context group (lc_encoder_par.cuh)
@@ -292,7 +402,7 @@ typedef cub::BlockScan<int, LC_SORT_THREADS> LcBlockScan;
 // Also emits what needs no model: the closed-form interval of every first visit (uniform model: cum[i] = i/n) and,
 // when `tables` is given, the interval of every second visit (table of exact cumsums of the model after one update,
 // lcv_tables_block), plus glist/ngroups = the contexts visited at least three times (the work items of phase A).
-__global__ void __launch_bounds__(LC_SORT_THREADS) lc_enc_sort_kernel(LcCoderCfg cfg, const int *__restrict__ codes,
+__global__ void __launch_bounds__(LC_SORT_THREADS) lc_enc_sort_kernel(LcCoderCfg cfg, LcCodes codes,
                                                           uint32_t *__restrict__ skeys, unsigned short *__restrict__ spos,
                                                           int *__restrict__ first_bad, unsigned short *__restrict__ glist,
                                                           int *__restrict__ ngroups, double *__restrict__ ivs,
@@ -303,7 +413,7 @@ __global__ void __launch_bounds__(LC_SORT_THREADS) lc_enc_sort_kernel(LcCoderCfg
     __shared__ int s_first_bad;
     constexpr int ITEMS = LC_PAR_MAX_SYMBOLS / LC_SORT_THREADS;
     const int total = cfg.total, n = cfg.n, C = cfg.C, RC = cfg.R * cfg.C;
-    const int *c = codes + (size_t)blockIdx.x * total;
+    const LcCodes c = codes + (size_t)blockIdx.x * total;
     if (threadIdx.x == 0) s_first_bad = total;
     __syncthreads();
     for (int p = threadIdx.x; p < total; p += LC_SORT_THREADS) {
@@ -395,7 +505,8 @@ __global__ void __launch_bounds__(LC_SORT_THREADS) lc_enc_sort_kernel(LcCoderCfg
     if (threadIdx.x == 0) ngroups[blockIdx.x] = g_total;
 }
 
-__global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, const int *__restrict__ codes, int B,
+#ifdef LC_DEBUG_VARIANTS // the dense warp-per-group phase A (4.1 ms on the benchmark against 1.3 ms): debug builds only
+__global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, LcCodes codes, int B,
                                                              const uint32_t *__restrict__ skeys,
                                                              const unsigned short *__restrict__ spos,
                                                              const int *__restrict__ first_bad, double *ivs)
@@ -403,13 +514,14 @@ __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, con
     extern __shared__ __align__(16) char lc_smem[];
     lc_enc_phase_a_block(cfg, codes, B, skeys, spos, first_bad, ivs, lc_smem);
 }
+#endif
 
 #define LCS_BLOCK_WARPS 4
 #ifndef LCS_BLOCKS_PER_SM
 #define LCS_BLOCKS_PER_SM 12
 #endif
 __global__ void __launch_bounds__(32 * LCS_BLOCK_WARPS, LCS_BLOCKS_PER_SM) lc_enc_phase_a_sparse_kernel(
-    LcCoderCfg cfg, const int *__restrict__ codes, int B, const uint32_t *__restrict__ skeys,
+    LcCoderCfg cfg, LcCodes codes, int B, const uint32_t *__restrict__ skeys,
     const unsigned short *__restrict__ spos, const int *__restrict__ first_bad, const unsigned short *__restrict__ glist,
     const int *__restrict__ ngroups, double *ivs, unsigned int *task_counter, const double *__restrict__ tables,
     const char *__restrict__ t2)
@@ -475,6 +587,18 @@ __global__ void __launch_bounds__(32) lc_stateful_decode_kernel(LcCoderCfg cfg, 
     int fi = 0;
     lcs_decode_stream(W, T, bytes, nbytes, out, &fi);
     if (W.lane == 0) { *status = W.status; *fault = fi; }
+}
+
+// ContextModel.update_model on one vector (the host-side ContextModel.update_model method)
+__global__ void __launch_bounds__(32) lc_model_update_kernel(LcCoderCfg cfg, double *vec, int symbol)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    LcWarp W;
+    lc_warp_init(W, cfg, lc_smem, (char *)0);
+    for (int i = W.lane; i < W.n; i += 32) W.dense[i] = vec[i];
+    __syncwarp();
+    lc_dense_update(W, symbol);
+    for (int i = W.lane; i < W.n; i += 32) vec[i] = W.dense[i];
 }
 
 // =================================================================================================
@@ -546,6 +670,31 @@ static int lc_make_cfg(LcCoderCfg &cfg, int imgs, int R, int C, int n, double ra
     return lc_cfg_finalize(&cfg);
 }
 
+static bool lc_idx_bytes_ok(int idx_bytes, int n) // can an element of idx_bytes bytes hold every symbol below n?
+{
+    return idx_bytes == 4 || (idx_bytes == 2 && n <= 65536) || (idx_bytes == 1 && n <= 256);
+}
+
+// Opt-in attributes (more than 48 KB of dynamic shared memory) are per device: set once per device, not per process.
+static void lc_prepare_device()
+{
+    const int dev = lc_cur_device();
+    if (dev >= 0 && dev < LC_MAX_DEVICES && g_attrs_set[dev].load(std::memory_order_acquire)) return;
+    cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LcBlockSort::TempStorage));
+    cudaFuncSetAttribute(lc_enc_phase_b2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(lc_enc_phase_a_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LCS_BLOCK_WARPS * 1024 * 8);
+    cudaFuncSetAttribute(lc_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lc_decode_v2_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lc_decode_v2_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lc_decode_v2_w8_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+#ifdef LC_DEBUG_VARIANTS
+    cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
+    cudaFuncSetAttribute(lc_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+#endif
+    cudaGetLastError();
+    if (dev >= 0 && dev < LC_MAX_DEVICES) g_attrs_set[dev].store(1, std::memory_order_release);
+}
+
 static int lc_grid_for(const LcCoderCfg &cfg, int B)
 {
     int per_sm = (int)((227u * 1024u) / (cfg.sm_bytes + 1024u));
@@ -560,38 +709,31 @@ static int lc_grid_for(const LcCoderCfg &cfg, int B)
 #define LC_PAR_STREAM_BYTES ((int64_t)LC_PAR_MAX_SYMBOLS * (4 + 2 + 8 + 8) + LC_PAR_MAX_GROUPS * 2 + 32)
 #define LC_PAR_TILE 8192
 
-static bool lc_use_parallel_encoder(const LcCoderCfg &cfg) { return cfg.has_ctx && cfg.total <= LC_PAR_MAX_SYMBOLS; }
-
-// decoder v2: which kernel decodes (LC_DECODER=fast keeps the previous kernel, for A/B runs), grid, scratch
-// 0: register-model kernel, 2: v2 (default), 3: v3 -- measured slower than v2 on the benchmark (11.1 vs 10.7 ms/step:
-// the two hand-overs per symbol cost what the decoder warp saves), kept selectable.  LC_DECODER=fast|v2|v3.
-static int lc_decoder_choice()
+static bool lc_use_parallel_encoder(const LcCoderCfg &cfg, int flags)
 {
-    static int choice = -1;
-    if (choice < 0) {
-        const char *e = getenv("LC_DECODER");
-        choice = 2;
-        if (e && e[0] == 'f') choice = 0;
-        if (e && e[0] == 'v' && e[1] == '3') choice = 3;
-    }
-    return choice;
+    return cfg.has_ctx && cfg.total <= LC_PAR_MAX_SYMBOLS && !(flags & LC_FLAG_ENC_SERIAL);
 }
-static bool lc_use_decoder_v2(const LcCoderCfg &cfg) { return lc_decoder_choice() != 0 && lcv_eligible(cfg); }
+
+// which kernel decodes: v2 (decoder + updater warp, n <= 256), the register-model kernel (lc_decoder_fast.cuh), or the
+// generic serial kernel (verbatim mode, global-context streams); the caller's `flags` can force the slower ones
+static bool lc_use_decoder_v2(const LcCoderCfg &cfg, int flags)
+{
+    return lcv_eligible(cfg) && !(flags & (LC_FLAG_DEC_REGISTER_MODEL | LC_FLAG_DEC_SERIAL));
+}
 // resident streams per SM for a batch of B: the latency build while one wave of it holds the batch
-static int lc_v2_per_sm(const LcV2Cfg &vc, int B)
+static int lc_v2_per_sm(const LcV2Cfg &vc, int B, int flags)
 {
     int fit = (int)((227u * 1024u) / (vc.sm_bytes + 1024u));
     if (fit < 1) fit = 1;
     const int lat = fit < LC_V2_LAT_PER_SM ? fit : LC_V2_LAT_PER_SM;
     const int thr = fit < LC_V2_THR_PER_SM ? fit : LC_V2_THR_PER_SM;
-    const char *e = getenv("LC_DECODER_BUILD"); // debug switch: "lat" / "thr"
-    if (e && e[0] == 'l') return lat;
-    if (e && e[0] == 't') return thr;
+    if (flags & LC_FLAG_DEC_LATENCY_BUILD) return lat;
+    if (flags & LC_FLAG_DEC_THROUGHPUT_BUILD) return thr;
     return (long long)B <= (long long)lc_num_sms() * lat ? lat : thr;
 }
-static int lc_v2_grid(const LcV2Cfg &vc, int B)
+static int lc_v2_grid(const LcV2Cfg &vc, int B, int flags)
 {
-    long long g = (long long)lc_num_sms() * lc_v2_per_sm(vc, B);
+    long long g = (long long)lc_num_sms() * lc_v2_per_sm(vc, B, flags);
     if (g > B) g = B;
     return g < 1 ? 1 : (int)g;
 }
@@ -599,18 +741,19 @@ static int64_t lc_v2_scratch_need(const LcCoderCfg &cfg, int B)
 {
     LcV2Cfg vc;
     lcv_cfg_make(cfg, &vc);
-    return (int64_t)lc_v2_grid(vc, B) * (int64_t)vc.g_stride + (int64_t)lcv_tables_bytes(cfg.n) + 512 +
-           (int64_t)cfg.n * cfg.n * 64;
+    // sized for the larger of the two grids, so the scratch size does not depend on the flags
+    return (int64_t)lc_v2_grid(vc, B, LC_FLAG_DEC_THROUGHPUT_BUILD) * (int64_t)vc.g_stride + (int64_t)lcv_tables_bytes(cfg.n) +
+           512 + (int64_t)cfg.n * cfg.n * 64;
 }
 
 static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
 {
     int64_t need = (int64_t)lc_grid_for(cfg, B) * (int64_t)cfg.scratch_stride;
-    if (lc_use_decoder_v2(cfg)) {
+    if (lcv_eligible(cfg)) {
         const int64_t v2 = lc_v2_scratch_need(cfg, B);
         if (v2 > need) need = v2;
     }
-    if (lc_use_parallel_encoder(cfg)) {
+    if (lc_use_parallel_encoder(cfg, 0)) {
         const int64_t par = (int64_t)(B < LC_PAR_TILE ? B : LC_PAR_TILE) * LC_PAR_STREAM_BYTES + 512 +
                             (int64_t)lcv_tables_bytes(cfg.n) +
                             (cfg.n <= LCS_T2_MAX_N ? (int64_t)cfg.n * cfg.n * 64 : 0);
@@ -621,7 +764,7 @@ static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
 
 static int lc_ew_grid(long long n_elem)
 {
-    long long blocks = (n_elem / 4 + 255) / 256;
+    long long blocks = (n_elem / 4 + 256 * LC_EW_UNROLL - 1) / (256 * LC_EW_UNROLL);
     const long long cap = (long long)lc_num_sms() * 8; // 2048 threads per SM
     if (blocks > cap) blocks = cap;
     return blocks < 1 ? 1 : (int)blocks;
@@ -631,49 +774,105 @@ extern "C" {
 
 int lc_version(void) { return LC_ABI_VERSION; }
 
-int lc_quantize_affine(const float *w, int64_t n_elem, int bits, int32_t *idx_out, float *wq_out, void *stream)
+int64_t lc_debug_launch_count(int reset)
+{
+    const long long v = t_launches;
+    if (reset) t_launches = 0;
+    return (int64_t)v;
+}
+
+int lc_quantize_affine_t(const float *w, int64_t n_elem, int bits, void *idx_out, int idx_bytes, float *wq_out, void *stream)
 {
     if (n_elem < 0 || bits < 1 || bits > 24 || !w) return -22;
+    if (idx_out && !lc_idx_bytes_ok(idx_bytes, 1 << bits)) return -22;
     if (n_elem == 0 || (!idx_out && !wq_out)) return 0;
     if ((((uintptr_t)w | (uintptr_t)idx_out | (uintptr_t)wq_out) & 15) != 0) return -22;
-    lc_quant_affine_kernel<<<lc_ew_grid(n_elem), 256, 0, (cudaStream_t)stream>>>(w, n_elem, (float)((1 << bits) - 1),
-                                                                                 idx_out, wq_out);
-    LC_CUDA_RET();
+    const float scale = (float)((1 << bits) - 1);
+    const int hi = (1 << bits) - 1, grid = lc_ew_grid(n_elem);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!idx_out || idx_bytes == 4)
+        lc_quant_affine_kernel<int><<<grid, 256, 0, st>>>(w, n_elem, scale, hi, (int *)idx_out, wq_out);
+    else if (idx_bytes == 2)
+        lc_quant_affine_kernel<unsigned short><<<grid, 256, 0, st>>>(w, n_elem, scale, hi, (unsigned short *)idx_out, wq_out);
+    else
+        lc_quant_affine_kernel<unsigned char><<<grid, 256, 0, st>>>(w, n_elem, scale, hi, (unsigned char *)idx_out, wq_out);
+    LC_LAUNCHED();
+    return 0;
+}
+
+int lc_quantize_affine(const float *w, int64_t n_elem, int bits, int32_t *idx_out, float *wq_out, void *stream)
+{
+    return lc_quantize_affine_t(w, n_elem, bits, idx_out, 4, wq_out, stream);
+}
+
+int lc_dequantize_affine_t(const void *idx, int idx_bytes, int64_t n_elem, int bits, float *w_out, void *stream)
+{
+    if (n_elem < 0 || bits < 1 || bits > 24 || !idx || !w_out) return -22;
+    if (idx_bytes != 1 && idx_bytes != 2 && idx_bytes != 4) return -22;
+    if (n_elem == 0) return 0;
+    if ((((uintptr_t)idx | (uintptr_t)w_out) & 15) != 0) return -22;
+    const float scale = (float)((1 << bits) - 1);
+    const int grid = lc_ew_grid(n_elem);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (idx_bytes == 4) lc_dequant_affine_kernel<int><<<grid, 256, 0, st>>>((const int *)idx, n_elem, scale, w_out);
+    else if (idx_bytes == 2)
+        lc_dequant_affine_kernel<unsigned short><<<grid, 256, 0, st>>>((const unsigned short *)idx, n_elem, scale, w_out);
+    else lc_dequant_affine_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char *)idx, n_elem, scale, w_out);
+    LC_LAUNCHED();
     return 0;
 }
 
 int lc_dequantize_affine(const int32_t *idx, int64_t n_elem, int bits, float *w_out, void *stream)
 {
-    if (n_elem < 0 || bits < 1 || bits > 24 || !idx || !w_out) return -22;
+    return lc_dequantize_affine_t(idx, 4, n_elem, bits, w_out, stream);
+}
+
+int lc_quantize_codebook_t(const float *z, int64_t n_elem, const float *codebook, int n, int sorted_ascending,
+                           void *idx_out, int idx_bytes, float *deq_out, void *stream)
+{
+    if (n_elem < 0 || n < 1 || n > 4096 || !z || !codebook || !idx_out || !lc_idx_bytes_ok(idx_bytes, n)) return -22;
     if (n_elem == 0) return 0;
-    if ((((uintptr_t)idx | (uintptr_t)w_out) & 15) != 0) return -22;
-    lc_dequant_affine_kernel<<<lc_ew_grid(n_elem), 256, 0, (cudaStream_t)stream>>>(idx, n_elem, (float)((1 << bits) - 1),
-                                                                                   w_out);
-    LC_CUDA_RET();
+    if ((((uintptr_t)z | (uintptr_t)idx_out | (uintptr_t)deq_out) & 15) != 0) return -22;
+    const int grid = lc_ew_grid(n_elem), so = sorted_ascending ? 1 : 0;
+    const size_t sm = (size_t)n * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (idx_bytes == 4)
+        lc_quant_codebook_kernel<int><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, so, (int *)idx_out, deq_out);
+    else if (idx_bytes == 2)
+        lc_quant_codebook_kernel<unsigned short><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, so, (unsigned short *)idx_out, deq_out);
+    else
+        lc_quant_codebook_kernel<unsigned char><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, so, (unsigned char *)idx_out, deq_out);
+    LC_LAUNCHED();
     return 0;
 }
 
 int lc_quantize_codebook(const float *z, int64_t n_elem, const float *codebook, int n, int sorted_ascending,
                          int32_t *idx_out, float *deq_out, void *stream)
 {
-    if (n_elem < 0 || n < 1 || n > 4096 || !z || !codebook || !idx_out) return -22;
+    return lc_quantize_codebook_t(z, n_elem, codebook, n, sorted_ascending, idx_out, 4, deq_out, stream);
+}
+
+int lc_dequantize_codebook_t(const void *idx, int idx_bytes, int64_t n_elem, const float *codebook, int n, float *w_out,
+                             void *stream)
+{
+    if (n_elem < 0 || n < 1 || n > 4096 || !idx || !codebook || !w_out) return -22;
+    if (idx_bytes != 1 && idx_bytes != 2 && idx_bytes != 4) return -22;
     if (n_elem == 0) return 0;
-    if ((((uintptr_t)z | (uintptr_t)idx_out | (uintptr_t)deq_out) & 15) != 0) return -22;
-    lc_quant_codebook_kernel<<<lc_ew_grid(n_elem), 256, (size_t)n * 4, (cudaStream_t)stream>>>(
-        z, n_elem, codebook, n, sorted_ascending ? 1 : 0, idx_out, deq_out);
-    LC_CUDA_RET();
+    if ((((uintptr_t)idx | (uintptr_t)w_out) & 15) != 0) return -22;
+    const int grid = lc_ew_grid(n_elem);
+    const size_t sm = (size_t)n * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (idx_bytes == 4) lc_dequant_codebook_kernel<int><<<grid, 256, sm, st>>>((const int *)idx, n_elem, codebook, n, w_out);
+    else if (idx_bytes == 2)
+        lc_dequant_codebook_kernel<unsigned short><<<grid, 256, sm, st>>>((const unsigned short *)idx, n_elem, codebook, n, w_out);
+    else lc_dequant_codebook_kernel<unsigned char><<<grid, 256, sm, st>>>((const unsigned char *)idx, n_elem, codebook, n, w_out);
+    LC_LAUNCHED();
     return 0;
 }
 
 int lc_dequantize_codebook(const int32_t *idx, int64_t n_elem, const float *codebook, int n, float *w_out, void *stream)
 {
-    if (n_elem < 0 || n < 1 || n > 4096 || !idx || !codebook || !w_out) return -22;
-    if (n_elem == 0) return 0;
-    if ((((uintptr_t)idx | (uintptr_t)w_out) & 15) != 0) return -22;
-    lc_dequant_codebook_kernel<<<lc_ew_grid(n_elem), 256, (size_t)n * 4, (cudaStream_t)stream>>>(idx, n_elem, codebook, n,
-                                                                                                 w_out);
-    LC_CUDA_RET();
-    return 0;
+    return lc_dequantize_codebook_t(idx, 4, n_elem, codebook, n, w_out, stream);
 }
 
 int lc_coder_grid(int B, int imgs, int R, int C, int n_symbols, int has_ctx)
@@ -702,13 +901,14 @@ int64_t lc_encode_slot_bytes(int imgs, int R, int C, int n_symbols)
     return (bytes + 15) & ~(int64_t)15;
 }
 
-int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_symbols, double adaptation_rate, int mode,
-                    int has_ctx, void *scratch, int64_t scratch_bytes, uint8_t *slots, int64_t slot_bytes,
-                    uint8_t *out_bytes, int64_t out_capacity, int64_t *out_offsets, int32_t *out_nbits, int32_t *status,
-                    int32_t *fault_index, void *stream)
+int lc_encode_batch_t(const void *idx, int idx_bytes, int B, int imgs, int R, int C, int n_symbols, double adaptation_rate,
+                      int mode, int has_ctx, void *scratch, int64_t scratch_bytes, uint8_t *slots, int64_t slot_bytes,
+                      uint8_t *out_bytes, int64_t out_capacity, int64_t *out_offsets, int32_t *out_nbits, int32_t *status,
+                      int32_t *fault_index, int flags, void *stream)
 {
     LcCoderCfg cfg;
     if (B < 0 || !idx || !scratch || !slots || !out_nbits || !status || !fault_index) return -22;
+    if (idx_bytes != 1 && idx_bytes != 2 && idx_bytes != 4) return -22;
     if (B == 0) return 0;
     int rc = lc_make_cfg(cfg, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx);
     if (rc) return rc;
@@ -716,24 +916,15 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
     if (out_bytes && !out_offsets) return -22;
     if ((((uintptr_t)slots | (uintptr_t)out_bytes | (uintptr_t)scratch) & 15) != 0) return -22;
     if (scratch_bytes < lc_scratch_need(cfg, B)) return -12;
+    lc_prepare_device();
     cudaStream_t st = (cudaStream_t)stream;
-    if (lc_use_parallel_encoder(cfg)) {
+    const LcCodes all_codes(idx, idx_bytes);
+    if (lc_use_parallel_encoder(cfg, flags)) {
         const size_t sort_smem = sizeof(LcBlockSort::TempStorage);
-        const size_t a_smem = (size_t)8 * cfg.n * 8;
-        static bool attr_done = false;
-        static int phase_a_choice = 0; // 0 auto, 1 dense warp-per-group, 2 sparse lane-per-group (LC_PHASE_A=warp|lanes)
-        if (!attr_done) {
-            cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
-            cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
-            cudaFuncSetAttribute(lc_enc_phase_b2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            cudaFuncSetAttribute(lc_enc_phase_a_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 LCS_BLOCK_WARPS * 1024 * 8);
-            const char *e = getenv("LC_PHASE_A");
-            if (e && e[0] == 'w') phase_a_choice = 1;
-            if (e && e[0] == 'l') phase_a_choice = 2;
-            attr_done = true;
-        }
-        const bool sparse_variant = phase_a_choice != 1;
+        bool sparse_variant = true;
+#ifdef LC_DEBUG_VARIANTS
+        if (flags & LC_FLAG_DEBUG_ENC_DENSE_PHASE_A) sparse_variant = false;
+#endif
         const int tile = B < LC_PAR_TILE ? B : LC_PAR_TILE;
         // per-launch tables (u after the first update, exact cumsum rows of the model after one update)
         double *tables = (double *)((char *)scratch + (((size_t)tile * LC_PAR_STREAM_BYTES + 255) & ~(size_t)255));
@@ -742,12 +933,12 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
         char *t2 = (char *)0;
         if (sparse_variant) {
             lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
-            LC_CUDA_RET();
+            LC_LAUNCHED();
             if (cfg.n <= LCS_T2_MAX_N && (long long)B * 1000 >= (long long)cfg.n * cfg.n) {
                 t2 = (char *)tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255);
                 const size_t t2_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;
                 lc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, t2_smem, st>>>(cfg, tables, t2);
-                LC_CUDA_RET();
+                LC_LAUNCHED();
             }
         }
         for (int b0 = 0; b0 < B; b0 += LC_PAR_TILE) {
@@ -760,10 +951,10 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
             int *first_bad = (int *)ws;                       ws += (size_t)nb * 4;
             int *ngroups = (int *)ws;                         ws += (size_t)nb * 4;
             unsigned int *task_counter = (unsigned int *)ws;
-            const int *codes = idx + (size_t)b0 * cfg.total;
+            const LcCodes codes = all_codes + (size_t)b0 * cfg.total;
             lc_enc_sort_kernel<<<nb, LC_SORT_THREADS, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs,
                                                            sparse_variant ? tables : (const double *)0);
-            LC_CUDA_RET();
+            LC_LAUNCHED();
             if (sparse_variant) {
                 const size_t sp_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;
                 int blocks_per_sm = (int)((200u * 1024u) / (sp_smem + 1024u));
@@ -771,38 +962,138 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
                 cudaMemsetAsync(task_counter, 0, 4, st);
                 lc_enc_phase_a_sparse_kernel<<<lc_num_sms() * blocks_per_sm, 32 * LCS_BLOCK_WARPS, sp_smem, st>>>(
                     cfg, codes, nb, skeys, spos, first_bad, glist, ngroups, ivs, task_counter, tables, t2);
-            } else {
-                lc_enc_phase_a_kernel<<<nb, 256, a_smem, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
             }
-            LC_CUDA_RET();
+#ifdef LC_DEBUG_VARIANTS
+            else
+                lc_enc_phase_a_kernel<<<nb, 256, (size_t)8 * cfg.n * 8, st>>>(cfg, codes, nb, skeys, spos, first_bad, ivs);
+#endif
+            LC_LAUNCHED();
             const size_t b2_smem = (size_t)slot_bytes + 4 + 24 * 4;
             if (cfg.mode == LC_MODE_REPAIRED && b2_smem <= 96 * 1024) {
                 // B1: the serial recurrence (leaves its first finish bit in out_nbits); B2: parallel bit placement
                 lc_enc_phase_b1_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, ivs, out_nbits + b0);
-                LC_CUDA_RET();
+                LC_LAUNCHED();
                 lc_enc_phase_b2_kernel<<<nb, LC_B2_THREADS, b2_smem, st>>>(cfg, nb, first_bad, ivs,
                                                                            slots + (size_t)b0 * slot_bytes, (uint32_t)slot_bytes,
                                                                            out_nbits + b0, status + b0, fault_index + b0);
             } else {
+                // verbatim mode (the fault of defect D3 has to surface at its symbol) and slots beyond 96 KB
                 lc_enc_phase_b_kernel<<<nb, 32, 0, st>>>(cfg, nb, first_bad, ivs, slots + (size_t)b0 * slot_bytes,
                                                         (uint32_t)slot_bytes, out_nbits + b0, status + b0, fault_index + b0);
             }
-            LC_CUDA_RET();
+            LC_LAUNCHED();
         }
     } else {
         const int grid = lc_grid_for(cfg, B);
         if (cfg.sm_bytes > 48 * 1024)
             cudaFuncSetAttribute(lc_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
-        lc_encode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, idx, B, slots, (uint32_t)slot_bytes, out_nbits, status,
+        lc_encode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, all_codes, B, slots, (uint32_t)slot_bytes, out_nbits, status,
                                                          fault_index, (char *)scratch);
-        LC_CUDA_RET();
+        LC_LAUNCHED();
     }
     if (out_bytes) {
         lc_scan_sizes_kernel<<<1, 1024, 0, st>>>(out_nbits, status, B, out_capacity, (long long *)out_offsets);
-        LC_CUDA_RET();
+        LC_LAUNCHED();
         lc_compact_kernel<<<B, 128, 0, st>>>(slots, slot_bytes, out_nbits, status, (const long long *)out_offsets, out_bytes);
-        LC_CUDA_RET();
+        LC_LAUNCHED();
     }
+    return 0;
+}
+
+int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_symbols, double adaptation_rate, int mode,
+                    int has_ctx, void *scratch, int64_t scratch_bytes, uint8_t *slots, int64_t slot_bytes,
+                    uint8_t *out_bytes, int64_t out_capacity, int64_t *out_offsets, int32_t *out_nbits, int32_t *status,
+                    int32_t *fault_index, void *stream)
+{
+    return lc_encode_batch_t(idx, 4, B, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx, scratch, scratch_bytes, slots,
+                             slot_bytes, out_bytes, out_capacity, out_offsets, out_nbits, status, fault_index, 0, stream);
+}
+
+int lc_decode_batch_t(const uint8_t *bytes, const int64_t *offsets, const int32_t *nbits, int B, int imgs, int R, int C,
+                      int n_symbols, double adaptation_rate, int mode, int has_ctx, void *scratch, int64_t scratch_bytes,
+                      void *idx_out, int idx_bytes, const float *deq_table, float *deq_out, int32_t *status,
+                      int32_t *fault_index, int flags, void *stream)
+{
+    LcCoderCfg cfg;
+    if (B < 0 || !bytes || !offsets || !nbits || !scratch || !status || !fault_index) return -22;
+    if (!idx_out && !deq_out) return -22;
+    if (B == 0) return 0;
+    if (deq_out && !deq_table) return -22;
+    int rc = lc_make_cfg(cfg, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx);
+    if (rc) return rc;
+    if (idx_out && !lc_idx_bytes_ok(idx_bytes, cfg.n)) return -22;
+    if ((((uintptr_t)bytes) & 3) != 0 || (((uintptr_t)scratch) & 15) != 0) return -22;
+    const int grid = lc_grid_for(cfg, B);
+    if (scratch_bytes < lc_scratch_need(cfg, B)) return -12;
+    lc_prepare_device();
+    cudaStream_t st = (cudaStream_t)stream;
+    const LcIdxOut out(idx_out, idx_out ? idx_bytes : 0);
+    if (cfg.sm_bytes > 48 * 1024)
+        cudaFuncSetAttribute(lc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+    if (lc_use_decoder_v2(cfg, flags)) {
+        // decoder/updater warps; streams with a context of more than 32 distinct symbols are flagged
+        // and redone from scratch by the generic kernel
+        LcV2Cfg vc;
+        lcv_cfg_make(cfg, &vc);
+        const int g2 = lc_v2_grid(vc, B, flags);
+        const int gmax = lc_v2_grid(vc, B, LC_FLAG_DEC_THROUGHPUT_BUILD);
+        double *tables = (double *)((char *)scratch + (((size_t)gmax * vc.g_stride + 255) & ~(size_t)255));
+        if (vc.sm_bytes > 64 * 1024) return -22;
+        lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
+        LC_LAUNCHED();
+        // records of the models after two visits: the updater's job for a second visit becomes a copy
+        char *t2 = (char *)0;
+        // (measured neutral on the decode time -- the updater is not the bottleneck -- so only where the table's
+        // n^2 updates are small against the batch: >= 4096 streams at n = 256)
+        bool v3 = false;
+#ifdef LC_DEBUG_VARIANTS
+        v3 = (flags & LC_FLAG_DEBUG_DEC_V3) && cfg.total <= (1 << 21);
+#endif
+        if (!v3 && (long long)B * 16 >= (long long)cfg.n * cfg.n) {
+            t2 = (char *)tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255);
+            lc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, (size_t)LCS_BLOCK_WARPS * cfg.n * 8, st>>>(cfg, tables, t2);
+            LC_LAUNCHED();
+        }
+        if (v3) {
+#ifdef LC_DEBUG_VARIANTS
+            if (idx_bytes != 4 || !idx_out) return -22;
+            lc_decode_v3_kernel<<<g2, 32 * LC3_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
+                                                                         B, (int *)idx_out, deq_table, deq_out, status,
+                                                                         fault_index, (char *)scratch, tables);
+#endif
+        } else {
+            const bool w8 = cfg.n == 256 && cfg.C == 512 && cfg.R == 16 && cfg.imgs == 1 && !(flags & LC_FLAG_DEC_GENERIC_SHAPE);
+            const bool thr = lc_v2_per_sm(vc, B, flags) > LC_V2_LAT_PER_SM;
+            auto kern = thr ? (w8 ? lc_decode_v2_w8_thr_kernel : lc_decode_v2_thr_kernel)
+                            : (w8 ? lc_decode_v2_w8_kernel : lc_decode_v2_kernel);
+            kern<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits, B, out,
+                                                          deq_table, deq_out, status, fault_index, (char *)scratch, tables,
+                                                          t2);
+        }
+        LC_LAUNCHED();
+        lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, out,
+                                                         deq_table, deq_out, status, fault_index, (char *)scratch,
+                                                         LC_NEEDS_GENERIC);
+        LC_LAUNCHED();
+        return 0;
+    }
+    if (cfg.mode == LC_MODE_REPAIRED && cfg.has_ctx && !(flags & LC_FLAG_DEC_SERIAL)) {
+        // register-model kernel; streams it cannot finish (a context with more than 32 distinct symbols) are
+        // flagged and redone from scratch by the generic kernel
+        if (cfg.sm_bytes > 48 * 1024)
+            cudaFuncSetAttribute(lc_fast_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+        lc_fast_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, out,
+                                                              deq_table, deq_out, status, fault_index, (char *)scratch);
+        LC_LAUNCHED();
+        lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, out,
+                                                         deq_table, deq_out, status, fault_index, (char *)scratch,
+                                                         LC_NEEDS_GENERIC);
+        LC_LAUNCHED();
+        return 0;
+    }
+    lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, out, deq_table,
+                                                     deq_out, status, fault_index, (char *)scratch, 0);
+    LC_LAUNCHED();
     return 0;
 }
 
@@ -811,84 +1102,9 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
                     int32_t *idx_out, const float *deq_table, float *deq_out, int32_t *status, int32_t *fault_index,
                     void *stream)
 {
-    LcCoderCfg cfg;
-    if (B < 0 || !bytes || !offsets || !nbits || !scratch || !idx_out || !status || !fault_index) return -22;
-    if (B == 0) return 0;
-    if (deq_out && !deq_table) return -22;
-    int rc = lc_make_cfg(cfg, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx);
-    if (rc) return rc;
-    if ((((uintptr_t)bytes) & 3) != 0 || (((uintptr_t)scratch) & 15) != 0) return -22;
-    const int grid = lc_grid_for(cfg, B);
-    if (scratch_bytes < lc_scratch_need(cfg, B)) return -12;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (cfg.sm_bytes > 48 * 1024)
-        cudaFuncSetAttribute(lc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
-    if (lc_use_decoder_v2(cfg)) {
-        // decoder/updater warps; streams with a context of more than 32 distinct symbols are flagged
-        // and redone from scratch by the generic kernel
-        LcV2Cfg vc;
-        lcv_cfg_make(cfg, &vc);
-        const int g2 = lc_v2_grid(vc, B);
-        double *tables = (double *)((char *)scratch + (((size_t)g2 * vc.g_stride + 255) & ~(size_t)255));
-        static bool v2_attr = false;
-        if (!v2_attr) {
-            cudaFuncSetAttribute(lc_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(lc_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(lc_decode_v2_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(lc_decode_v2_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(lc_decode_v2_w8_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            v2_attr = true;
-        }
-        if (vc.sm_bytes > 64 * 1024) return -22;
-        lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
-        LC_CUDA_RET();
-        // records of the models after two visits: the updater's job for a second visit becomes a copy
-        char *t2 = (char *)0;
-        // (measured neutral on the decode time -- the updater is not the bottleneck -- so only where the table's
-        // n^2 updates are small against the batch: >= 4096 streams at n = 256)
-        if (lc_decoder_choice() == 2 && (long long)B * 16 >= (long long)cfg.n * cfg.n) {
-            t2 = (char *)tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255);
-            lc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, (size_t)LCS_BLOCK_WARPS * cfg.n * 8, st>>>(cfg, tables, t2);
-            LC_CUDA_RET();
-        }
-        if (lc_decoder_choice() == 3 && cfg.total <= (1 << 21))
-            lc_decode_v3_kernel<<<g2, 32 * LC3_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits,
-                                                                         B, idx_out, deq_table, deq_out, status,
-                                                                         fault_index, (char *)scratch, tables);
-        else {
-            const bool w8 = cfg.n == 256 && cfg.C == 512 && cfg.R == 16 && cfg.imgs == 1 && !getenv("LC_DECODER_GENERIC");
-            const bool thr = lc_v2_per_sm(vc, B) > LC_V2_LAT_PER_SM;
-            auto kern = thr ? (w8 ? lc_decode_v2_w8_thr_kernel : lc_decode_v2_thr_kernel)
-                            : (w8 ? lc_decode_v2_w8_kernel : lc_decode_v2_kernel);
-            kern<<<g2, 32 * LCV_WARPS, vc.sm_bytes, st>>>(cfg, vc, bytes, (const long long *)offsets, nbits, B, idx_out,
-                                                          deq_table, deq_out, status, fault_index, (char *)scratch, tables,
-                                                          t2);
-        }
-        LC_CUDA_RET();
-        lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
-                                                         deq_table, deq_out, status, fault_index, (char *)scratch,
-                                                         LC_NEEDS_GENERIC);
-        LC_CUDA_RET();
-        return 0;
-    }
-    if (cfg.mode == LC_MODE_REPAIRED && cfg.has_ctx) {
-        // fast kernel; streams it cannot finish (a context with more than 32 distinct symbols) are
-        // flagged and redone from scratch by the generic kernel
-        if (cfg.sm_bytes > 48 * 1024)
-            cudaFuncSetAttribute(lc_fast_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
-        lc_fast_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
-                                                              deq_table, deq_out, status, fault_index, (char *)scratch);
-        LC_CUDA_RET();
-        lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out,
-                                                         deq_table, deq_out, status, fault_index, (char *)scratch,
-                                                         LC_NEEDS_GENERIC);
-        LC_CUDA_RET();
-        return 0;
-    }
-    lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, (const long long *)offsets, nbits, B, idx_out, deq_table,
-                                                     deq_out, status, fault_index, (char *)scratch, 0);
-    LC_CUDA_RET();
-    return 0;
+    if (!idx_out) return -22;
+    return lc_decode_batch_t(bytes, offsets, nbits, B, imgs, R, C, n_symbols, adaptation_rate, mode, has_ctx, scratch,
+                             scratch_bytes, idx_out, 4, deq_table, deq_out, status, fault_index, 0, stream);
 }
 
 #ifdef LC_DEC_PROFILE
@@ -901,6 +1117,18 @@ int lc_debug_profile(unsigned long long *out64)
     return 0;
 }
 #endif
+
+int lc_model_update(double *vec, int n_symbols, int symbol, double adaptation_rate, void *stream)
+{
+    LcCoderCfg cfg;
+    if (!vec || (((uintptr_t)vec) & 7) != 0) return -22;
+    int rc = lc_make_cfg(cfg, 1, 1, 1, n_symbols, adaptation_rate, LC_MODE_REPAIRED, 0);
+    if (rc) return rc;
+    if (symbol < -n_symbols || symbol >= n_symbols) return -22;
+    lc_model_update_kernel<<<1, 32, (size_t)cfg.n * 8, (cudaStream_t)stream>>>(cfg, vec, symbol);
+    LC_LAUNCHED();
+    return 0;
+}
 
 static int lc_stateful_check(LcCoderCfg &cfg, LcStatefulTable &T, int imgs, int R, int C, int n, double rate, int mode,
                              int has_ctx, void *table, int64_t table_bytes)
@@ -944,7 +1172,7 @@ int lc_stateful_encode(const int32_t *idx, int imgs, int R, int C, int n_symbols
     const size_t smem = (size_t)cfg.n * 8;
     lc_stateful_encode_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(cfg, idx, T, slot, (uint32_t)slot_bytes, out_nbits,
                                                                     status, fault_index);
-    LC_CUDA_RET();
+    LC_LAUNCHED();
     return 0;
 }
 
@@ -960,7 +1188,7 @@ int lc_stateful_decode(const uint8_t *bytes, int64_t nbytes, int imgs, int R, in
     const size_t smem = (size_t)cfg.n * 8;
     lc_stateful_decode_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(cfg, bytes, (long long)nbytes, T, idx_out, status,
                                                                     fault_index);
-    LC_CUDA_RET();
+    LC_LAUNCHED();
     return 0;
 }
 

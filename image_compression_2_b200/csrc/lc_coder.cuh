@@ -484,7 +484,7 @@ __device__ __forceinline__ int lc_br_bit(LcBitReader &b, int lane)
 // codes: int32[total]; out: this stream's output slot (word aligned), cap_words 32-bit words.
 // Returns nbits (valid when status == LC_OK); W.status / fault index report faults.
 // ================================================================================================
-__device__ __forceinline__ long long lc_encode_stream(LcWarp &W, const int *codes, uint32_t *out, uint32_t cap_words,
+__device__ __forceinline__ long long lc_encode_stream(LcWarp &W, LcCodes codes, uint32_t *out, uint32_t cap_words,
                                                       int *fault_index)
 {
     lc_stream_reset(W);
@@ -500,10 +500,10 @@ __device__ __forceinline__ long long lc_encode_stream(LcWarp &W, const int *code
             const int p = pos + W.lane;
             my_code = 0; my_key = 0;
             if (p < W.total) {
-                my_code = __ldg(codes + p);
+                my_code = codes[p];
                 const int q = p % RC, c = q % W.C, r = q / W.C;
-                const int left = c > 0 ? __ldg(codes + p - 1) : -1;
-                const int up = r > 0 ? __ldg(codes + p - W.C) : -1;
+                const int left = c > 0 ? codes[p - 1] : -1;
+                const int up = r > 0 ? codes[p - W.C] : -1;
                 my_key = lc_ctx_key(W, left, up);
             }
         }
@@ -567,7 +567,7 @@ __device__ __forceinline__ long long lc_encode_stream(LcWarp &W, const int *code
 // src/nbytes: MSB-first packed bits (:260-270).  out: int32[total] (zeros after a fault).
 // deq_table (may be NULL): codebook for the fused dequantiser, deq_out fp32[total].
 // ================================================================================================
-__device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char *src, long long nbytes, int *out,
+__device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char *src, long long nbytes, LcIdxOut out,
                                                  const float *deq_table, float *deq_out, int *fault_index)
 {
     lc_stream_reset(W);
@@ -629,7 +629,7 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
         if (W.has_ctx && W.lane == 0) W.rows[(r & 1) * W.C + c] = (unsigned short)s;
         if ((pos & 31) == 31) {
             const int p = pos - 31 + W.lane;
-            out[p] = my_out;
+            out.store(p, my_out);
             if (deq_out) deq_out[p] = __ldg(deq_table + my_out);
         }
         const LcListPos lp = lc_list_locate(W, s);
@@ -643,8 +643,8 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
     {
         const int done = pos; // symbols [0,done) are valid; full chunks were already written
         const int p = (done & ~31) + W.lane;
-        if (p < done) { out[p] = my_out; if (deq_out) deq_out[p] = __ldg(deq_table + my_out); }
-        for (int z = done + W.lane; z < W.total; z += 32) { out[z] = 0; if (deq_out) deq_out[z] = 0.0f; }
+        if (p < done) { out.store(p, my_out); if (deq_out) deq_out[p] = __ldg(deq_table + my_out); }
+        for (int z = done + W.lane; z < W.total; z += 32) { out.store(z, 0); if (deq_out) deq_out[z] = 0.0f; }
     }
 }
 
@@ -655,7 +655,7 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
 
 // codes: int32[B][total].  out_slots: B slots of slot_bytes (multiple of 4) receiving the packed
 // stream of each input; nbits/status/fault: per stream.
-__device__ __forceinline__ void lc_encode_block(const LcCoderCfg &cfg, const int *codes, int B, unsigned char *out_slots,
+__device__ __forceinline__ void lc_encode_block(const LcCoderCfg &cfg, LcCodes codes, int B, unsigned char *out_slots,
                                                 uint32_t slot_bytes, int *nbits, int *status, int *fault,
                                                 char *scratch, char *smem)
 {
@@ -673,7 +673,7 @@ __device__ __forceinline__ void lc_encode_block(const LcCoderCfg &cfg, const int
 // bytes + offsets[B] + nbits[B]: stream b starts at byte offsets[b] (a multiple of 4; the buffer is
 // readable up to the next multiple of 4 past each stream) and holds ceil(nbits[b]/8) bytes.
 __device__ __forceinline__ void lc_decode_block(const LcCoderCfg &cfg, const unsigned char *bytes, const long long *offsets,
-                                                const int *nbits, int B, int *out, const float *deq_table,
+                                                const int *nbits, int B, LcIdxOut out, const float *deq_table,
                                                 float *deq_out, int *status, int *fault, char *scratch, char *smem,
                                                 int only_flagged)
 {

@@ -77,6 +77,38 @@ static inline void lc_prefetch_l1(const void *) {}
 static __device__ __forceinline__ void lc_prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
+// Index arrays cross the C ABI as int32 (the reference's `.astype(np.int32)` codes, cabac_compression.py:471) or, to
+// cut HBM traffic, as uint16 / uint8 (`idx_bytes` = 4, 2, 1 in include/latentcodec.h).  The kernels read and write them
+// through these two views; the element size is warp-uniform, so the selects cost a predicated load or store.
+struct LcCodes { // read-only
+    const void *p;
+    int eb;
+    LC_HD LcCodes() : p(0), eb(4) {}
+    LC_HD LcCodes(const int *q) : p(q), eb(4) {}
+    LC_HD LcCodes(const void *q, int bytes) : p(q), eb(bytes) {}
+    LC_HD int operator[](size_t i) const
+    {
+        if (eb == 4) return ((const int *)p)[i];
+        if (eb == 1) return (int)((const unsigned char *)p)[i];
+        return (int)((const unsigned short *)p)[i];
+    }
+    LC_HD LcCodes operator+(size_t off) const { return LcCodes((const char *)p + off * (size_t)eb, eb); }
+};
+struct LcIdxOut { // write-only (narrow types store the value truncated: decoded symbols are below n <= 2^(8*eb))
+    void *p;
+    int eb;
+    LC_HD LcIdxOut() : p(0), eb(4) {}
+    LC_HD LcIdxOut(int *q) : p(q), eb(4) {}
+    LC_HD LcIdxOut(void *q, int bytes) : p(q), eb(bytes) {}
+    LC_HD void store(size_t i, int v) const
+    {
+        if (eb == 4) ((int *)p)[i] = v;
+        else if (eb == 1) ((unsigned char *)p)[i] = (unsigned char)v;
+        else if (eb == 2) ((unsigned short *)p)[i] = (unsigned short)v; // eb == 0: the caller wants no index output
+    }
+    LC_HD LcIdxOut operator+(size_t off) const { return LcIdxOut((char *)p + off * (size_t)eb, eb); }
+};
+
 // Launch-time description of one coder launch.  All streams in a launch share it.
 struct LcCoderCfg {
     int n;       // alphabet size, power of two in [2,1024]

@@ -500,7 +500,7 @@ __device__ __forceinline__ bool lcf_uniform_symbol(int n, uint32_t lg_n, uint32_
 }
 
 // =================================================================================================
-__device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned char *src, long long nbytes, int *out,
+__device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned char *src, long long nbytes, LcIdxOut out,
                                                       const float *deq_table, float *deq_out, int *status_out,
                                                       int *fault_index)
 {
@@ -612,7 +612,7 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
         if (F.lane == (pos & 31)) my_out = s;
         if ((pos & 31) == 31) {
             const int p = pos - 31 + F.lane;
-            out[p] = my_out;
+            out.store(p, my_out);
             if (deq_out) deq_out[p] = __ldg(deq_table + my_out);
         }
         LCP_MARK(5);
@@ -654,15 +654,15 @@ __device__ __forceinline__ void lc_fast_decode_stream(LcFast &F, const unsigned 
     {
         const int done = pos;
         const int p = (done & ~31) + F.lane;
-        if (p < done) { out[p] = my_out; if (deq_out) deq_out[p] = __ldg(deq_table + my_out); }
-        for (int z = done + F.lane; z < F.total; z += 32) { out[z] = 0; if (deq_out) deq_out[z] = 0.0f; }
+        if (p < done) { out.store(p, my_out); if (deq_out) deq_out[p] = __ldg(deq_table + my_out); }
+        for (int z = done + F.lane; z < F.total; z += 32) { out.store(z, 0); if (deq_out) deq_out[z] = 0.0f; }
     }
     (void)left;
 }
 
 // Block entry: one warp per block, persistent over streams.  smem: dense[n] | u1tab[max(16,n<8?n:..)] | rows
 __device__ __forceinline__ void lc_fast_decode_block(const LcCoderCfg &cfg, const unsigned char *bytes,
-                                                     const long long *offsets, const int *nbits, int B, int *out,
+                                                     const long long *offsets, const int *nbits, int B, LcIdxOut out,
                                                      const float *deq_table, float *deq_out, int *status, int *fault,
                                                      char *scratch, char *smem)
 {

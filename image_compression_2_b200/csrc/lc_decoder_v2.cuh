@@ -754,19 +754,19 @@ __device__ __forceinline__ void lcv_prefetch_staged(const LcV2 &V, int lane, int
 }
 
 // write decoded symbols [first, first+count) of the row held in shared memory (and their dequantised values)
-__device__ __forceinline__ void lcv_flush_row(const unsigned char *row, int first_col, int count, int *out,
+__device__ __forceinline__ void lcv_flush_row(const unsigned char *row, int first_col, int count, LcIdxOut out,
                                               const float *deq_table, float *deq_out, int lane)
 {
     for (int i = lane; i < count; i += 32) {
         const int sy = (int)row[first_col + i];
-        out[i] = sy;
+        out.store(i, sy);
         if (deq_out) deq_out[i] = __ldg(deq_table + sy);
     }
 }
 
 template <bool OUTLINE>
 __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvPost &P, const unsigned char *src,
-                                                  long long nbytes, int *out, const float *deq_table, float *deq_out,
+                                                  long long nbytes, LcIdxOut out, const float *deq_table, float *deq_out,
                                                   int *status_out, int *fault_index)
 {
     const int lane = F.lane, n = F.n, C = F.C;
@@ -890,7 +890,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
         const int part = (c < C) ? c : 0;
         if (part > 0) lcv_flush_row(V.rows + (row_cur - V.sa_rows), 0, part, out + (done - part), deq_table,
                                     deq_out ? deq_out + (done - part) : (float *)0, lane);
-        for (int z = done + lane; z < F.total; z += 32) { out[z] = 0; if (deq_out) deq_out[z] = 0.0f; }
+        for (int z = done + lane; z < F.total; z += 32) { out.store(z, 0); if (deq_out) deq_out[z] = 0.0f; }
     }
 }
 
@@ -898,7 +898,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
 // compile time (one image per stream): keys, shifts, margins and loop bounds become immediates on the serial chain.
 template <int FN, int FC, int FR, bool OUTLINE = false>
 __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const LcV2Cfg &vc, const unsigned char *bytes,
-                                                 const long long *offsets, const int *nbits, int B, int *out,
+                                                 const long long *offsets, const int *nbits, int B, LcIdxOut out,
                                                  const float *deq_table, float *deq_out, int *status, int *fault,
                                                  char *scratch, const double *tables, const char *t2, char *smem)
 {

@@ -34,9 +34,12 @@ __device__ __forceinline__ double lc_dense_prefix(const double *dense, int s)
     return T;
 }
 
-// ContextModel.update_model (:119-144) on the dense image held in shared memory
-__device__ __forceinline__ void lc_dense_update(LcWarp &W, int s)
+// ContextModel.update_model (:119-144) on the dense image held in shared memory.  A negative symbol is NumPy's
+// negative index (the reference gets there after decoding symbol -1, :288-292,403): element n+s takes the increment
+// and, because `i != symbol` is then true for every i, the scale factor is applied to ALL elements.
+__device__ __forceinline__ void lc_dense_update(LcWarp &W, int s_signed)
 {
+    const int s = s_signed < 0 ? s_signed + W.n : s_signed;
     const double p_old = W.dense[s];
     const double p_new = LC_DADD(p_old, LC_DMUL(W.rate, LC_DSUB(1.0, p_old)));
     __syncwarp();
@@ -47,13 +50,13 @@ __device__ __forceinline__ void lc_dense_update(LcWarp &W, int s)
     const double others = LC_DSUB(total, p_new);
     const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, p_new), others) : 0.0;
     for (int i = W.lane; i < W.n; i += 32)
-        if (i != s) W.dense[i] = LC_DMUL(W.dense[i], f);
+        if (i != s_signed) W.dense[i] = LC_DMUL(W.dense[i], f);
     __syncwarp();
 }
 
 // Phase A for one warp.  skeys/spos: this stream's positions sorted by (key, position); entries at
 // index >= total are padding.  iv: float64 [2*total], iv[2p] = cum[s_p], iv[2p+1] = cum[s_p+1].
-__device__ __forceinline__ void lc_enc_phase_a_warp(LcWarp &W, const int *__restrict__ codes,
+__device__ __forceinline__ void lc_enc_phase_a_warp(LcWarp &W, LcCodes codes,
                                                     const uint32_t *__restrict__ skeys,
                                                     const unsigned short *__restrict__ spos, double *iv,
                                                     int total, int warp_id, int n_warps)
@@ -262,7 +265,7 @@ __device__ __forceinline__ long long lc_enc_phase_b_repaired(int lane, const dou
 // the first out-of-range symbol found by phase S: only the positions before it are sorted (the
 // rest carry padding keys) and coded, then phase B reports LC_BAD_SYMBOL there -- exactly where
 // the serial encoder stops.
-__device__ __forceinline__ void lc_enc_phase_a_block(const LcCoderCfg &cfg, const int *codes, int B,
+__device__ __forceinline__ void lc_enc_phase_a_block(const LcCoderCfg &cfg, LcCodes codes, int B,
                                                      const uint32_t *skeys, const unsigned short *spos,
                                                      const int *first_bad, double *ivs, char *smem)
 {

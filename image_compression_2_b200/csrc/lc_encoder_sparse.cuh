@@ -28,7 +28,7 @@
 // visit of the g-th context visited at least three times; first visits get i/n, second visits the table row of
 // their first symbol.  (On the GPU phase S -- lc_enc_sort_kernel -- produces the same from the sorted keys it holds
 // in registers; this warp version feeds the CPU emulator.)
-__device__ __forceinline__ int lc_enc_group_list3_warp(int lane, const int *codes, const uint32_t *skeys,
+__device__ __forceinline__ int lc_enc_group_list3_warp(int lane, LcCodes codes, const uint32_t *skeys,
                                                        const unsigned short *spos, int total, int n, double u0,
                                                        const double *cum1, double *ivs, unsigned short *glist)
 {
@@ -62,7 +62,7 @@ __device__ __forceinline__ int lc_enc_group_list3_warp(int lane, const int *code
 
 // Persistent warps pull tasks (stream, chunk of LCS_TASK_GROUPS contexts) from *task_counter.
 // smem: one dense image (n doubles) per warp.  tables: u1tab[32] | ru1tab[32] | cum1[n][n+1].
-__device__ __forceinline__ void lc_enc_phase_a_sparse_block(const LcCoderCfg &cfg, const int *codes_all, int B,
+__device__ __forceinline__ void lc_enc_phase_a_sparse_block(const LcCoderCfg &cfg, LcCodes codes_all, int B,
                                                             const uint32_t *skeys_all, const unsigned short *spos_all,
                                                             const int *first_bad, const unsigned short *glist_all,
                                                             const int *ngroups_all, double *ivs_all,
@@ -97,7 +97,7 @@ __device__ __forceinline__ void lc_enc_phase_a_sparse_block(const LcCoderCfg &cf
         if (g_lo >= ngroups) continue;
         const int g_hi = (g_lo + LCS_TASK_GROUPS < ngroups) ? g_lo + LCS_TASK_GROUPS : ngroups;
         const size_t o = (size_t)sidx * LC_PAR_MAX_SYMBOLS;
-        const int *codes = codes_all + (size_t)sidx * cfg.total;
+        const LcCodes codes = codes_all + (size_t)sidx * cfg.total;
         const uint32_t *skeys = skeys_all + o;
         const unsigned short *spos = spos_all + o;
         const unsigned short *glist = glist_all + (size_t)sidx * LC_PAR_MAX_GROUPS;

@@ -14,7 +14,7 @@ from . import codec
 
 class LatentPipeline:
     def __init__(self, n_symbols=256, R=16, C=512, quantizer="codebook", mode="repaired", adaptation_rate=0.05,
-                 device=None):
+                 device=None, idx_dtype=None):
         if not torch.cuda.is_available():
             raise RuntimeError("LatentPipeline needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -24,6 +24,9 @@ class LatentPipeline:
         self.quantizer = quantizer
         self.mode = mode
         self.rate = float(adaptation_rate)
+        # indices travel between the kernels as uint8 (up to 256 symbols) or int16: 1-2 bytes of HBM traffic per
+        # symbol instead of the int32 the reference's host code uses (idx_dtype=torch.int32 restores that)
+        self.idx_dtype = codec.idx_dtype_for(self.n) if idx_dtype is None else idx_dtype
         # table from the host's torch.linspace, as the reference builds it
         # (gumbel_softmax_compression.py:49-52); for quantiser A the dequantisation table is the
         # affine grid idx/(2^bits-1)*2-1 produced by the dequantise-A kernel itself
@@ -42,23 +45,26 @@ class LatentPipeline:
     # ---- stages -------------------------------------------------------------------------------
     def quantize(self, latents):
         if self.quantizer == "codebook":
-            idx, _ = codec.quantize_codebook(latents, self.codebook, sorted_ascending=True)
+            idx, _ = codec.quantize_codebook(latents, self.codebook, sorted_ascending=True, idx_dtype=self.idx_dtype)
         else:
-            idx, _ = codec.quantize_affine(latents, self.bits, want_wq=False)
-            # quantiser A does not clamp (stylegan3_hvae_full.py:313-316); the coder alphabet does
-            idx = idx.clamp_(0, self.n - 1)
+            idx, _ = codec.quantize_affine(latents, self.bits, want_wq=False, idx_dtype=self.idx_dtype)
+            # quantiser A does not clamp (stylegan3_hvae_full.py:313-316); the coder alphabet does (the narrow
+            # index types are clamped by the kernel)
+            if self.idx_dtype == torch.int32:
+                idx = idx.clamp_(0, self.n - 1)
         return idx
 
-    def encode(self, idx, ws=None):
+    def encode(self, idx, ws=None, reuse_output=False):
         B = idx.shape[0]
         layout = codec.StreamLayout(B, 1, self.R, self.C, 1)
         return codec.encode_batch(idx.reshape(-1), layout, self.n, mode=self.mode, adaptation_rate=self.rate,
-                                  workspace=ws or self.ws)
+                                  workspace=ws or self.ws, reuse_output=reuse_output)
 
-    def decode(self, data, offsets, nbits, B, ws=None, deq_out=None):
+    def decode(self, data, offsets, nbits, B, ws=None, deq_out=None, want_idx=True, reuse_output=False, flags=0):
         layout = codec.StreamLayout(B, 1, self.R, self.C, 1)
         return codec.decode_batch(data, offsets, nbits, layout, self.n, mode=self.mode, adaptation_rate=self.rate,
-                                  codebook=self.deq_table, workspace=ws or self.ws, deq_out=deq_out)
+                                  codebook=self.deq_table, workspace=ws or self.ws, deq_out=deq_out, flags=flags,
+                                  idx_dtype=self.idx_dtype, want_idx=want_idx, reuse_output=reuse_output)
 
     # ---- whole path ---------------------------------------------------------------------------
     def roundtrip_device(self, latents):

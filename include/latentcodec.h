@@ -10,7 +10,12 @@
  * Conventions
  *  - every pointer is a DEVICE pointer unless the name says host; sizes are in elements unless
  *    they say bytes; `stream` is a cudaStream_t passed as void* (NULL = default stream);
- *  - all calls are asynchronous on `stream`, keep no global state and never synchronise;
+ *  - all calls are asynchronous on `stream`, launch on the CURRENT device (cudaSetDevice it to the device the
+ *    pointers live on) and never synchronise.  The library keeps no mutable state between calls: the only statics are
+ *    write-once caches of per-device facts (SM count, "opt-in shared-memory attributes set on this device") keyed by
+ *    cudaGetDevice() and updated with atomics, and a thread-local launch counter (lc_debug_launch_count).  It reads no
+ *    environment variable; behaviour switches are the `flags` argument of the _t entry points.  Any number of host
+ *    threads may call into it concurrently, on the same or on different devices, each with its own scratch;
  *  - return value: 0 on success, a negative errno-style value (-EINVAL = -22) for arguments the
  *    implementation does not support, or -1000 - cudaError for a CUDA launch error;
  *  - per-stream faults of the coder are reported in `status[b]` / `fault_index[b]` (LC_STATUS_*),
@@ -25,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LC_ABI_VERSION 1
+#define LC_ABI_VERSION 2 /* 2: typed index arrays (_t entry points), flags, lc_debug_launch_count */
 
 /* coder modes */
 #define LC_CODER_VERBATIM 0 /* /root/reference/cabac_compression.py as shipped (defect D3 kept)      */
@@ -41,7 +46,26 @@ extern "C" {
 #define LC_STATUS_BAD_SYMBOL 6       /* input index outside [0,n_symbols) (reference: IndexError :343)   */
 #define LC_STATUS_POOL_OVERFLOW 7    /* internal scratch exhausted (never expected)                      */
 
+/* `flags` of lc_encode_batch_t / lc_decode_batch_t: 0 = let the library choose.  The choices never change a result,
+ * only which kernel produces it (tests use them to drive every kernel over the same inputs). */
+#define LC_FLAG_DEC_LATENCY_BUILD 1     /* decoder v2: the 8-streams-per-SM build whatever the batch size            */
+#define LC_FLAG_DEC_THROUGHPUT_BUILD 2  /* decoder v2: the 10-streams-per-SM build                                    */
+#define LC_FLAG_DEC_GENERIC_SHAPE 4     /* decoder v2: not the kernel specialised for 8-bit [16,512] W+ latents       */
+#define LC_FLAG_DEC_REGISTER_MODEL 8    /* the register-model decoder (the n > 256 kernel) also for n <= 256         */
+#define LC_FLAG_DEC_SERIAL 16           /* the generic serial decoder only                                            */
+#define LC_FLAG_ENC_SERIAL 32           /* the serial warp-per-stream encoder instead of the phase-split one          */
+#define LC_FLAG_DEC_NO_SMALL 64         /* not the dense shared-memory decoder of alphabets up to 32 symbols          */
+#define LC_FLAG_DEBUG_DEC_V3 256        /* builds with -DLC_DEBUG_VARIANTS only: three-warp decoder                   */
+#define LC_FLAG_DEBUG_ENC_DENSE_PHASE_A 512 /* builds with -DLC_DEBUG_VARIANTS only: dense warp-per-context phase A   */
+
 int lc_version(void);
+
+/* kernels launched by the calling host thread since the last reset (diagnostic; bench.py's gpu_launches) */
+int64_t lc_debug_launch_count(int reset);
+
+/* Index arrays: the reference hands the coder `.astype(np.int32)` codes (cabac_compression.py:471), so every entry
+ * point exists in an int32 form.  The _t forms take `idx_bytes` = 4 (int32), 2 (uint16) or 1 (uint8; alphabets up to
+ * 256 symbols): 1 or 2 bytes of HBM traffic per symbol instead of 4. */
 
 /* ---- quantisers ------------------------------------------------------------------------------ */
 
@@ -49,9 +73,15 @@ int lc_version(void);
  * idx = round_half_even(((w+1)*0.5)*(2^bits-1)) (no clamp), wq = idx/(2^bits-1)*2-1, five separately
  * rounded fp32 operations.  idx_out and wq_out may each be NULL. */
 int lc_quantize_affine(const float *w, int64_t n_elem, int bits, int32_t *idx_out, float *wq_out, void *stream);
+/* ... with uint16 / uint8 indices.  The narrow forms hold what the coder consumes -- the index CLAMPED to the alphabet
+ * [0, 2^bits-1] (NaN -> 0) -- because the unclamped value of an out-of-range latent does not fit them; wq_out is
+ * computed from the unclamped index exactly as above.  idx_bytes = 4 is lc_quantize_affine. */
+int lc_quantize_affine_t(const float *w, int64_t n_elem, int bits, void *idx_out, int idx_bytes, float *wq_out,
+                         void *stream);
 
 /* Dequantiser A alone (same lines): w_out = idx/(2^bits-1)*2-1. */
 int lc_dequantize_affine(const int32_t *idx, int64_t n_elem, int bits, float *w_out, void *stream);
+int lc_dequantize_affine_t(const void *idx, int idx_bytes, int64_t n_elem, int bits, float *w_out, void *stream);
 
 /* Quantiser B: GumbelSoftmaxDiscretization.forward -> encoding_indices,
  * gumbel_softmax_compression.py:97,118: argmin_k |z - codebook[k]| in fp32, first minimum.
@@ -60,11 +90,15 @@ int lc_dequantize_affine(const int32_t *idx, int64_t n_elem, int bits, float *w_
  * receives codebook[idx] (cabac_compression.py:531). */
 int lc_quantize_codebook(const float *z, int64_t n_elem, const float *codebook, int n, int sorted_ascending,
                          int32_t *idx_out, float *deq_out, void *stream);
+int lc_quantize_codebook_t(const float *z, int64_t n_elem, const float *codebook, int n, int sorted_ascending,
+                           void *idx_out, int idx_bytes, float *deq_out, void *stream);
 
 /* Dequantiser B: codebook[idx], cabac_compression.py:531 / gumbel_softmax_compression.py:258.
  * Indices outside [0,n) produce NaN. */
 int lc_dequantize_codebook(const int32_t *idx, int64_t n_elem, const float *codebook, int n, float *w_out,
                            void *stream);
+int lc_dequantize_codebook_t(const void *idx, int idx_bytes, int64_t n_elem, const float *codebook, int n, float *w_out,
+                             void *stream);
 
 /* ---- entropy coder --------------------------------------------------------------------------- */
 
@@ -95,6 +129,11 @@ int lc_encode_batch(const int32_t *idx, int B, int imgs, int R, int C, int n_sym
                     int mode, int has_ctx, void *scratch, int64_t scratch_bytes, uint8_t *slots, int64_t slot_bytes,
                     uint8_t *out_bytes, int64_t out_capacity, int64_t *out_offsets, int32_t *out_nbits,
                     int32_t *status, int32_t *fault_index, void *stream);
+/* the same with idx of idx_bytes-byte elements and `flags` (LC_FLAG_ENC_*) */
+int lc_encode_batch_t(const void *idx, int idx_bytes, int B, int imgs, int R, int C, int n_symbols,
+                      double adaptation_rate, int mode, int has_ctx, void *scratch, int64_t scratch_bytes, uint8_t *slots,
+                      int64_t slot_bytes, uint8_t *out_bytes, int64_t out_capacity, int64_t *out_offsets,
+                      int32_t *out_nbits, int32_t *status, int32_t *fault_index, int flags, void *stream);
 
 /* cabac_decode, cabac_compression.py:363-406 (+ ArithmeticCoder :247-311).
  *   bytes, offsets[B], nbits[B]: stream b = ceil(nbits[b]/8) bytes at bytes + offsets[b];
@@ -105,6 +144,12 @@ int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t 
                     int n_symbols, double adaptation_rate, int mode, int has_ctx, void *scratch,
                     int64_t scratch_bytes, int32_t *idx_out, const float *deq_table, float *deq_out, int32_t *status,
                     int32_t *fault_index, void *stream);
+/* the same with idx_out of idx_bytes-byte elements -- or NULL when only the dequantised values are wanted (then
+ * deq_out is required) -- and `flags` (LC_FLAG_DEC_*) */
+int lc_decode_batch_t(const uint8_t *bytes, const int64_t *offsets, const int32_t *nbits, int B, int imgs, int R, int C,
+                      int n_symbols, double adaptation_rate, int mode, int has_ctx, void *scratch,
+                      int64_t scratch_bytes, void *idx_out, int idx_bytes, const float *deq_table, float *deq_out,
+                      int32_t *status, int32_t *fault_index, int flags, void *stream);
 
 /* ---- stateful coder: the reference's shared ContextModel (cabac_compression.py:438,478,517) --------------------- */
 
@@ -129,6 +174,13 @@ int lc_stateful_encode(const int32_t *idx, int imgs, int R, int C, int n_symbols
 int lc_stateful_decode(const uint8_t *bytes, int64_t nbytes, int imgs, int R, int C, int n_symbols,
                        double adaptation_rate, int mode, int has_ctx, void *table, int64_t table_bytes, int32_t *idx_out,
                        int32_t *status, int32_t *fault_index, void *stream);
+
+/* ContextModel.update_model (cabac_compression.py:119-144) on ONE probability vector: vec[n_symbols] float64 in device
+ * memory is replaced by the vector after observing `symbol` -- p[s] += rate*(1-p[s]), the others scaled by
+ * (1-p[s]) / (pairwise-sum(p) - p[s]).  A negative symbol (>= -n_symbols) follows NumPy's negative indexing as the
+ * reference does after decoding symbol -1 (:288-292,403): element n+symbol gets the increment and EVERY element is
+ * scaled (`i != symbol` never excludes it).  n_symbols: power of two in [2,1024]. */
+int lc_model_update(double *vec, int n_symbols, int symbol, double adaptation_rate, void *stream);
 
 /* number of thread blocks (= resident streams) the coder kernels launch for B streams */
 int lc_coder_grid(int B, int imgs, int R, int C, int n_symbols, int has_ctx);

@@ -284,11 +284,12 @@ def test_cfg4_large_batch_roundtrip():
 @pytest.mark.parametrize("build", ["lat", "thr"])
 def test_decoder_v2_and_sparse_encoder_special_paths(build, monkeypatch):
     """(build: the decoder kernel's two register budgets -- 8 or 10 resident streams per SM; the host picks by batch
-    size, LC_DECODER_BUILD forces one.)  The paths the synthetic latents rarely reach: contexts with 7..32 distinct symbols (pool records) and more
+    size, codec.DEFAULT_DECODE_FLAGS forces one.)  The paths the synthetic latents rarely reach: contexts with 7..32 distinct symbols (pool records) and more
     than 32 (decoder: stream redone by the generic kernel; encoder phase A: dense continuation), small alphabets,
     short rows, several images sharing a model -- bitstreams and decoded symbols equal the oracle's."""
     from image_compression_2_b200 import coder
-    monkeypatch.setenv("LC_DECODER_BUILD", build)
+    from image_compression_2_b200 import codec as _codec
+    monkeypatch.setattr(_codec, "DEFAULT_DECODE_FLAGS", {"lat": 1, "thr": 2}[build])  # LC_FLAG_DEC_*_BUILD
     rng = np.random.default_rng(31)
     cases = []
     wide = np.zeros((3, 4, 400), np.int32)

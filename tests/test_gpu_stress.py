@@ -20,7 +20,8 @@ def _load_tool():
 
 @pytest.mark.parametrize("build", ["lat", "thr"])
 def test_random_cases_match_the_oracle(build, monkeypatch):
-    monkeypatch.setenv("LC_DECODER_BUILD", build)
+    from image_compression_2_b200 import codec as _codec
+    monkeypatch.setattr(_codec, "DEFAULT_DECODE_FLAGS", {"lat": 1, "thr": 2}[build])  # LC_FLAG_DEC_*_BUILD
     tool = _load_tool()
     rng = np.random.default_rng(20261018 if build == "lat" else 20261019)
     fails, symbols = [], 0

@@ -25,7 +25,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(_native.SIGNATURES) == declared
-    assert lib.lc_version() == 1
+    assert lib.lc_version() == _native.ABI_VERSION
 
 
 def test_sizing_helpers_without_gpu():
