@@ -15,6 +15,7 @@
 #include "lc_encoder_par.cuh"
 #include "lc_decoder_fast.cuh"
 #include "lc_decoder_v2.cuh"
+#include "lc_decoder_small.cuh"
 #ifdef LC_DEBUG_VARIANTS
 #include "lc_decoder_v3.cuh"
 #endif
@@ -86,17 +87,17 @@ __device__ __forceinline__ int lc_qa_int(float q)
 }
 
 // four indices -> one vector store.  int32 keeps the unclamped value (the reference's quantiser A does not clamp);
-// the narrow types hold what the coder consumes: the index clamped to the alphabet [0, hi].
+// the narrow types hold what the coder consumes: the index clamped to the alphabet [0, hi] (NaN -> 0).
 template <typename T> struct LcIdx4;
 template <> struct LcIdx4<int> {
     typedef int4 V;
-    static __device__ __forceinline__ int fix(int v, int) { return v; }
+    static __device__ __forceinline__ int fix(float q, int) { return lc_qa_int(q); }
     static __device__ __forceinline__ V pack(int a, int b, int c, int d) { return make_int4(a, b, c, d); }
     static __device__ __forceinline__ int4 unpack(V v) { return v; }
 };
 template <> struct LcIdx4<unsigned short> {
     typedef ushort4 V;
-    static __device__ __forceinline__ int fix(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+    static __device__ __forceinline__ int fix(float q, int hi) { return (int)fminf(fmaxf(q, 0.0f), (float)hi); } // NaN -> 0
     static __device__ __forceinline__ V pack(int a, int b, int c, int d)
     {
         return make_ushort4((unsigned short)a, (unsigned short)b, (unsigned short)c, (unsigned short)d);
@@ -105,7 +106,7 @@ template <> struct LcIdx4<unsigned short> {
 };
 template <> struct LcIdx4<unsigned char> {
     typedef uchar4 V;
-    static __device__ __forceinline__ int fix(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+    static __device__ __forceinline__ int fix(float q, int hi) { return (int)fminf(fmaxf(q, 0.0f), (float)hi); } // NaN -> 0
     static __device__ __forceinline__ V pack(int a, int b, int c, int d)
     {
         return make_uchar4((unsigned char)a, (unsigned char)b, (unsigned char)c, (unsigned char)d);
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(256) lc_quant_affine_kernel(const float *__res
             q.z = lc_qa_round(v[u].z, scale); q.w = lc_qa_round(v[u].w, scale);
             if (idx_out)
                 __stcs(reinterpret_cast<IV *>(idx_out) + i,
-                       LcIdx4<T>::pack(LcIdx4<T>::fix(lc_qa_int(q.x), hi), LcIdx4<T>::fix(lc_qa_int(q.y), hi),
-                                       LcIdx4<T>::fix(lc_qa_int(q.z), hi), LcIdx4<T>::fix(lc_qa_int(q.w), hi)));
+                       LcIdx4<T>::pack(LcIdx4<T>::fix(q.x, hi), LcIdx4<T>::fix(q.y, hi), LcIdx4<T>::fix(q.z, hi),
+                                       LcIdx4<T>::fix(q.w, hi)));
             if (wq_out) {
                 float4 o; o.x = lc_qa_deq(q.x, scale); o.y = lc_qa_deq(q.y, scale);
                 o.z = lc_qa_deq(q.z, scale); o.w = lc_qa_deq(q.w, scale);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) lc_quant_affine_kernel(const float *__res
     // tail (n_elem not a multiple of 4)
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
         const float q = lc_qa_round(w[i], scale);
-        if (idx_out) idx_out[i] = (T)LcIdx4<T>::fix(lc_qa_int(q), hi);
+        if (idx_out) idx_out[i] = (T)LcIdx4<T>::fix(q, hi);
         if (wq_out) wq_out[i] = lc_qa_deq(q, scale);
     }
 }
@@ -190,34 +191,55 @@ __global__ void __launch_bounds__(256) lc_dequant_affine_kernel(const T *__restr
 // =================================================================================================
 __device__ __forceinline__ float lc_dist(float z, float c) { return fabsf(__fsub_rn(z, c)); }
 
-__device__ __forceinline__ int lc_argmin_sorted(const float *cb, int n, float z, float guess_scale)
+// cb: the codebook replicated `rep` times in shared memory, entry k of copy c at cb[k * rep + c] -- with rep = 32 every
+// lane reads its own bank whatever k is (the data-dependent lookups of a single copy measured 3-4-way bank conflicts
+// and made the kernel shared-memory bound at 20 % of the HBM roofline).
+#define LC_CB(k) cb[(k) * rep + copy]
+
+// the exact search: lower bound, nearer neighbour, then walks over equal rounded distances (first minimum)
+__device__ __noinline__ int lc_argmin_sorted_slow(const float *cb, int rep, int copy, int n, float z, float guess_scale)
 {
-    if (!(z == z)) return 0; // NaN: every distance is NaN, argmin returns 0
-    // first k with cb[k] >= z, seeded by the affine position of z between the end points
     int k;
     {
-        float g = (z - cb[0]) * guess_scale;
+        float g = (z - LC_CB(0)) * guess_scale;
         g = g < 0.0f ? 0.0f : (g > (float)(n - 1) ? (float)(n - 1) : g);
         k = (int)g;
-        while (k < n && cb[k] < z) k++;
-        while (k > 0 && cb[k - 1] >= z) k--;
+        while (k < n && LC_CB(k) < z) k++;
+        while (k > 0 && LC_CB(k - 1) >= z) k--;
     }
     int best;
     if (k == 0) best = 0;
     else if (k == n) best = n - 1;
-    else best = (lc_dist(z, cb[k]) < lc_dist(z, cb[k - 1])) ? k : k - 1;
-    float d = lc_dist(z, cb[best]);
-    while (best > 0 && lc_dist(z, cb[best - 1]) <= d) { best--; d = lc_dist(z, cb[best]); }
-    while (best < n - 1 && lc_dist(z, cb[best + 1]) < d) { best++; d = lc_dist(z, cb[best]); }
+    else best = (lc_dist(z, LC_CB(k)) < lc_dist(z, LC_CB(k - 1))) ? k : k - 1;
+    float d = lc_dist(z, LC_CB(best));
+    while (best > 0 && lc_dist(z, LC_CB(best - 1)) <= d) { best--; d = lc_dist(z, LC_CB(best)); }
+    while (best < n - 1 && lc_dist(z, LC_CB(best + 1)) < d) { best++; d = lc_dist(z, LC_CB(best)); }
     return best;
 }
 
-__device__ __forceinline__ int lc_argmin_scan(const float *cb, int n, float z)
+// Fast path: the rounded distances fl(|z - cb[k]|) of an ascending table are unimodal in k (rounding is monotone), so
+// if the guessed entry k satisfies d(k-1) > d(k) <= d(k+1) it is torch.argmin's first minimum -- three independent
+// lookups, no loop.  A guess that is off (non-uniform table, |z| so large that distances tie over several entries,
+// +-inf) takes the exact search.
+__device__ __forceinline__ int lc_argmin_sorted(const float *cb, int rep, int copy, int n, float z, float guess_scale, float cb0)
 {
-    float best = lc_dist(z, cb[0]);
+    if (!(z == z)) return 0; // NaN: every distance is NaN, argmin returns 0
+    float g = rintf((z - cb0) * guess_scale);
+    g = g < 0.0f ? 0.0f : (g > (float)(n - 1) ? (float)(n - 1) : g);
+    const int k = (int)g;
+    const int kl = k > 0 ? k - 1 : 0, kr = k < n - 1 ? k + 1 : n - 1;
+    const float dl = lc_dist(z, LC_CB(kl)), dm = lc_dist(z, LC_CB(k)), dr = lc_dist(z, LC_CB(kr));
+    const bool left_ok = k == 0 || dl > dm, right_ok = k == n - 1 || dr >= dm;
+    if (left_ok && right_ok) return k;
+    return lc_argmin_sorted_slow(cb, rep, copy, n, z, guess_scale);
+}
+
+__device__ __forceinline__ int lc_argmin_scan(const float *cb, int rep, int copy, int n, float z)
+{
+    float best = lc_dist(z, LC_CB(0));
     int bi = 0;
     for (int k = 1; k < n; k++) {
-        const float d = lc_dist(z, cb[k]);
+        const float d = lc_dist(z, LC_CB(k));
         if (d < best) { best = d; bi = k; }
     }
     return bi;
@@ -225,14 +247,16 @@ __device__ __forceinline__ int lc_argmin_scan(const float *cb, int n, float z)
 
 template <typename T>
 __global__ void __launch_bounds__(256) lc_quant_codebook_kernel(const float *__restrict__ z, long long n_elem,
-                                                                const float *__restrict__ codebook, int n, int sorted,
-                                                                T *__restrict__ idx_out, float *__restrict__ deq_out)
+                                                                const float *__restrict__ codebook, int n, int rep,
+                                                                int sorted, T *__restrict__ idx_out,
+                                                                float *__restrict__ deq_out)
 {
     typedef typename LcIdx4<T>::V IV;
     extern __shared__ float cb[];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) cb[i] = codebook[i];
+    for (int i = threadIdx.x; i < n * rep; i += blockDim.x) cb[i] = codebook[i / rep];
     __syncthreads();
-    const float span = cb[n - 1] - cb[0];
+    const int copy = (int)(threadIdx.x & (unsigned)(rep - 1));
+    const float cb0 = cb[0], span = cb[(n - 1) * rep] - cb0;
     const float guess_scale = (sorted && span > 0.0f) ? (float)(n - 1) / span : 0.0f;
     const long long n4 = n_elem >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -249,25 +273,28 @@ __global__ void __launch_bounds__(256) lc_quant_codebook_kernel(const float *__r
             if (i >= n4) break;
             int4 o;
             if (sorted) {
-                o.x = lc_argmin_sorted(cb, n, v[u].x, guess_scale); o.y = lc_argmin_sorted(cb, n, v[u].y, guess_scale);
-                o.z = lc_argmin_sorted(cb, n, v[u].z, guess_scale); o.w = lc_argmin_sorted(cb, n, v[u].w, guess_scale);
+                o.x = lc_argmin_sorted(cb, rep, copy, n, v[u].x, guess_scale, cb0);
+                o.y = lc_argmin_sorted(cb, rep, copy, n, v[u].y, guess_scale, cb0);
+                o.z = lc_argmin_sorted(cb, rep, copy, n, v[u].z, guess_scale, cb0);
+                o.w = lc_argmin_sorted(cb, rep, copy, n, v[u].w, guess_scale, cb0);
             } else {
-                o.x = lc_argmin_scan(cb, n, v[u].x); o.y = lc_argmin_scan(cb, n, v[u].y);
-                o.z = lc_argmin_scan(cb, n, v[u].z); o.w = lc_argmin_scan(cb, n, v[u].w);
+                o.x = lc_argmin_scan(cb, rep, copy, n, v[u].x); o.y = lc_argmin_scan(cb, rep, copy, n, v[u].y);
+                o.z = lc_argmin_scan(cb, rep, copy, n, v[u].z); o.w = lc_argmin_scan(cb, rep, copy, n, v[u].w);
             }
             __stcs(reinterpret_cast<IV *>(idx_out) + i, LcIdx4<T>::pack(o.x, o.y, o.z, o.w));
             if (deq_out) {
-                float4 d; d.x = cb[o.x]; d.y = cb[o.y]; d.z = cb[o.z]; d.w = cb[o.w];
+                float4 d; d.x = LC_CB(o.x); d.y = LC_CB(o.y); d.z = LC_CB(o.z); d.w = LC_CB(o.w);
                 __stcs(reinterpret_cast<float4 *>(deq_out) + i, d);
             }
         }
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
-        const int o = sorted ? lc_argmin_sorted(cb, n, z[i], guess_scale) : lc_argmin_scan(cb, n, z[i]);
+        const int o = sorted ? lc_argmin_sorted(cb, rep, copy, n, z[i], guess_scale, cb0) : lc_argmin_scan(cb, rep, copy, n, z[i]);
         idx_out[i] = (T)o;
-        if (deq_out) deq_out[i] = cb[o];
+        if (deq_out) deq_out[i] = LC_CB(o);
     }
 }
+#undef LC_CB
 
 template <typename T>
 __global__ void __launch_bounds__(256) lc_dequant_codebook_kernel(const T *__restrict__ idx, long long n_elem,
@@ -366,6 +393,18 @@ LC_V2_KERNEL(lc_decode_v2_kernel, 0, 0, 0, LC_V2_LAT_PER_SM, false)
 LC_V2_KERNEL(lc_decode_v2_w8_kernel, 256, 512, 16, LC_V2_LAT_PER_SM, false)
 LC_V2_KERNEL(lc_decode_v2_thr_kernel, 0, 0, 0, LC_V2_THR_PER_SM, true)
 LC_V2_KERNEL(lc_decode_v2_w8_thr_kernel, 256, 512, 16, LC_V2_THR_PER_SM, true)
+
+// Small-alphabet decoder (lc_decoder_small.cuh): one warp per stream, dense model in shared memory, n <= 16
+template <int N>
+__global__ void __launch_bounds__(32) lc_decode_small_kernel(LcCoderCfg cfg, const unsigned char *__restrict__ bytes,
+                                                             const long long *__restrict__ offsets,
+                                                             const int *__restrict__ nbits, int B, LcIdxOut out,
+                                                             const float *__restrict__ deq_table, float *deq_out,
+                                                             int *status, int *fault)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lcd_decode_block<N>(cfg, bytes, offsets, nbits, B, out, deq_table, deq_out, status, fault, lc_smem);
+}
 
 #ifdef LC_DEBUG_VARIANTS
 // Decoder v3 (lc_decoder_v3.cuh): decoder warp + context warp + updater warp per stream -- measured slower than v2
@@ -687,6 +726,10 @@ static void lc_prepare_device()
     cudaFuncSetAttribute(lc_decode_v2_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(lc_decode_v2_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(lc_decode_v2_w8_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lc_decode_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lc_decode_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lc_decode_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(lc_decode_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 #ifdef LC_DEBUG_VARIANTS
     cudaFuncSetAttribute(lc_enc_phase_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
     cudaFuncSetAttribute(lc_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -834,14 +877,16 @@ int lc_quantize_codebook_t(const float *z, int64_t n_elem, const float *codebook
     if (n_elem == 0) return 0;
     if ((((uintptr_t)z | (uintptr_t)idx_out | (uintptr_t)deq_out) & 15) != 0) return -22;
     const int grid = lc_ew_grid(n_elem), so = sorted_ascending ? 1 : 0;
-    const size_t sm = (size_t)n * 4;
+    int rep = 32; // copies of the table in shared memory (one per bank while they fit 32 KB)
+    while (rep > 1 && (size_t)n * rep * 4 > 32 * 1024) rep >>= 1;
+    const size_t sm = (size_t)n * rep * 4;
     cudaStream_t st = (cudaStream_t)stream;
     if (idx_bytes == 4)
-        lc_quant_codebook_kernel<int><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, so, (int *)idx_out, deq_out);
+        lc_quant_codebook_kernel<int><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, rep, so, (int *)idx_out, deq_out);
     else if (idx_bytes == 2)
-        lc_quant_codebook_kernel<unsigned short><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, so, (unsigned short *)idx_out, deq_out);
+        lc_quant_codebook_kernel<unsigned short><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, rep, so, (unsigned short *)idx_out, deq_out);
     else
-        lc_quant_codebook_kernel<unsigned char><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, so, (unsigned char *)idx_out, deq_out);
+        lc_quant_codebook_kernel<unsigned char><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, rep, so, (unsigned char *)idx_out, deq_out);
     LC_LAUNCHED();
     return 0;
 }
@@ -1030,6 +1075,28 @@ int lc_decode_batch_t(const uint8_t *bytes, const int64_t *offsets, const int32_
     const LcIdxOut out(idx_out, idx_out ? idx_bytes : 0);
     if (cfg.sm_bytes > 48 * 1024)
         cudaFuncSetAttribute(lc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.sm_bytes);
+    if (lcd_eligible(cfg) && !(flags & (LC_FLAG_DEC_NO_SMALL | LC_FLAG_DEC_REGISTER_MODEL | LC_FLAG_DEC_SERIAL)) &&
+        lcd_smem_bytes(cfg.n, cfg.C) <= 64 * 1024) {
+        // alphabets of up to 16 symbols: dense model in shared memory, one warp per stream; anything unusual
+        // (corrupt streams) is flagged and redone by the generic kernel
+        const size_t sm = lcd_smem_bytes(cfg.n, cfg.C);
+        int per_sm = (int)((227u * 1024u) / (sm + 1024u));
+        if (per_sm > 32) per_sm = 32;
+        long long gs = (long long)lc_num_sms() * per_sm;
+        if (gs > B) gs = B;
+        const long long *offs = (const long long *)offsets;
+        switch (cfg.n) {
+        case 2: lc_decode_small_kernel<2><<<(int)gs, 32, sm, st>>>(cfg, bytes, offs, nbits, B, out, deq_table, deq_out, status, fault_index); break;
+        case 4: lc_decode_small_kernel<4><<<(int)gs, 32, sm, st>>>(cfg, bytes, offs, nbits, B, out, deq_table, deq_out, status, fault_index); break;
+        case 8: lc_decode_small_kernel<8><<<(int)gs, 32, sm, st>>>(cfg, bytes, offs, nbits, B, out, deq_table, deq_out, status, fault_index); break;
+        default: lc_decode_small_kernel<16><<<(int)gs, 32, sm, st>>>(cfg, bytes, offs, nbits, B, out, deq_table, deq_out, status, fault_index); break;
+        }
+        LC_LAUNCHED();
+        lc_decode_kernel<<<grid, 32, cfg.sm_bytes, st>>>(cfg, bytes, offs, nbits, B, out, deq_table, deq_out, status,
+                                                         fault_index, (char *)scratch, LC_NEEDS_GENERIC);
+        LC_LAUNCHED();
+        return 0;
+    }
     if (lc_use_decoder_v2(cfg, flags)) {
         // decoder/updater warps; streams with a context of more than 32 distinct symbols are flagged
         // and redone from scratch by the generic kernel

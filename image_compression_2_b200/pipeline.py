@@ -40,6 +40,7 @@ class LatentPipeline:
             raise ValueError(quantizer)
         self.ws = codec.CoderWorkspace()
         self._pinned = {}
+        self._bytes_hint = 0  # roundtrip_host: largest compressed stream seen so far, in bytes
         self._chunk_ctx = []  # roundtrip_host: (stream, workspace) per chunk
 
     # ---- stages -------------------------------------------------------------------------------
@@ -83,71 +84,108 @@ class LatentPipeline:
         return buf
 
     def roundtrip_host(self, latents_host, chunks=None):
-        """latents_host: pinned CPU fp32 [B,R,C].  Returns dict(bytes = pinned uint8 view of the compressed streams,
-        offsets, nbits, enc_status, deq = pinned fp32 [B,R,C], dec_status, h2d_bytes, d2h_bytes).  Synchronises at
-        the end.
+        """latents_host: pinned CPU fp32 [B,R,C].  Returns dict(bytes = pinned uint8 buffer holding the compressed
+        streams, offsets, nbits, enc_status, deq = pinned fp32 [B,R,C], dec_status, h2d_bytes, d2h_bytes).
+        Synchronises once, at the end.  The returned tensors are pinned buffers of this object: the next call
+        overwrites them (copy what has to outlive it).
 
-        The batch is cut into `chunks` contiguous sub-batches (default: about 2048 streams each, from 1536 streams up), each with its own CUDA
-        stream and workspace, so that the host<->device copies of one chunk run under the kernels of the others.
-        Every chunk still makes the full trip: latents up, compressed bytes down to the host and up again, dequantised
-        fp32 down.  Measured on a B200: 8192 streams 73.0 -> 63.5 ms; at 1024 streams (one latency-bound wave per
-        kernel, encoder blocks of one chunk waiting for registers held by the decoder blocks of another) chunking
-        gains nothing, so small batches stay in one piece."""
+        Every chunk makes the full trip -- latents up, compressed bytes down to the host (what save_compressed
+        writes) and up again (what load_compressed reads), dequantised fp32 down (written by the decoder straight
+        into the pinned buffer) -- and nothing in it waits for the host: the number of compressed bytes to move is
+        not read back mid-way but bounded by a size hint (the largest per-stream size seen by earlier calls, +2 %;
+        the whole slot area on the first call), and checked after the final synchronise; a chunk whose streams
+        outgrew the hint is simply done again with the exact size.
+
+        The batch is cut into `chunks` contiguous sub-batches (default: two from 1024 streams, about 2048 streams
+        each from 4096 up), each with its own CUDA stream and workspace, all enqueued up front, so the copies of one
+        chunk run under the kernels of the others."""
         B = latents_host.shape[0]
-        if chunks is None:  # chunks of about 2048 streams, from 1536 streams up (measured: 1536 -6 %, 2048 -8 %, 4096 -6 %)
-            chunks = max(2, min(4, (B + 1024) // 2048)) if B >= 1536 else 1
+        if chunks is None:
+            chunks = max(2, min(4, (B + 1024) // 2048)) if B >= 1024 else 1
         chunks = max(1, min(int(chunks), B))
         bounds = [(B * c) // chunks for c in range(chunks + 1)]
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.device)
         while len(self._chunk_ctx) < chunks:
             self._chunk_ctx.append((torch.cuda.Stream(device=self.device), codec.CoderWorkspace()))
+        slot = int(codec._native.load().lc_encode_slot_bytes(1, self.R, self.C, self.n))
+        per_stream = min(slot, int(self._bytes_hint * 1.02) + 64) if self._bytes_hint else slot
         deq_host = self._pin("deq", latents_host.shape, torch.float32)
         st_host = self._pin("dstatus", (B,), torch.int32)
         meta_all = self._pin("meta", (3 * B + chunks,), torch.int64)  # per chunk: offsets[Bc+1] | nbits[Bc] | status[Bc]
-        stage = []
-        for c in range(chunks):  # everything up to the compressed product, all chunks enqueued before any host wait
+        caps = [((bounds[c + 1] - bounds[c]) * per_stream + 15) // 16 * 16 for c in range(chunks)]
+        bytes_host = self._pin("bytes", (sum(caps),), torch.uint8)
+        with torch.cuda.device(self.device):
+            redo = self._roundtrip_chunks(latents_host, bounds, caps, range(chunks), main, deq_host, st_host, meta_all,
+                                          bytes_host)
+            if redo:  # streams larger than the hint: those chunks again, with room for any stream
+                full = [((bounds[c + 1] - bounds[c]) * slot + 15) // 16 * 16 for c in range(chunks)]
+                bytes_host = self._pin("bytes_full", (sum(full),), torch.uint8)
+                self._roundtrip_chunks(latents_host, bounds, full, range(chunks), main, deq_host, st_host, meta_all,
+                                       bytes_host)
+                caps = full
+        offs_out = torch.empty(B + 1, dtype=torch.int64)
+        nbits_out = torch.empty(B, dtype=torch.int64)
+        status_out = torch.empty(B, dtype=torch.int64)
+        base, used_total = 0, 0
+        for c in range(chunks):
             c0, c1 = bounds[c], bounds[c + 1]
+            Bc = c1 - c0
+            m = meta_all[3 * c0 + c:3 * c0 + c + 3 * Bc + 1]
+            offs_out[c0:c1] = m[:Bc] + base
+            nbits_out[c0:c1] = m[Bc + 1:2 * Bc + 1]
+            status_out[c0:c1] = m[2 * Bc + 1:]
+            used_total += int(m[Bc])
+            base += caps[c]
+        offs_out[B] = base
+        ok = status_out == 0
+        if bool(ok.any()):
+            self._bytes_hint = max(self._bytes_hint, int(((nbits_out[ok] + 7) // 8).max()) + 16)
+        moved = sum(caps)
+        h2d = latents_host.numel() * 4 + moved + (2 * B + chunks) * 8
+        d2h = meta_all.numel() * 8 + moved + deq_host.numel() * 4 + B * 4
+        return dict(bytes=bytes_host, offsets=offs_out, nbits=nbits_out, enc_status=status_out, deq=deq_host,
+                    dec_status=st_host, h2d_bytes=h2d, d2h_bytes=d2h, chunks=chunks, compressed_bytes=used_total)
+
+    def _roundtrip_chunks(self, latents_host, bounds, caps, which, main, deq_host, st_host, meta_all, bytes_host):
+        """Enqueue the whole trip of the listed chunks (no host wait), synchronise, return the chunks whose compressed
+        size exceeded their cap."""
+        base = [sum(caps[:c]) for c in range(len(caps))]
+        for c in which:
+            c0, c1 = bounds[c], bounds[c + 1]
+            Bc = c1 - c0
             st, ws = self._chunk_ctx[c]
             st.wait_stream(main)
             with torch.cuda.stream(st):
                 lat = latents_host[c0:c1].to(self.device, non_blocking=True)
-                enc = self.encode(self.quantize(lat), ws)
-                m0 = 3 * c0 + c
-                meta_host = meta_all[m0:m0 + 3 * (c1 - c0) + 1]
-                meta_host.copy_(torch.cat([enc.offsets, enc.nbits.long(), enc.status.long()]), non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(st)
-            stage.append((enc, meta_host, ev))
-        bytes_host = self._pin("bytes", (sum(e.data.numel() + 16 for e, _, _ in stage),), torch.uint8)
-        base, used_total = 0, 0
-        offs_out = torch.empty(B + 1, dtype=torch.int64)
-        for c in range(chunks):
-            c0, c1 = bounds[c], bounds[c + 1]
-            Bc = c1 - c0
-            st, ws = self._chunk_ctx[c]
-            enc, meta_host, ev = stage[c]
-            ev.synchronize()  # this chunk's sizes are on the host; the other chunks keep the GPU busy meanwhile
-            used = int(meta_host[Bc])
-            offs_out[c0:c1] = meta_host[:Bc] + base
-            with torch.cuda.stream(st):
+                enc = self.encode(self.quantize(lat), ws, reuse_output=True)
+                meta_dev = ws.get(("meta", self.device), 3 * Bc + 1, self.device, torch.int64)[:3 * Bc + 1]
+                meta_dev[:Bc + 1] = enc.offsets
+                meta_dev[Bc + 1:2 * Bc + 1] = enc.nbits
+                meta_dev[2 * Bc + 1:] = enc.status
+                meta_host = meta_all[3 * c0 + c:3 * c0 + c + 3 * Bc + 1]
+                meta_host.copy_(meta_dev, non_blocking=True)
+                cap = min(caps[c], enc.data.numel())
+                seg = bytes_host[base[c]:base[c] + cap]
                 # compressed product -> host (what save_compressed would write) ...
-                bytes_host[base:base + used].copy_(enc.data[:used], non_blocking=True)
+                seg.copy_(enc.data[:cap], non_blocking=True)
                 # ... and host -> device again (what load_compressed would read), decode + dequantise
-                data_dev = bytes_host[base:base + max(used, 16)].to(self.device, non_blocking=True)
-                offs_dev = meta_host[:Bc + 1].to(self.device, non_blocking=True)
-                nbits_dev = meta_host[Bc + 1:2 * Bc + 1].to(self.device, non_blocking=True).int()
-                # (the decoder writes the dequantised rows straight into the pinned host buffer as it goes)
-                dec_idx, deq, dstatus, dfault = self.decode(data_dev, offs_dev, nbits_dev, Bc, ws, deq_out=deq_host[c0:c1])
+                data_dev = ws.get(("bytes_back", self.device), cap, self.device)[:cap]
+                data_dev.copy_(seg, non_blocking=True)
+                meta_back = ws.get(("meta_back", self.device), 3 * Bc + 1, self.device, torch.int64)[:3 * Bc + 1]
+                meta_back.copy_(meta_host, non_blocking=True)
+                nbits_dev = ws.get(("nbits_back", self.device), Bc, self.device, torch.int32)[:Bc]
+                nbits_dev.copy_(meta_back[Bc + 1:2 * Bc + 1])
+                # (the decoder writes the dequantised rows straight into the pinned host buffer as it goes; a
+                # stream cut short by the cap decodes garbage inside its own slot and is redone by the caller)
+                _, _, dstatus, _ = self.decode(data_dev, meta_back[:Bc + 1], nbits_dev, Bc, ws, deq_out=deq_host[c0:c1],
+                                               want_idx=False, reuse_output=True)
                 st_host[c0:c1].copy_(dstatus, non_blocking=True)
-            base += (used + 15) // 16 * 16
-            used_total += used
-        offs_out[B] = base
-        for c in range(chunks):
+        for c in which:
             main.wait_stream(self._chunk_ctx[c][0])
         main.synchronize()
-        nbits_out = torch.cat([m[(bounds[c + 1] - bounds[c]) + 1:2 * (bounds[c + 1] - bounds[c]) + 1] for c, (_, m, _) in enumerate(stage)])
-        status_out = torch.cat([m[2 * (bounds[c + 1] - bounds[c]) + 1:] for c, (_, m, _) in enumerate(stage)])
-        h2d = latents_host.numel() * 4 + used_total + (2 * B + chunks) * 8
-        d2h = meta_all.numel() * 8 + used_total + deq_host.numel() * 4 + B * 4
-        return dict(bytes=bytes_host[:base], offsets=offs_out, nbits=nbits_out, enc_status=status_out, deq=deq_host,
-                    dec_status=st_host, h2d_bytes=h2d, d2h_bytes=d2h, chunks=chunks)
+        redo = []
+        for c in which:
+            c0, c1 = bounds[c], bounds[c + 1]
+            if int(meta_all[3 * c0 + c + (c1 - c0)]) > caps[c]:
+                redo.append(c)
+        return redo

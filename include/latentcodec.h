@@ -74,7 +74,7 @@ int64_t lc_debug_launch_count(int reset);
  * rounded fp32 operations.  idx_out and wq_out may each be NULL. */
 int lc_quantize_affine(const float *w, int64_t n_elem, int bits, int32_t *idx_out, float *wq_out, void *stream);
 /* ... with uint16 / uint8 indices.  The narrow forms hold what the coder consumes -- the index CLAMPED to the alphabet
- * [0, 2^bits-1] (NaN -> 0) -- because the unclamped value of an out-of-range latent does not fit them; wq_out is
+ * [0, 2^bits-1] (NaN -> 0, +-inf clamped) -- because the unclamped value of an out-of-range latent does not fit them; wq_out is
  * computed from the unclamped index exactly as above.  idx_bytes = 4 is lc_quantize_affine. */
 int lc_quantize_affine_t(const float *w, int64_t n_elem, int bits, void *idx_out, int idx_bytes, float *wq_out,
                          void *stream);

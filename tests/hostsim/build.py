@@ -15,6 +15,7 @@ SRCS = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "cuda_emul.h"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_fast.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v2.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v3.cuh"),
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_small.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_sparse.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_pack.cuh")]
 _lib = None
@@ -95,7 +96,8 @@ def decode(streams, n, shape, mode=1, rate=0.05, grid=None, codebook=None, fast=
         redone = ctypes.c_int(0)
         if fast in ("v2", "v3"):
             lib().hostsim_set_decoder_version(int(fast[1]))
-        fn = lib().hostsim_decode_v2 if fast in ("v2", "v3") else lib().hostsim_decode_fast
+        fn = (lib().hostsim_decode_v2 if fast in ("v2", "v3") else
+              lib().hostsim_decode_small if fast == "small" else lib().hostsim_decode_fast)
         rc = fn(_p(blob, ctypes.c_ubyte), _p(offs, ctypes.c_longlong), _p(nbits, ctypes.c_int), B,
                                        imgs, R, C, int(n), ctypes.c_double(rate), _p(out, ctypes.c_int), cbp, deqp,
                                        _p(status, ctypes.c_int), _p(fault, ctypes.c_int), grid, ctypes.byref(redone))

@@ -13,6 +13,7 @@
 #include "../../image_compression_2_b200/csrc/lc_decoder_fast.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_v2.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_v3.cuh"
+#include "../../image_compression_2_b200/csrc/lc_decoder_small.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_sparse.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_pack.cuh"
 #include <algorithm>
@@ -214,6 +215,41 @@ extern "C" int hostsim_decode_fast(const unsigned char *bytes, const long long *
     for (int b = 0; b < B; b++) redo += status[b] == LC_NEEDS_GENERIC;
     *n_redone = redo;
     a.only_flagged = LC_NEEDS_GENERIC;
+    for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a, (unsigned)b, (unsigned)grid);
+    return 0;
+}
+
+// small-alphabet decoder (dense shared-memory model, n <= 16) followed by the generic redo pass, as the host does
+static void decsmall_body(void *p)
+{
+    DecArgs *a = (DecArgs *)p;
+    const LcIdxOut out(a->out);
+    switch (a->cfg.n) {
+    case 2: lcd_decode_block<2>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
+    case 4: lcd_decode_block<4>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
+    case 8: lcd_decode_block<8>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
+    default: lcd_decode_block<16>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
+    }
+}
+extern "C" int hostsim_decode_small(const unsigned char *bytes, const long long *offsets, const int *nbits, int B,
+                                    int imgs, int R, int C, int n, double rate, int *out, const float *deq_table,
+                                    float *deq_out, int *status, int *fault, int grid, int *n_redone)
+{
+    DecArgs a;
+    int rc = make_cfg(a.cfg, imgs, R, C, n, rate, LC_MODE_REPAIRED, 1);
+    if (rc) return rc;
+    if (!lcd_eligible(a.cfg)) return -22;
+    std::vector<char> scratch((size_t)grid * a.cfg.scratch_stride + 256);
+    std::vector<char> smem_small(lcd_smem_bytes(n, C) + 64), smem(a.cfg.sm_bytes + 64);
+    a.bytes = bytes; a.offsets = offsets; a.nbits = nbits; a.B = B; a.out = out; a.deq_table = deq_table; a.deq_out = deq_out;
+    a.status = status; a.fault = fault; a.scratch = scratch.data(); a.only_flagged = 0;
+    a.smem = (char *)(((uintptr_t)smem_small.data() + 15) & ~(uintptr_t)15);
+    for (int b = 0; b < grid; b++) emu::run_warp(decsmall_body, &a, (unsigned)b, (unsigned)grid);
+    int redo = 0;
+    for (int b = 0; b < B; b++) redo += status[b] == LC_NEEDS_GENERIC;
+    *n_redone = redo;
+    a.only_flagged = LC_NEEDS_GENERIC;
+    a.smem = (char *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     for (int b = 0; b < grid; b++) emu::run_warp(dec_body, &a, (unsigned)b, (unsigned)grid);
     return 0;
 }

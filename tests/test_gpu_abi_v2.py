@@ -28,7 +28,7 @@ def test_narrow_index_quantisers_match_the_int32_forms(dtype):
         i32, wq32 = codec.quantize_affine(w, bits)
         i8, wq8 = codec.quantize_affine(w, bits, idx_dtype=dtype)
         ref = q["a_idx_%d" % bits]
-        want = np.where(np.isfinite(ref), np.clip(ref, 0, (1 << bits) - 1), 0).astype(np.int64)
+        want = np.where(np.isnan(ref), 0, np.clip(ref, 0, (1 << bits) - 1)).astype(np.int64)
         assert np.array_equal(i8.cpu().numpy().astype(np.int64), want), bits
         assert _eq_f32(wq8.cpu().numpy(), wq32.cpu().numpy())
         # dequantiser A on the narrow type = on int32
@@ -229,3 +229,29 @@ def test_compress_retries_streams_that_overflow_the_default_slot():
     assert status[0] == 0 and nbits[0] == ref["nbits"] and streams[0] == ref["packed"]
     packed, nb = coder.cabac_encode_packed(codes, coder.ContextModel(n))
     assert nb == ref["nbits"] and packed == ref["packed"]
+
+
+@pytest.mark.parametrize("n,sd", [(16, 1.14), (16, 3.0), (8, 1.0), (4, 0.8), (2, 0.5)])
+def test_small_alphabet_decoder_and_its_alternatives_agree_with_the_oracle(n, sd):
+    """Alphabets up to 16 symbols take the dense shared-memory decoder (lc_decoder_small.cuh); LC_FLAG_DEC_NO_SMALL
+    sends them down the other kernels.  Narrow 4-bit data does not round-trip in the reference (hazards H1-H3): the
+    test is decoder-vs-decoder -- same symbols up to the fault, same fault class, same fault index."""
+    from image_compression_2_b200 import _native, codec
+    rng = np.random.default_rng(n * 100 + int(sd * 10))
+    shape = (6, 16, 512)
+    codes = np.clip(np.round(rng.normal(n / 2, sd, shape)), 0, n - 1).astype(np.int32)
+    streams = [O.encode_stream(codes[b:b + 1], n)["packed"] for b in range(shape[0])]
+    bad = bytearray(streams[-1]); bad[len(bad) // 3] ^= 0x11; streams[-1] = bytes(bad)   # a corrupted stream
+    layout = codec.layout_independent(shape)
+    data, offsets, nbits = codec.pack_streams_for_device(streams, "cuda")
+    cb = torch.linspace(-1, 1, n).float().cuda()
+    refs = [O.decode_stream(streams[b], n, (1,) + shape[1:]) for b in range(shape[0])]
+    for flags in (0, _native.FLAG_DEC_NO_SMALL, _native.FLAG_DEC_SERIAL):
+        idx, deq, st, fi = codec.decode_batch(data, offsets, nbits, layout, n, codebook=cb, flags=flags,
+                                              idx_dtype=torch.uint8)
+        idx, deq, st, fi = idx.cpu().numpy(), deq.cpu().numpy(), st.cpu().numpy(), fi.cpu().numpy()
+        for b, ref in enumerate(refs):
+            k = int(ref["fault_index"]) if ref["status"] else codes[b].size
+            assert st[b] == ref["status"] and (ref["status"] == 0 or fi[b] == k), (flags, b, st[b], ref["status"])
+            assert np.array_equal(idx[b][:k], ref["symbols"].ravel()[:k]), (flags, b)
+            assert np.array_equal(deq[b][:k], cb.cpu().numpy()[ref["symbols"].ravel()[:k]]), (flags, b)

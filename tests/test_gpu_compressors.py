@@ -114,9 +114,17 @@ def test_pipeline_host_roundtrip():
     lat = synth_latents("enc_like", B, 77).pin_memory()
     for quantizer, chunks in (("codebook", None), ("affine", None), ("codebook", 3)):  # 3: uneven chunks on 3 streams
         pipe = LatentPipeline(n_symbols=256, quantizer=quantizer)
-        res = pipe.roundtrip_host(lat, chunks=chunks)
-        assert res["chunks"] == (chunks or 1)
-        assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any()
+        for attempt in range(3):
+            # 0: no size hint yet (whole slots travel); 1: hint from the first call; 2: a hint that is too small --
+            # the chunks are redone with the exact size.  Same result every time.
+            if attempt == 2:
+                pipe._bytes_hint = 100
+            res = pipe.roundtrip_host(lat, chunks=chunks)
+            assert res["chunks"] == (chunks or 1)
+            assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any()
+            if attempt == 1:
+                assert res["h2d_bytes"] < first_h2d  # the hint shrinks the compressed-bytes round trip
+            first_h2d = res["h2d_bytes"] if attempt == 0 else first_h2d
         if quantizer == "codebook":
             cb = pipe.codebook.cpu().numpy()
             idx = O.quantize_codebook(lat.numpy(), cb)

@@ -304,3 +304,55 @@ def test_decoder_v2_wide_contexts_and_images_sharing_a_model(ver):
     dec, st, fi, _ = H.decode([bytes(bad)], 64, (1,) + imgs.shape, 1, fast=ver, grid=1)
     k = int(ref["fault_index"]) if ref["status"] else imgs.size
     assert st[0] == ref["status"] and np.array_equal(dec.ravel()[:k], ref["symbols"].ravel()[:k])
+
+
+# ---- small-alphabet decoder (dense shared-memory model, n <= 16) ----
+
+def test_small_decoder_matches_reference_vectors():
+    ran = 0
+    for fixture in ("kat.npz", "coder_small.npz", "coder_full.npz"):
+        for name, rec in coder_cases(golden(fixture), mode="repaired").items():
+            n, codes = int(rec["n"]), rec["codes"]
+            if not _pow2(n) or n > 16 or codes.ndim != 3 or "enc_error" in rec:
+                continue
+            batch = codes[None]
+            dec, st, fi, _ = H.decode([rec["packed"].tobytes()], n, batch.shape, 1, fast="small")
+            ref = rec["decoded"].reshape(batch.shape)
+            if "dec_error" in rec:
+                k = int(rec["dec_fault_index"])
+                assert st[0] == ERR_TO_STATUS[str(rec["dec_error"][0])] and fi[0] == k, name
+                assert np.array_equal(dec.ravel()[:k], ref.ravel()[:k]) and not dec.ravel()[k:].any(), name
+            elif st[0] == 4:
+                assert ref.ravel()[fi[0]] == -1, name
+            else:
+                assert st[0] == 0 and np.array_equal(dec, ref), name
+            ran += 1
+    assert ran > 10, ran
+
+
+def test_small_decoder_against_oracle_decoder():
+    """Random streams at 1..4 bits, including narrow 4-bit data the reference cannot round-trip (hazards H1-H3), several
+    images sharing a model, short rows and a corrupted stream: same symbols, fault class and fault index as the oracle."""
+    rng = np.random.default_rng(1234)
+    cases = ((16, (3, 16, 512), 1.14), (16, (2, 16, 512), 0.6), (16, (2, 16, 512), 3.0), (8, (3, 6, 64), 1.0),
+             (4, (2, 5, 33), 0.8), (2, (2, 3, 40), 0.5), (16, (4, 1, 7), 2.0), (8, (2, 9, 1), 1.5))
+    for n, shape, sd in cases:
+        codes = np.clip(np.round(rng.normal(n / 2, sd, shape)), 0, n - 1).astype(np.int32)
+        codes[0, 0, :3] = n - 1
+        streams = [O.encode_stream(codes[b:b + 1], n)["packed"] for b in range(shape[0])]
+        bad = bytearray(streams[-1])
+        if len(bad) > 4:
+            bad[len(bad) // 2] ^= 0x5a
+            streams[-1] = bytes(bad)
+        cb = np.linspace(-1, 1, n).astype(np.float32)
+        dec, st, fi, deq = H.decode(streams, n, codes.shape, 1, fast="small", grid=2, codebook=cb)
+        for b in range(shape[0]):
+            ref = O.decode_stream(streams[b], n, (1,) + shape[1:])
+            k = int(ref["fault_index"]) if ref["status"] else codes[b].size
+            assert st[b] == ref["status"] and (ref["status"] == 0 or fi[b] == k), (n, shape, b, st[b], ref["status"])
+            assert np.array_equal(dec[b].ravel()[:k], ref["symbols"].ravel()[:k]), (n, shape, b)
+            assert np.array_equal(deq[b][:k], cb[dec[b].ravel()[:k]])
+    imgs = np.clip(np.round(rng.normal(8, 2, (3, 4, 64))), 0, 15).astype(np.int32)
+    packed = O.encode_stream(imgs, 16)["packed"]
+    dec, st, fi, _ = H.decode([packed], 16, (1,) + imgs.shape, 1, fast="small", grid=1)
+    assert not st.any() and np.array_equal(dec[0], imgs)
