@@ -9,8 +9,8 @@ Deviations, all documented in DESIGN.md:
     created with track_state=True;
   * a non-empty model (or track_state=True) takes the stateful kernel (csrc/lc_stateful.cuh): the stream is coded
     from that model and the object is left holding what the reference's object would hold (the reference mutates
-    one shared model across calls, defect D5).  Supported for alphabets up to 256 symbols with (left,up)
-    contexts, up to 1024 with the single global context; otherwise NotImplementedError -- no CPU fallback;
+    one shared model across calls, defect D5).  Alphabets up to 1024 symbols (the direct-mapped device table is
+    (n+1)^2*n*8 bytes: 8.6 GB of the B200's 180 GB at 1024 symbols; only valid[]/counts[] are cleared);
   * DEFAULT_MODE is "repaired": the file as shipped ("verbatim") raises ValueError within a few
     hundred symbols on any realistic stream (defect D3).  mode="verbatim" reproduces that.
 """
@@ -94,8 +94,8 @@ class _StatefulTable:
         n, has_ctx = int(context_model.n_symbols), int(layout.has_ctx)
         nbytes = lib.lc_stateful_table_bytes(n, has_ctx)
         if nbytes < 0:
-            raise NotImplementedError("stateful coding needs a power-of-two alphabet of at most 256 symbols with "
-                                      "(left,up) contexts (1024 with the global context); there is no CPU fallback")
+            raise NotImplementedError("stateful coding needs a power-of-two alphabet of at most 1024 symbols; "
+                                      "there is no CPU fallback")
         self.n, self.has_ctx, self.nkeys = n, has_ctx, ((n + 1) ** 2 if has_ctx else 1)
         off_c, off_v = lib.lc_stateful_table_offset(n, has_ctx, 1), lib.lc_stateful_table_offset(n, has_ctx, 2)
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)

@@ -6,8 +6,12 @@
 // is the wrong shape for them: at 4 bits 73 % of the symbols found a pool record of more than six entries, every
 // symbol was an updater job, and decoder and updater warp took ~3000 cycles per symbol (profiles/r01_*, DESIGN.md
 // section 5).  Here the model is what the reference keeps (ContextModel.context_models, :73): one DENSE float64
-// vector per context, all of them in shared memory (289 x 16 doubles = 37 KB per stream), and one warp per stream
-// does everything with the lanes working on the vector elements:
+// vector per context (289 x 16 doubles = 37 KB per stream), and one warp per stream does everything with the lanes
+// working on the vector elements.  The table lives in GLOBAL memory, one per resident warp: in shared memory it
+// capped an SM at five streams and the kernel was latency bound at ~1560 cycles per symbol (35.8 ms for 4096
+// streams of cfg3 at 4 bits); in global memory 32 warps fit an SM, the 128-byte vector reads and writes stay in
+// the L2 (the tables of all resident warps are ~175 MB of address space, a stream touches its own 37 KB over
+// and over), and their latency is covered by the other warps:
 //   * open a context: every lane reads the whole vector (broadcast loads) and runs the strictly sequential
 //     np.cumsum (:346-347) up to its own element, so lane i holds cum[i] and cum[i+1] EXACTLY as the reference
 //     computes them -- no guard bands, no approximate sums;
@@ -29,9 +33,10 @@ static inline int lcd_eligible(const LcCoderCfg &c)
 {
     return c.mode == LC_MODE_REPAIRED && c.has_ctx && c.n >= 2 && c.n <= LCD_MAX_N && c.C <= 8192;
 }
-// shared memory of one block (= one stream): the dense table, then the previous/current row of decoded symbols
-static inline LC_HD uint32_t lcd_tab_bytes(int n) { return (uint32_t)(n + 1) * (uint32_t)(n + 1) * (uint32_t)n * 8u; }
-static inline LC_HD uint32_t lcd_smem_bytes(int n, int C) { return lcd_tab_bytes(n) + lc_round_up(2u * (uint32_t)C, 16); }
+// per resident warp: the dense table in global scratch; shared memory: the previous/current row of decoded symbols
+static inline LC_HD uint32_t lcd_tab_bytes(int n) { return lc_round_up((uint32_t)(n + 1) * (uint32_t)(n + 1) * (uint32_t)n * 8u, 256); }
+static inline LC_HD uint32_t lcd_smem_bytes(int C) { return lc_round_up(2u * (uint32_t)C, 16); }
+#define LCD_WARPS_PER_SM 32
 
 // NumPy's pairwise float64 sum (call site :135) of the N values held one per lane (lane l < N holds a[l]); every lane
 // gets the total.  N >= 8: accumulators r[j] = a[j] (+ a[j+8]), combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) -- an
@@ -173,11 +178,11 @@ __device__ __forceinline__ void lcd_decode_stream(const LcCoderCfg &cfg, double 
 template <int N>
 __device__ __forceinline__ void lcd_decode_block(const LcCoderCfg &cfg, const unsigned char *bytes, const long long *offsets,
                                                  const int *nbits, int B, LcIdxOut out, const float *deq_table,
-                                                 float *deq_out, int *status, int *fault, char *smem)
+                                                 float *deq_out, int *status, int *fault, char *scratch, char *smem)
 {
     const int lane = (int)(threadIdx.x & 31);
-    double *tab = (double *)smem;
-    unsigned char *rows = (unsigned char *)(smem + lcd_tab_bytes(N));
+    double *tab = (double *)(scratch + (size_t)blockIdx.x * lcd_tab_bytes(N));
+    unsigned char *rows = (unsigned char *)smem;
     for (int sidx = (int)blockIdx.x; sidx < B; sidx += (int)gridDim.x) {
         int fi = 0, st = 0;
         const long long nby = ((long long)nbits[sidx] + 7) >> 3;

@@ -161,7 +161,9 @@ int lc_decode_batch_t(const uint8_t *bytes, const int64_t *offsets, const int32_
  *   int32 counts[nkeys]                     at lc_stateful_table_offset(..., 1)   context_counts
  *   float64 vectors[nkeys][n]               at lc_stateful_table_offset(..., 2)   the probability vectors
  * The caller zeroes valid/counts, scatters the given model in, and gathers the valid entries after the call.
- * n_symbols: power of two, <= 256 when has_ctx (the table is (n+1)^2 * n * 8 bytes), <= 1024 otherwise. */
+ * n_symbols: power of two up to 1024.  With (left,up) contexts the table is direct-mapped, (n+1)^2 * n * 8 bytes: 135 MB
+ * at 256 symbols, 8.6 GB at 1024 -- sized for the 180 GB of a B200; only the vectors of contexts that exist are ever
+ * touched (the valid flags say which), and nothing but valid[] and counts[] needs clearing. */
 int64_t lc_stateful_table_bytes(int n_symbols, int has_ctx);
 int64_t lc_stateful_table_offset(int n_symbols, int has_ctx, int which);
 

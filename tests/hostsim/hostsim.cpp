@@ -225,10 +225,10 @@ static void decsmall_body(void *p)
     DecArgs *a = (DecArgs *)p;
     const LcIdxOut out(a->out);
     switch (a->cfg.n) {
-    case 2: lcd_decode_block<2>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
-    case 4: lcd_decode_block<4>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
-    case 8: lcd_decode_block<8>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
-    default: lcd_decode_block<16>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->smem); break;
+    case 2: lcd_decode_block<2>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->scratch, a->smem); break;
+    case 4: lcd_decode_block<4>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->scratch, a->smem); break;
+    case 8: lcd_decode_block<8>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->scratch, a->smem); break;
+    default: lcd_decode_block<16>(a->cfg, a->bytes, a->offsets, a->nbits, a->B, out, a->deq_table, a->deq_out, a->status, a->fault, a->scratch, a->smem); break;
     }
 }
 extern "C" int hostsim_decode_small(const unsigned char *bytes, const long long *offsets, const int *nbits, int B,
@@ -239,8 +239,8 @@ extern "C" int hostsim_decode_small(const unsigned char *bytes, const long long 
     int rc = make_cfg(a.cfg, imgs, R, C, n, rate, LC_MODE_REPAIRED, 1);
     if (rc) return rc;
     if (!lcd_eligible(a.cfg)) return -22;
-    std::vector<char> scratch((size_t)grid * a.cfg.scratch_stride + 256);
-    std::vector<char> smem_small(lcd_smem_bytes(n, C) + 64), smem(a.cfg.sm_bytes + 64);
+    std::vector<char> scratch((size_t)grid * (a.cfg.scratch_stride > lcd_tab_bytes(n) ? a.cfg.scratch_stride : lcd_tab_bytes(n)) + 256);
+    std::vector<char> smem_small(lcd_smem_bytes(C) + 64), smem(a.cfg.sm_bytes + 64);
     a.bytes = bytes; a.offsets = offsets; a.nbits = nbits; a.B = B; a.out = out; a.deq_table = deq_table; a.deq_out = deq_out;
     a.status = status; a.fault = fault; a.scratch = scratch.data(); a.only_flagged = 0;
     a.smem = (char *)(((uintptr_t)smem_small.data() + 15) & ~(uintptr_t)15);

@@ -167,7 +167,8 @@ def _same_model(a, b):
         assert a[k][1] == b[k][1] and np.array_equal(a[k][0], b[k][0]), k
 
 
-@pytest.mark.parametrize("n,shape", [(16, (2, 3, 30)), (64, (1, 4, 48)), (256, (1, 16, 128)), (16, (50,)), (1024, (40,))])
+@pytest.mark.parametrize("n,shape", [(16, (2, 3, 30)), (64, (1, 4, 48)), (256, (1, 16, 128)), (16, (50,)), (1024, (40,)),
+                                     (1024, (2, 4, 96))])  # 10 bits with (left,up) contexts: cfg3's alphabet
 def test_shared_context_model_across_calls(n, shape):
     """The reference mutates ONE ContextModel in cabac_encode, cabac_decode and across calls (defect D5).  With a
     non-empty model (or track_state=True) the stream is coded from that state and the object ends up holding what
@@ -206,9 +207,9 @@ def test_shared_context_model_across_calls(n, shape):
 
 def test_stateful_model_limits():
     from image_compression_2_b200 import coder
-    cm = coder.ContextModel(1024)
-    cm.context_models[(0, 0)] = np.ones(1024) / 1024
-    with pytest.raises(NotImplementedError):  # (left,up) contexts: the dense table is limited to 256 symbols
+    cm = coder.ContextModel(2048)
+    cm.context_models[(0, 0)] = np.ones(2048) / 2048
+    with pytest.raises(NotImplementedError):  # alphabets end at 1024 symbols
         coder.cabac_encode(np.zeros((1, 2, 8), np.int32), cm)
     cm = coder.ContextModel(16)
     cm.context_models[(99, 0)] = np.ones(16) / 16

@@ -169,3 +169,54 @@ def test_cabac_compressor_shared_model_like_the_reference():
     assert len(comp.context_model.context_models) == len(model)
     e1, _ = fresh.compress(x2)
     assert e1 == O.encode_stream(fresh._codes_device(x2).cpu().numpy(), 64)["packed"] and e1 != encoded
+
+
+@pytest.mark.parametrize("container", ["packed", "reference"])
+def test_compare_compression_methods_report(container):
+    """The reference's per-method comparison (cabac_compression.py:800-881) over GPU outputs: same keys, the sizes the
+    reference would report (the 'reference' container counts bits as bytes, defect D1), ratios consistent."""
+    from image_compression_2_b200 import CABACCompressor, stats
+    enc, gen = StubEncoder().cuda(), StubGenerator().cuda()
+    comp = CABACCompressor(enc, gen, n_embeddings=256, container=container)
+    x = (torch.rand(1, 3, 64, 64, device="cuda") * 2 - 1)
+    rep = stats.compare_compression_methods(comp, x)
+    assert {"original", "png", "jpg", "hvae", "cabac", "hvae_ratio", "cabac_ratio", "cabac_vs_hvae"} <= set(rep)
+    cb = torch.linspace(-1, 1, 256).float().numpy()
+    ref = O.encode_stream(O.quantize_codebook(enc.means_for(1).numpy(), cb), 256, "repaired")
+    assert rep["hvae"] == 16 * 512 * 4                                    # the int32 codes of use_cabac=False (:484)
+    assert rep["cabac"] == (ref["nbits"] if container == "reference" else len(ref["packed"]))
+    assert rep["cabac_vs_hvae"] == rep["hvae"] / rep["cabac"]
+    assert abs(rep["coded_bits_per_symbol"] - ref["nbits"] / 8192) < 8 / 8192
+    assert rep["original"] == 3 * 64 * 64 and len(rep["table"]) == 5
+    if rep["png"] is not None:
+        assert rep["png"] > 0 and rep["jpg"] > 0
+    # the batch form: one table for a whole coded batch
+    from image_compression_2_b200 import LatentPipeline
+    from tests.helpers import synth_latents
+    pipe = LatentPipeline(n_symbols=256)
+    enc_b = pipe.encode(pipe.quantize(synth_latents("enc_like", 16, 99).cuda()))
+    tab = stats.method_table(enc_b)
+    assert tab["streams"] == 16 and [r["method"][:5] for r in tab["rows"]] == ["int32", "fixed", "arith"]
+    assert abs(tab["rows"][1]["ratio"] - 4.0) < 1e-9 and 3.9 < tab["rows"][2]["ratio"] < 4.1
+
+
+def test_gumbel_discretization_loads_a_reference_state_dict():
+    """Same parameter/buffer names as the reference layer (gumbel_softmax_compression.py:49-63), so the
+    `discretization_state_dict` of a reference checkpoint loads (cabac_compression.py:660-666)."""
+    from image_compression_2_b200 import GumbelSoftmaxDiscretization
+    ref_state = {"codebook": torch.linspace(-1, 1, 64).float(), "log_temperature": torch.ones(1) * np.log(0.7),
+                 "usage": torch.arange(64).float()}
+    for learnable in (True, False):
+        d = GumbelSoftmaxDiscretization(latent_dim=512, n_embeddings=64, learnable_temp=learnable).cuda()
+        assert set(d.state_dict()) == set(ref_state)
+        d.load_state_dict(ref_state)
+        assert abs(float(d.temperature) - 0.7) < 1e-6
+        assert torch.allclose(d.get_code_usage().cpu(), ref_state["usage"] / ref_state["usage"].sum())
+        d.update_temp(anneal_rate=0.1, min_temp=0.5)
+        assert float(d.log_temperature) < np.log(0.7)
+    d.train()
+    z = (torch.randn(2, 16, 512, device="cuda") * 0.3)
+    before = d.usage.clone()
+    deq, perplexity, idx = d(z)
+    assert d.usage.sum() == before.sum() + z.numel() and deq.shape == z.shape and idx.shape == (z.numel(),)
+    assert np.array_equal(idx.cpu().numpy(), O.quantize_codebook(z.cpu().numpy(), d.codebook.cpu().numpy()).reshape(-1))
