@@ -23,8 +23,9 @@ DEFAULT_MODE = "repaired"
 
 
 class DecodeFault(IndexError):
-    """The decoder produced symbol -1 (the reference carries on with negative-index wraparound,
-    cabac_compression.py:288-292); decoding stops at that symbol here."""
+    """Status 4 of ABI version 1 (decoding stopped at symbol -1).  Not raised any more: the kernels now follow the
+    reference through symbol -1 (NumPy negative indexing, cabac_compression.py:288-292,403) and the decoded array
+    simply holds -1 there, as the reference's does."""
 
 
 class ContextModel:

@@ -235,8 +235,10 @@ __device__ __forceinline__ LcListPos lc_list_locate(const LcWarp &W, int s)
     return r;
 }
 
-// ---- ContextModel.update_model (cabac_compression.py:119-144) on the sparse record
-__device__ __forceinline__ void lc_ctx_update(LcWarp &W, int s, const LcListPos &lp)
+// ---- ContextModel.update_model (cabac_compression.py:119-144) on the sparse record.  scale_self: the update that
+// follows a decoded symbol -1 (:403) -- s is then n-1 (NumPy's negative index) and, since `i != symbol` holds for every
+// i, the incremented element is scaled like all the others.
+__device__ __forceinline__ void lc_ctx_update(LcWarp &W, int s, const LcListPos &lp, bool scale_self = false)
 {
     if (!W.dense_ready) lc_dense_fresh(W);
     const bool present = lp.js >= 0;
@@ -264,13 +266,13 @@ __device__ __forceinline__ void lc_ctx_update(LcWarp &W, int s, const LcListPos 
     unsigned short *syms = (unsigned short *)(rec + 8 + 8 * ((size_t)1 << cl));
     if (W.lane == 0) __stcg((double *)rec, LC_DMUL(W.u, f));
     for (int j = W.lane; j < k; j += 32) {
-        const double v = (j == lp.js) ? p_new : LC_DMUL(W.lval[j], f);
+        const double v = (j == lp.js) ? (scale_self ? LC_DMUL(p_new, f) : p_new) : LC_DMUL(W.lval[j], f);
         const int jd = j + ((!present && j >= lp.ins) ? 1 : 0);
         __stcg(vals + jd, v);
         __stcg(syms + jd, W.lsym[j]);
     }
     if (W.lane == 0) {
-        if (!present) { __stcg(vals + lp.ins, p_new); __stcg(syms + lp.ins, (unsigned short)s); }
+        if (!present) { __stcg(vals + lp.ins, scale_self ? LC_DMUL(p_new, f) : p_new); __stcg(syms + lp.ins, (unsigned short)s); }
         __stcg(&W.slots[W.slot_idx], LC_SLOT_PACK(W.key + 1u, k_new, cl, off16));
     }
     __syncwarp();
@@ -285,6 +287,14 @@ __device__ __noinline__ LcInterval lc_exact_cum_enc(const double *dense, int s)
     for (int i = 0; i < s; i++) T = LC_DADD(T, dense[i]);
     out.sym = s; out.clo = T; out.chi = LC_DADD(T, dense[s]); out.exact = 1;
     return out;
+}
+
+// cum[n]: the sequential sum of the whole vector (what cumulative_probs[-1] reads after symbol -1, :292)
+__device__ __noinline__ double lc_exact_cum_total(const double *dense, int n)
+{
+    double T = 0.0;
+    for (int i = 0; i < n; i++) T = LC_DADD(T, dense[i]);
+    return T;
 }
 
 // np.searchsorted(cum, v, 'left') - 1 with the exact sums (cabac_compression.py:288)
@@ -578,7 +588,7 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
     int left = -1, my_out = 0;
     int pos = 0, r = 0, c = 0;
     for (; pos < W.total; pos++) {
-        const int up = (W.has_ctx && r > 0) ? (int)W.rows[((r - 1) & 1) * W.C + c] : -1;
+        const int up = (W.has_ctx && r > 0) ? (int)(short)W.rows[((r - 1) & 1) * W.C + c] : -1; // (a stored -1 stays -1)
         const uint32_t key = lc_ctx_key(W, c > 0 ? left : -1, up);
         lc_ctx_open(W, key);
 
@@ -605,7 +615,13 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
         if (!W.found) LC_STAT(fresh);
         if (!fast) { LC_STAT(search_fail); if (!W.dense_ready) lc_dense_fresh(W); iv = lc_exact_search_dec(W.dense, W.n, v); }
         if (iv.sym >= W.n) { W.status = LC_DEC_SYMBOL_OOB; break; }
-        if (iv.sym < 0) { W.status = LC_DEC_NEG_SYMBOL; break; }
+        if (iv.sym < 0) {
+            // symbol -1 (scaled value <= 0; only from an already inconsistent coder state) is not a fault in the
+            // reference: cumulative_probs[symbol] is NumPy's cum[-1] = cum[n], cumulative_probs[symbol+1] = cum[0] = 0
+            // (:291-292), -1 is stored, update_model(context, -1) runs, and decoding carries on (:400-403)
+            if (!W.dense_ready) lc_dense_fresh(W);
+            iv.clo = lc_exact_cum_total(W.dense, W.n); iv.chi = 0.0; iv.exact = 1;
+        }
         if (!lc_interval_apply(iv, W.delta, low, high)) {
             LC_STAT(interval_fail);
             if (!W.dense_ready) lc_dense_fresh(W);
@@ -630,10 +646,11 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
         if ((pos & 31) == 31) {
             const int p = pos - 31 + W.lane;
             out.store(p, my_out);
-            if (deq_out) deq_out[p] = __ldg(deq_table + my_out);
+            if (deq_out) deq_out[p] = __ldg(deq_table + (my_out < 0 ? my_out + W.n : my_out)); // codebook[-1]: last entry
         }
-        const LcListPos lp = lc_list_locate(W, s);
-        lc_ctx_update(W, s, lp);
+        const int su = s < 0 ? W.n - 1 : s;
+        const LcListPos lp = lc_list_locate(W, su);
+        lc_ctx_update(W, su, lp, s < 0);
         if (W.status != LC_OK) break;
         left = s;
         if (++c == W.C) { c = 0; if (++r == W.R) r = 0; }
@@ -643,7 +660,7 @@ __device__ __forceinline__ void lc_decode_stream(LcWarp &W, const unsigned char 
     {
         const int done = pos; // symbols [0,done) are valid; full chunks were already written
         const int p = (done & ~31) + W.lane;
-        if (p < done) { out.store(p, my_out); if (deq_out) deq_out[p] = __ldg(deq_table + my_out); }
+        if (p < done) { out.store(p, my_out); if (deq_out) deq_out[p] = __ldg(deq_table + (my_out < 0 ? my_out + W.n : my_out)); }
         for (int z = done + W.lane; z < W.total; z += 32) { out.store(z, 0); if (deq_out) deq_out[z] = 0.0f; }
     }
 }

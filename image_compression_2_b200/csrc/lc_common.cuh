@@ -17,7 +17,7 @@ enum {
     LC_ENC_BIT_OVERFLOW = 1, // reference: ValueError from bytearray.append (defect D3, verbatim mode)
     LC_DEC_SYMBOL_OOB = 2,   // reference: IndexError at cum[symbol+1]   (cabac_compression.py:291)
     LC_DEC_ZERO_RANGE = 3,   // reference: ZeroDivisionError             (cabac_compression.py:285)
-    LC_DEC_NEG_SYMBOL = 4,   // reference: symbol -1 (negative-index wraparound); decoding stops here
+    LC_DEC_NEG_SYMBOL = 4,   // (not produced since ABI 2: symbol -1 is followed through NumPy's negative indexing like the reference)
     LC_OUT_OVERFLOW = 5,     // per-stream output slot too small
     LC_BAD_SYMBOL = 6,       // input index outside [0, n_symbols)
     LC_POOL_OVERFLOW = 7     // internal scratch exhausted (sizing bug; never expected)

@@ -441,7 +441,7 @@ __device__ __forceinline__ int lcf_find_symbol(const LcFast &F, int state, int s
     }
     if (state == 0) { iv.clo = LC_DMUL((double)iv.sym, F.u0); iv.chi = LC_DMUL((double)(iv.sym + 1), F.u0); }
     if (iv.sym >= F.n) return LC_DEC_SYMBOL_OOB;
-    if (iv.sym < 0) return LC_DEC_NEG_SYMBOL;
+    if (iv.sym < 0) return LC_NEEDS_GENERIC; // symbol -1: the generic kernel follows the reference through it
     return LC_OK | flags;
 }
 

@@ -123,7 +123,7 @@ __device__ __forceinline__ void lcs_decode_stream(LcWarp &W, const LcStatefulTab
         v = LC_DSUB(v, 1e-10);
         LcInterval iv = lc_exact_search_dec(W.dense, W.n, v);
         if (iv.sym >= W.n) { W.status = LC_DEC_SYMBOL_OOB; lcs_close(W, T, key, false); break; }
-        if (iv.sym < 0) { W.status = LC_DEC_NEG_SYMBOL; lcs_close(W, T, key, false); break; }
+        if (iv.sym < 0) { iv.clo = lc_exact_cum_total(W.dense, W.n); iv.chi = 0.0; } // cum[-1], cum[0] (:291-292)
         lc_interval_apply(iv, 0.0, low, high);
         while ((high & LC_HALF) == (low & LC_HALF)) {
             low = (low << 1) & (LC_FULL - 1);

@@ -41,7 +41,7 @@ extern "C" {
 #define LC_STATUS_ENC_BIT_OVERFLOW 1 /* reference: ValueError, bytearray.append out of range (:193-197) */
 #define LC_STATUS_DEC_SYMBOL_OOB 2   /* reference: IndexError at cumulative_probs[symbol+1] (:291)       */
 #define LC_STATUS_DEC_ZERO_RANGE 3   /* reference: ZeroDivisionError (:285)                              */
-#define LC_STATUS_DEC_NEG_SYMBOL 4   /* reference: symbol -1 / negative-index wraparound (:288-292)      */
+#define LC_STATUS_DEC_NEG_SYMBOL 4   /* not produced since ABI 2: symbol -1 is followed like the reference  */
 #define LC_STATUS_OUT_OVERFLOW 5     /* per-stream output slot too small                                 */
 #define LC_STATUS_BAD_SYMBOL 6       /* input index outside [0,n_symbols) (reference: IndexError :343)   */
 #define LC_STATUS_POOL_OVERFLOW 7    /* internal scratch exhausted (never expected)                      */
@@ -138,7 +138,10 @@ int lc_encode_batch_t(const void *idx, int idx_bytes, int B, int imgs, int R, in
 /* cabac_decode, cabac_compression.py:363-406 (+ ArithmeticCoder :247-311).
  *   bytes, offsets[B], nbits[B]: stream b = ceil(nbits[b]/8) bytes at bytes + offsets[b];
  *              offsets[b] must be a multiple of 4 and the buffer readable to the next multiple of 4
- *   idx_out    int32 [B][imgs*R*C], zeros from the fault position on
+ *   idx_out    int32 [B][imgs*R*C], zeros from the fault position on.  A decoded symbol can be -1 (scaled value
+ *              <= 0, from an already inconsistent coder state): the reference does not fault there, it goes on with
+ *              NumPy's negative indexing (:288-292,403) and so do the kernels; -1 is stored (255 / 65535 in the
+ *              narrow index types) and dequantises to the LAST table entry, as codebook[-1] does
  *   deq_table / deq_out: optional fused dequantiser B (deq_out = deq_table[idx], fp32), may be NULL */
 int lc_decode_batch(const uint8_t *bytes, const int64_t *offsets, const int32_t *nbits, int B, int imgs, int R, int C,
                     int n_symbols, double adaptation_rate, int mode, int has_ctx, void *scratch,

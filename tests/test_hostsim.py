@@ -44,9 +44,6 @@ def _check(rec):
         assert dstatus[0] == ERR_TO_STATUS[str(rec["dec_error"][0])] and dfault[0] == k
         assert np.array_equal(dec.ravel()[:k], ref_dec.ravel()[:k])
         assert not dec.ravel()[k:].any()
-    elif dstatus[0] == 4:
-        k = dfault[0]
-        assert ref_dec.ravel()[k] == -1 and np.array_equal(dec.ravel()[:k], ref_dec.ravel()[:k])
     else:
         assert dstatus[0] == 0
         assert np.array_equal(dec, ref_dec)
@@ -170,8 +167,6 @@ def test_fast_decoder_matches_reference_vectors():
                 k = int(rec["dec_fault_index"])
                 assert st[0] == ERR_TO_STATUS[str(rec["dec_error"][0])] and fi[0] == k, name
                 assert np.array_equal(dec.ravel()[:k], ref.ravel()[:k]) and not dec.ravel()[k:].any(), name
-            elif st[0] == 4:
-                assert ref.ravel()[fi[0]] == -1, name
             else:
                 assert st[0] == 0 and np.array_equal(dec, ref), name
             ran += 1
@@ -244,8 +239,6 @@ def test_decoder_v2_matches_reference_vectors(ver):
                 k = int(rec["dec_fault_index"])
                 assert st[0] == ERR_TO_STATUS[str(rec["dec_error"][0])] and fi[0] == k, name
                 assert np.array_equal(dec.ravel()[:k], ref.ravel()[:k]) and not dec.ravel()[k:].any(), name
-            elif st[0] == 4:
-                assert ref.ravel()[fi[0]] == -1, name
             else:
                 assert st[0] == 0 and np.array_equal(dec, ref), name
             ran += 1
@@ -322,8 +315,6 @@ def test_small_decoder_matches_reference_vectors():
                 k = int(rec["dec_fault_index"])
                 assert st[0] == ERR_TO_STATUS[str(rec["dec_error"][0])] and fi[0] == k, name
                 assert np.array_equal(dec.ravel()[:k], ref.ravel()[:k]) and not dec.ravel()[k:].any(), name
-            elif st[0] == 4:
-                assert ref.ravel()[fi[0]] == -1, name
             else:
                 assert st[0] == 0 and np.array_equal(dec, ref), name
             ran += 1
@@ -356,3 +347,37 @@ def test_small_decoder_against_oracle_decoder():
     packed = O.encode_stream(imgs, 16)["packed"]
     dec, st, fi, _ = H.decode([packed], 16, (1,) + imgs.shape, 1, fast="small", grid=1)
     assert not st.any() and np.array_equal(dec[0], imgs)
+
+
+def test_symbol_minus_one_is_followed_like_the_reference():
+    """A decoded symbol -1 is not a fault in the reference (NumPy negative indexing, cabac_compression.py:288-292,403).
+    The state is nearly unreachable, so the oracle (pinned against the live reference on exactly this in
+    tests/test_oracle_vs_reference.py) searches random corruptions for streams that pass through it; the device code
+    -- generic kernel, and the fast kernels handing over to it -- must give the oracle's symbols, status, fault index."""
+    rng = np.random.default_rng(3)
+    hits = []
+    for trial in range(40000):
+        n = int(rng.choice([2, 4, 8, 16, 64, 256]))
+        shape = (1, int(rng.choice([1, 2, 4])), int(rng.choice([8, 16, 48])))
+        codes = rng.integers(0, n, shape).astype(np.int32)
+        mode = "verbatim" if trial % 3 else "repaired"
+        packed = bytearray(O.encode_stream(codes, n, "repaired")["packed"])
+        for _ in range(int(rng.integers(0, 4))):
+            packed[int(rng.integers(0, len(packed)))] = int(rng.integers(0, 256))
+        ref = O.decode_stream(bytes(packed), n, shape, mode)
+        k = ref["fault_index"] if ref["status"] else codes.size
+        if (ref["symbols"].ravel()[:k] == -1).any():
+            hits.append((n, shape, mode, bytes(packed), ref, k))
+    assert len(hits) >= 3
+    for n, shape, mode, packed, ref, k in hits[:10]:
+        cb = np.linspace(-1, 1, n).astype(np.float32)
+        dec, st, fi, deq = H.decode([packed], n, (1,) + shape, 0 if mode == "verbatim" else 1, codebook=cb)
+        assert st[0] == ref["status"] and (ref["status"] == 0 or fi[0] == k), (n, shape, mode)
+        assert np.array_equal(dec.ravel()[:k], ref["symbols"].ravel()[:k]), (n, shape, mode)
+        assert np.array_equal(deq.ravel()[:k], cb[ref["symbols"].ravel()[:k]])  # codebook[-1] is the last entry
+        if mode == "repaired" and shape[2] >= 4:
+            for fast in (True, "v2", "small"):
+                if (fast == "small" and n > 16) or (fast == "v2" and not _v2_ok(n, (1,) + shape[1:])):
+                    continue
+                dec, st, fi, _ = H.decode([packed], n, (1,) + shape, 1, fast=fast)
+                assert st[0] == ref["status"] and np.array_equal(dec.ravel()[:k], ref["symbols"].ravel()[:k]), (n, shape, fast)

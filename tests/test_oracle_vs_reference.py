@@ -20,12 +20,57 @@ def _compare(codes, n, mode):
     packed = R.pack_bits(bits)
     dec, derr = R.ref_decode(packed, n, codes.shape, mode)
     mine = O.decode_stream(packed, n, codes.shape, mode)
+    _same_decode(dec, derr, mine)
+
+
+def _same_decode(dec, derr, mine):
+    """Reference result (symbols, error) against the oracle's: same symbols, same fault class, same fault index."""
     if derr is not None:
-        assert mine["status"] == ERR_TO_STATUS[derr[0]] and mine["fault_index"] == derr[1]
-    elif mine["status"] == O.DEC_NEG_SYMBOL:
-        assert dec.ravel()[mine["fault_index"]] == -1
+        assert mine["status"] == ERR_TO_STATUS[derr[0]] and mine["fault_index"] == derr[1], (derr, mine["status"], mine["fault_index"])
+        k = derr[1]
+        assert np.array_equal(np.asarray(dec).ravel()[:k], mine["symbols"].ravel()[:k])
     else:
         assert mine["status"] == O.OK and np.array_equal(dec, mine["symbols"])
+
+
+def _corrupt_case(rng, trial):
+    n = int(rng.choice([2, 4, 8, 16, 64, 256]))
+    shape = (1, int(rng.choice([1, 2, 4])), int(rng.choice([8, 16, 48])))
+    if trial % 2:
+        codes = rng.integers(0, n, shape).astype(np.int32)
+    else:
+        codes = np.clip(np.round(rng.normal(n / 2, max(1, n / 16), shape)), 0, n - 1).astype(np.int32)
+    mode = "verbatim" if trial % 3 else "repaired"
+    packed = bytearray(O.encode_stream(codes, n, "repaired")["packed"])
+    for _ in range(int(rng.integers(0, 4))):
+        packed[int(rng.integers(0, len(packed)))] = int(rng.integers(0, 256))
+    if trial % 7 == 0:
+        packed = packed[: max(1, len(packed) // 2)]
+    return n, shape, mode, bytes(packed)
+
+
+def test_corrupt_streams_including_symbol_minus_one():
+    """Corrupted streams drive the decoder through its hazards.  One of them is symbol -1 (scaled value <= 0): the
+    reference does not fault there, it indexes cumulative_probs[-1] / [0], stores -1, updates probs[-1] and every
+    other element, and carries on (cabac_compression.py:288-292,403) -- the oracle follows it step by step.  The
+    state is nearly unreachable (a consistent decoder never has code < low; it takes the 33-bit values of the
+    verbatim mode), so the oracle first searches many random corruptions for streams that pass through it, and the
+    live reference is then run on those and on a sample of the others."""
+    rng = np.random.default_rng(3)
+    hits, others = [], []
+    for trial in range(40000):
+        n, shape, mode, packed = _corrupt_case(rng, trial)
+        mine = O.decode_stream(packed, n, shape, mode)
+        k = mine["fault_index"] if mine["status"] else int(np.prod(shape))
+        if (mine["symbols"].ravel()[:k] == -1).any():
+            hits.append((n, shape, mode, packed))
+        elif trial % 100 == 0:
+            others.append((n, shape, mode, packed))
+    assert len(hits) >= 3, len(hits)
+    for n, shape, mode, packed in hits[:12] + others:
+        dec, derr = R.ref_decode(packed, n, shape, mode)
+        mine = O.decode_stream(packed, n, shape, mode)
+        _same_decode(dec, derr, mine)
 
 
 def test_random_small_streams_both_modes():
@@ -86,8 +131,8 @@ def test_shared_model_across_calls_defect_d5():
         except (IndexError, ZeroDivisionError, ValueError) as e:
             derr = type(e).__name__
         mine, model2 = O.decode_stream_model(packed, n, a.shape, model)
-        if derr is None and mine["status"] == O.OK:
-            assert np.array_equal(np.asarray(dec, np.int32), mine["symbols"])
+        if derr is None:
+            assert mine["status"] == O.OK and np.array_equal(np.asarray(dec, np.int32), mine["symbols"])
             _same_model(_ref_model_dict(cm), model2)
         else:
-            assert derr is not None or mine["status"] == O.DEC_NEG_SYMBOL
+            assert mine["status"] == ERR_TO_STATUS[derr]
