@@ -264,8 +264,9 @@ __device__ __forceinline__ int lc_argmin_scan(const float *cb, int rep, int copy
     return bi;
 }
 
+#define LC_K2_THREADS 512 // one 32 KB table copy set per 512 threads: four blocks = 2048 threads per SM
 template <typename T>
-__global__ void __launch_bounds__(256) lc_quant_codebook_kernel(const float *__restrict__ z, long long n_elem,
+__global__ void __launch_bounds__(LC_K2_THREADS) lc_quant_codebook_kernel(const float *__restrict__ z, long long n_elem,
                                                                 const float *__restrict__ codebook, int n, int rep,
                                                                 int sorted, T *__restrict__ idx_out,
                                                                 float *__restrict__ deq_out)
@@ -421,8 +422,11 @@ __global__ void __launch_bounds__(32) lc_v2_tables_kernel(LcCoderCfg cfg, double
         lcv_decode_block<FN, FC, FR, OUTLINE>(cfg, vc, bytes, offsets, nbits, B, out, deq_table, deq_out, status,     \
                                               fault, scratch, tables, t2, lc_smem);                                    \
     }
-LC_V2_KERNEL(lc_decode_v2_kernel, 0, 0, 0, LC_V2_LAT_PER_SM, false)
-LC_V2_KERNEL(lc_decode_v2_w8_kernel, 256, 512, 16, LC_V2_LAT_PER_SM, false)
+#ifndef LCV_OPT_OUTLINE_LAT
+#define LCV_OPT_OUTLINE_LAT false
+#endif
+LC_V2_KERNEL(lc_decode_v2_kernel, 0, 0, 0, LC_V2_LAT_PER_SM, LCV_OPT_OUTLINE_LAT)
+LC_V2_KERNEL(lc_decode_v2_w8_kernel, 256, 512, 16, LC_V2_LAT_PER_SM, LCV_OPT_OUTLINE_LAT)
 LC_V2_KERNEL(lc_decode_v2_thr_kernel, 0, 0, 0, LC_V2_THR_PER_SM, true)
 LC_V2_KERNEL(lc_decode_v2_w8_thr_kernel, 256, 512, 16, LC_V2_THR_PER_SM, true)
 
@@ -841,13 +845,11 @@ static int64_t lc_scratch_need(const LcCoderCfg &cfg, int B)
     return need;
 }
 
-// grid of the elementwise kernels: one wave of resident blocks (a grid-stride loop gives every block the same share,
-// so blocks beyond the resident ones would run as a second, nearly empty wave: measured +40 % on K2, whose 32 KB of
-// shared memory fit seven blocks on an SM where eight were launched)
-static int lc_ew_grid(long long n_elem, size_t smem_per_block = 0)
+// grid of the elementwise kernels: one wave of resident blocks (a grid-stride loop gives every block the same share)
+static int lc_ew_grid(long long n_elem, size_t smem_per_block = 0, int threads = 256)
 {
-    long long blocks = (n_elem / 4 + 256 * LC_EW_UNROLL - 1) / (256 * LC_EW_UNROLL);
-    int per_sm = 8; // 2048 threads per SM
+    long long blocks = (n_elem / 4 + threads * LC_EW_UNROLL - 1) / (threads * LC_EW_UNROLL);
+    int per_sm = 2048 / threads; // 2048 threads per SM
     if (smem_per_block) {
         const int fit = (int)((227u * 1024u) / (smem_per_block + 1024u));
         per_sm = fit < per_sm ? (fit < 1 ? 1 : fit) : per_sm;
@@ -924,14 +926,14 @@ int lc_quantize_codebook_t(const float *z, int64_t n_elem, const float *codebook
     int rep = 32; // copies of the table in shared memory (one per bank while they fit 32 KB)
     while (rep > 1 && (size_t)n * rep * 4 > 32 * 1024) rep >>= 1;
     const size_t sm = (size_t)n * rep * 4;
-    const int grid = lc_ew_grid(n_elem, sm);
+    const int grid = lc_ew_grid(n_elem, sm, LC_K2_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
     if (idx_bytes == 4)
-        lc_quant_codebook_kernel<int><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, rep, so, (int *)idx_out, deq_out);
+        lc_quant_codebook_kernel<int><<<grid, LC_K2_THREADS, sm, st>>>(z, n_elem, codebook, n, rep, so, (int *)idx_out, deq_out);
     else if (idx_bytes == 2)
-        lc_quant_codebook_kernel<unsigned short><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, rep, so, (unsigned short *)idx_out, deq_out);
+        lc_quant_codebook_kernel<unsigned short><<<grid, LC_K2_THREADS, sm, st>>>(z, n_elem, codebook, n, rep, so, (unsigned short *)idx_out, deq_out);
     else
-        lc_quant_codebook_kernel<unsigned char><<<grid, 256, sm, st>>>(z, n_elem, codebook, n, rep, so, (unsigned char *)idx_out, deq_out);
+        lc_quant_codebook_kernel<unsigned char><<<grid, LC_K2_THREADS, sm, st>>>(z, n_elem, codebook, n, rep, so, (unsigned char *)idx_out, deq_out);
     LC_LAUNCHED();
     return 0;
 }

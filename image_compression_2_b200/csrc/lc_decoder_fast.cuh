@@ -87,6 +87,12 @@ static inline void lcv_sa_st16(lcv_sa a, int v) { *(volatile unsigned short *)a 
 static inline double lcv_sa_ldf64(lcv_sa a) { return *(const volatile double *)a; }
 static inline void lcv_sa_or32(lcv_sa a, uint32_t v) { atomicOr((uint32_t *)a, v); }
 static inline void lcv_sa_bar_arrive(lcv_sa b) { *(volatile unsigned long long *)b += 1ull; }
+// predicated forms (p != 0: do it): straight-line code on the GPU, no branch region around a one-lane store
+static inline void lcv_sa_st32_if(uint32_t p, lcv_sa a, uint32_t v) { if (p) lcv_sa_st32(a, v); }
+static inline void lcv_sa_st8_if(uint32_t p, lcv_sa a, int v) { if (p) lcv_sa_st8(a, v); }
+static inline void lcv_sa_or32_if(uint32_t p, lcv_sa a, uint32_t v) { if (p) lcv_sa_or32(a, v); }
+static inline void lcv_sa_bar_arrive_if(uint32_t p, lcv_sa b) { if (p) lcv_sa_bar_arrive(b); }
+static inline void lcv_stcg32_if(uint32_t p, uint32_t *g, uint32_t v) { if (p) *g = v; }
 #else
 typedef uint32_t lcv_sa;
 static __device__ __forceinline__ lcv_sa lcv_sa_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,6 +145,28 @@ static __device__ __forceinline__ void lcv_sa_or32(lcv_sa a, uint32_t v)
 static __device__ __forceinline__ void lcv_sa_bar_arrive(lcv_sa b) // release.cta
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
+}
+// predicated forms (p != 0: do it): straight-line code, no branch region (BSSY/BSYNC) around a one-lane store -- every
+// such region cost the decoder warp 25-40 cycles per symbol (profiles/r02_decoder_regions.md)
+static __device__ __forceinline__ void lcv_sa_st32_if(uint32_t p, lcv_sa a, uint32_t v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.volatile.shared.u32 [%1], %2; }" ::"r"(p), "r"(a), "r"(v));
+}
+static __device__ __forceinline__ void lcv_sa_st8_if(uint32_t p, lcv_sa a, int v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.volatile.shared.u8 [%1], %2; }" ::"r"(p), "r"(a), "r"(v));
+}
+static __device__ __forceinline__ void lcv_sa_or32_if(uint32_t p, lcv_sa a, uint32_t v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.shared.or.b32 [%1], %2; }" ::"r"(p), "r"(a), "r"(v) : "memory");
+}
+static __device__ __forceinline__ void lcv_sa_bar_arrive_if(uint32_t p, lcv_sa b) // release.cta
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q mbarrier.arrive.shared::cta.b64 _, [%1]; }" ::"r"(p), "r"(b) : "memory");
+}
+static __device__ __forceinline__ void lcv_stcg32_if(uint32_t p, uint32_t *g, uint32_t v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.cg.u32 [%1], %2; }" ::"r"(p), "l"(g), "r"(v) : "memory");
 }
 #endif
 

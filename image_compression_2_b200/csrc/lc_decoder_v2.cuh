@@ -39,6 +39,9 @@
 #define LCV_SENTINEL 0xFFFFFFFFu
 #define LCV_MAX_N 256
 #define LCV_MAX_C 4096
+#ifndef LCV_OPT_RINV
+#define LCV_OPT_RINV 0 // carry 1/range across symbols (see LcvRinv)
+#endif
 
 // launch description (host fills it: lcv_cfg_make)
 struct LcV2Cfg {
@@ -580,6 +583,23 @@ static __device__ __noinline__ LcvCold lcv_cold_symbol(LcFast *Fp, const char *p
     return lcv_exact_symbol(*Fp, pool, st, s1, gw, q0, q1, q2, q3, lo, hi, code);
 }
 
+// 1/range carried from symbol to symbol (LCV_OPT_RINV): the range after renormalisation is the range before it times
+// 2^t exactly (low gets zeros shifted in, high ones; an underflow step flips the same bit of both), so its reciprocal
+// is the reciprocal of the pre-renormalisation range with t subtracted from the exponent -- and that one can be
+// computed while the leading-zero counts of the renormalisation are still in flight, instead of at the head of the
+// next symbol's dependent chain (I2F + MUFU.RCP for fresh contexts, MUFU.RCP64H + four DFMA for the others).
+struct LcvRinv { double d; float f; };
+#ifdef LC_HOSTSIM
+static inline double lcv_scale_down(double r, int t) { return std::ldexp(r, -t); }
+static inline float lcv_scale_down_f(float r, int t) { return std::ldexp(r, -t); }
+#else
+static __device__ __forceinline__ double lcv_scale_down(double r, int t) // r * 2^-t, r in [2^-33, 2^-15], t <= 32
+{
+    return __hiloint2double(__double2hiint(r) - (t << 20), __double2loint(r));
+}
+static __device__ __forceinline__ float lcv_scale_down_f(float r, int t) { return __int_as_float(__float_as_int(r) - (t << 23)); }
+#endif
+
 // decode_symbol (:272-292) for one symbol: the symbol, and low/high after the interval update (before
 // renormalisation), from the context's state st and the data that state needs (gw: the context word for states 1
 // and 3; q0..q3: the inline record for state 2).  on_candidate(sym) is called as soon as a path has its candidate
@@ -589,7 +609,7 @@ template <bool OUTLINE, class OnCandidate>
 __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int st, uint32_t gw, const double2 &q0,
                                                  const double2 &q1, const double2 &q2, const double2 &q3, uint32_t lo,
                                                  uint32_t hi, uint32_t code, int &s, int &s1, uint32_t &nlo, uint32_t &nhi,
-                                                 int &fallback, OnCandidate on_candidate)
+                                                 int &fallback, OnCandidate on_candidate, const LcvRinv &rinv)
 {
     const int lane = F.lane, n = F.n;
     const double cfix = 1e-10;
@@ -604,7 +624,7 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
             // uniform model: cum[i] = i/n exactly, so range*cum is exact and everything is integer work.
             // With a = (code-low+1)*n and E = 1e-10*n*range, the symbol is the s with
             // s*range < a - E (+- 3e-4) <= (s+1)*range; candidate from a float quotient, checked with margins.
-            int cand = (int)((float)off * lcv_rcp_f32((float)rng1) * (float)n);
+            int cand = (int)((float)off * (LCV_OPT_RINV ? rinv.f : lcv_rcp_f32((float)rng1)) * (float)n);
             cand = cand > n - 1 ? n - 1 : cand; // (float)off rounds up to 2^32 at most: cand <= n
             on_candidate(cand);
             const unsigned long long below = (unsigned long long)(uint32_t)cand * rng1 + (uint32_t)cand; // cand*range
@@ -627,7 +647,7 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
             const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
             const int t = lcf_tab_index(F, s1);
             const double u = lcv_sa_ldf64(V.sa_tab + 8u * (uint32_t)t), ru = lcv_sa_ldf64(V.sa_tab + 256u + 8u * (uint32_t)t);
-            const double va = nd * lc_rcp_fast(rd) - cfix;
+            const double va = nd * (LCV_OPT_RINV ? rinv.d : lc_rcp_fast(rd)) - cfix;
             const double A0 = (double)s1 * u, B0 = A0 + F.P1;
             int sc;
             if (va < A0) sc = (int)(va * ru);
@@ -656,7 +676,7 @@ __device__ __forceinline__ int lcv_decode_symbol(LcFast &F, const LcV2 &V, int s
         const double rd = lc_ll2d_small((long long)rng1 + 1), nd = lc_ll2d_small((long long)off + 1);
         if (pre_ok) {
             const double ru = lc_rcp_fast(u);
-            const double va = nd * lc_rcp_fast(rd) - cfix;
+            const double va = nd * (LCV_OPT_RINV ? rinv.d : lc_rcp_fast(rd)) - cfix;
             // entries in ascending symbol order; approximate cum before (A) and after (B) each: stop at the first entry
             // whose upper bound reaches v.  Sequential with early exit -- a record holds 2-3 entries on average, and
             // the fully unrolled select form of this scan was a quarter of the warp's instructions on these symbols.
@@ -764,6 +784,76 @@ __device__ __forceinline__ void lcv_flush_row(const unsigned char *row, int firs
     }
 }
 
+// Compile-time switches of the decoder warp's loop skeleton (each measured on its own, tools/dec_variants.py;
+// profiles/r02_decoder_variants.txt):
+//   LCV_OPT_SPEC     request the next context's word AND record as soon as a candidate symbol exists, whatever the
+//                    context's state turns out to be (a wasted 68-byte L2 read for fresh contexts; the record of a
+//                    context seen twice or more arrives ~300 cycles earlier than when it is requested after the state
+//                    lookup -- the decoder warp waited 188 cycles per such symbol for it)
+//   LCV_OPT_PRED     the one-lane stores of the bookkeeping (row entry, state bits, context word, job post) as
+//                    predicated instructions instead of branch regions
+//   LCV_OPT_ROWLOOP  one loop per row inside a loop over rows: the row-end work leaves the per-symbol path
+#ifndef LCV_OPT_SPEC
+#define LCV_OPT_SPEC 0
+#endif
+#ifndef LCV_OPT_PRED
+#define LCV_OPT_PRED 0
+#endif
+#ifndef LCV_OPT_ROWLOOP
+#define LCV_OPT_ROWLOOP 1
+#endif
+//   LCV_OPT_UNROLL   symbols per trip of the row loop
+#ifndef LCV_OPT_UNROLL
+#define LCV_OPT_UNROLL 1
+#endif
+//   LCV_OPT_COLD     rarely executed parts of the loop (renormalisation by more than 32 bits, the wait for a pending
+//                    job) as real function calls: the loop body is ~25 KB of SASS against a 6 KB L0 / 32 KB L1.5
+//                    instruction cache, and every taken branch to a line that is not resident costs tens of cycles
+#ifndef LCV_OPT_COLD
+#define LCV_OPT_COLD 0
+#endif
+#define LCV_PRAGMA(x) _Pragma(#x)
+#define LCV_UNROLL(n) LCV_PRAGMA(unroll n)
+
+// lcv_post with predicated stores: posts the job when `doit` is set (warp-uniform), otherwise only passes through
+__device__ __forceinline__ void lcv_post_if(const LcV2 &V, LcvPost &P, int lane, bool doit, uint32_t key, uint32_t pay)
+{
+    const uint32_t j = P.njobs, slot = j & (LCV_RING - 1);
+    if (doit && j - P.done_seen >= (uint32_t)LCV_RING) { // (rare: the updater is ahead nearly always)
+        for (;;) {
+            P.done_seen = lcv_sa_ld32_acq(V.sa_ring_done);
+            if (j - P.done_seen < (uint32_t)LCV_RING) break;
+            LCV_SPIN();
+        }
+    }
+    const uint32_t p0 = (doit && lane == 0) ? 1u : 0u;
+    lcv_sa_st32_if(p0, V.sa_ring_key + 4u * slot, key);
+    lcv_sa_st32_if(p0, V.sa_ring_pay + 4u * slot, pay);
+    lcv_sa_bar_arrive_if(p0, V.sa_ring_bar + 8u * slot);
+    const bool mine = doit && (uint32_t)lane == slot;
+    P.my_key = mine ? key : P.my_key;
+    P.my_job = mine ? j : P.my_job;
+    P.njobs = j + (doit ? 1u : 0u);
+}
+
+// renormalisation by more than 32 bits (d + e > 32: a nearly empty range; only on streams about to fault)
+static __device__ __noinline__ uint32_t lcv_cold_renorm(LcvBits *b, uint32_t code, int d, int e, uint32_t em)
+{
+    const uint32_t b1 = lcv_br_take(*b, d);
+    code = __funnelshift_lc(0u, code, d) | b1;
+    const uint32_t b2 = lcv_br_take(*b, e);
+    return ((code << e) | b2) ^ em;
+}
+// the wait for a job on the next context that is still running, then that context's state
+static __device__ __noinline__ int lcv_cold_pend(uint32_t sa_ring_done, uint32_t sa_bits_word, uint32_t shift2, bool mine,
+                                                 uint32_t my_job)
+{
+    if (mine) while ((int)(lcv_sa_ld32(sa_ring_done) - (my_job + 1u)) < 0) LCV_SPIN();
+    __syncwarp();
+    LCV_FENCE();
+    return (int)((lcv_sa_ld32(sa_bits_word) >> shift2) & 3u);
+}
+
 template <bool OUTLINE>
 __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvPost &P, const unsigned char *src,
                                                   long long nbytes, LcIdxOut out, const float *deq_table, float *deq_out,
@@ -782,22 +872,23 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     uint32_t gw = 0u;  //   states 1, 3: the context's 4-byte word
     //   state 2: the inline record  u | val[6] | sym[6] k, copied to staging slot (pos & 1) in shared memory
     P.my_key = LCV_SENTINEL; // contexts of the previous stream are not this stream's
+    LcvRinv rinv; rinv.d = 2.3283064365386963e-10; rinv.f = 2.3283064365386963e-10f; // 1/2^32: the initial range
     LCP_DECL
     LCP_INIT();
-    for (; pos < F.total; pos++) {
+    // one symbol.  Returns false on a fault (status set).
+    auto one_symbol = [&](const bool last) -> bool {
         LCP_START();
         LCP_ROW(st); LCP_COUNT(st, 0);
         const uint32_t shift = (key & 15u) * 2u;
         // next position and the symbol above it (written at least C-1 >= 3 symbols ago): requested early.  At the
         // end of a row the next position is column 0 of the next row, under column 0 of this one.
-        const bool last = c + 1 == C;
         const bool has_up2 = last ? next_ok : up_ok;
         const int up2 = has_up2 ? lcv_sa_ld8(last ? row_cur : row_prev + (uint32_t)(c + 1)) : -1;
         // ---- decode_symbol (:272-292).  The next position's context key needs only the symbol: as soon as a path
         // has its candidate, the state word of that context is requested from shared memory, so the load overlaps
         // the bounds arithmetic.
         int s = 0, s1 = 0, fell_back = 0;
-        uint32_t nlo = 0u, nhi = 0u, key2 = 0u, w2 = 0u;
+        uint32_t nlo = 0u, nhi = 0u, key2 = 0u, w2 = 0u, spec_key = LCV_SENTINEL, gw2 = 0u;
         double2 q0 = {0.0, 0.0}, q1 = q0, q2 = q0, q3 = q0;
         if (st == 2) { // the record requested during the previous symbol
             const lcv_sa slot = V.sa_stage + 64u * (uint32_t)(pos & 1);
@@ -812,22 +903,40 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
                                                  LCV_USE_AFTER(up_, sym_); // keeps the consumer of the early load here
                                                  key2 = (uint32_t)((last ? -1 : sym_) + 1) * (uint32_t)(n + 1) + (uint32_t)(up_ + 1);
                                                  w2 = lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4));
-                                             });
-            if (fs != LC_OK) { status = fs; break; }
+                                                 if (LCV_OPT_SPEC && spec_key == LCV_SENTINEL) {
+                                                     // speculative: whatever the state is (valid unless a job on this
+                                                     // context is still running -- then it is requested again below)
+                                                     spec_key = key2;
+                                                     lcv_stage_copy(V.sa_stage + 64u * (uint32_t)((pos + 1) & 1), V.grec + (size_t)key2 * 64, lane);
+                                                     gw2 = __ldcg(V.gword + key2);
+                                                 }
+                                             }, rinv);
+            if (fs != LC_OK) { status = fs; return false; }
             if (fell_back) LCP_COUNT(4, st);
         }
         lo = nlo; hi = nhi;
+        if (LCV_OPT_RINV) { // reciprocal of the new range, before renormalisation scales it by 2^t
+            const uint32_t w = nhi - nlo; // range - 1
+            rinv.d = lc_rcp_fast(lc_ll2d_small((long long)w + 1));
+            rinv.f = lcv_rcp_f32((float)w);
+        }
         LCP_MARK(1);
         // ---- next position's context (get_context :78-117): the data its state needs is requested now (loaded
         // straight into the registers the next iteration reads) and arrives during renormalisation and write-back
-        if (lane == 0) lcv_sa_st8(row_cur + (uint32_t)c, s);
+        if (LCV_OPT_PRED) lcv_sa_st8_if(lane == 0 ? 1u : 0u, row_cur + (uint32_t)c, s);
+        else if (lane == 0) lcv_sa_st8(row_cur + (uint32_t)c, s);
         const uint32_t shift2 = (key2 & 15u) * 2u;
         int st2 = (int)((w2 >> shift2) & 3u);
         bool pend2 = key2 == key; // this symbol's own update of the same context comes first
+        const bool spec_ok = LCV_OPT_SPEC && spec_key == key2; // (a fallback may have changed the symbol)
+        if (LCV_OPT_SPEC && !spec_ok) lcv_stage_wait(); // the slot must not receive two copies at once
         if (st2 != 0 && !pend2) {
             // a job on that context among the last LCV_RING posted ones may still be running
             pend2 = __ballot_sync(LC_FULL_MASK, P.my_key == key2) != 0u;
-            if (!pend2) lcv_prefetch_staged(V, lane, st2, key2, gw, V.sa_stage + 64u * (uint32_t)((pos + 1) & 1));
+            if (!pend2) {
+                if (spec_ok) gw = gw2;
+                else lcv_prefetch_staged(V, lane, st2, key2, gw, V.sa_stage + 64u * (uint32_t)((pos + 1) & 1));
+            }
         }
         // ---- renormalise (:295-303) and underflow (:306-309): closed form, the d+e new bits come straight from
         // the top of the bit window
@@ -840,6 +949,10 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             if (t <= 32) {
                 code = __funnelshift_lc((uint32_t)(br.win >> 32), code, t) ^ em;
                 lcv_br_skip(br, t);
+            } else if (LCV_OPT_COLD) {
+                LcvBits tmp = br; // only the copy's address is taken: br itself stays in registers
+                code = lcv_cold_renorm(&tmp, code, d, e, em);
+                br = tmp;
             } else {
                 const uint32_t b1 = lcv_br_take(br, d);
                 code = __funnelshift_lc(0u, code, d) | b1;
@@ -848,35 +961,77 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
             }
             lo = __funnelshift_lc(0u, lo_d, e) & ~em;
             hi = __funnelshift_lc(0xffffffffu, hi_d, e) | em;
+            if (LCV_OPT_RINV) {
+                if (t <= 32 && hi - lo >= 0xffffu) { rinv.d = lcv_scale_down(rinv.d, t); rinv.f = lcv_scale_down_f(rinv.f, t); }
+                else { // (only on streams that are about to fault: the fast paths reject such a range anyway)
+                    rinv.d = lc_rcp_fast(lc_ll2d_small((long long)(hi - lo) + 1)); rinv.f = lcv_rcp_f32((float)(hi - lo));
+                }
+            }
         }
         LCP_MARK(2);
         // ---- this context's model moves on
-        if (st == 0) {
+        if (LCV_OPT_PRED) {
+            const uint32_t p0 = (st == 0 && lane == 0) ? 1u : 0u;
+            lcv_stcg32_if(p0, V.gword + key, (uint32_t)s);
+            lcv_sa_or32_if(p0, V.sa_bits + 4u * (key >> 4), 1u << shift);
+            lcv_post_if(V, P, lane, st != 0, key, LCV_PAY(s, st, s1));
+        } else if (st == 0) {
             if (lane == 0) { __stcg(V.gword + key, (uint32_t)s); lcv_sa_or32(V.sa_bits + 4u * (key >> 4), 1u << shift); }
         } else {
             lcv_post(V, P, lane, key, LCV_PAY(s, st, s1));
         }
         __syncwarp(); // lane 0's writes (row, word, state bits) are ordered before the other lanes' next reads
-        if (last) { // a row is complete: write it out
-            lcv_flush_row(V.rows + (row_cur - V.sa_rows), 0, C, out + (pos - (C - 1)), deq_table,
-                          deq_out ? deq_out + (pos - (C - 1)) : (float *)0, lane);
-            const uint32_t ab = lcv_sa_ld32(V.sa_abort);
-            if (ab) { status = (int)ab; pos++; c = C; break; }
-            const lcv_sa t_ = row_cur; row_cur = row_prev; row_prev = t_;
-            c = 0; r = r + 1 == F.R ? 0 : r + 1; // (the next image of the stream starts without a row above)
-            up_ok = r > 0; next_ok = r + 1 != F.R;
-        } else c++;
         if (pend2) {
             LCP_COUNT(6, st2);
             const bool mine = P.my_key == key2;
-            if (mine) while ((int)(lcv_sa_ld32(V.sa_ring_done) - (P.my_job + 1u)) < 0) LCV_SPIN();
-            __syncwarp();
-            LCV_FENCE();
-            st2 = (int)((lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4)) >> shift2) & 3u);
+            if (LCV_OPT_COLD) st2 = lcv_cold_pend(V.sa_ring_done, V.sa_bits + 4u * (key2 >> 4), shift2, mine, P.my_job);
+            else {
+                if (mine) while ((int)(lcv_sa_ld32(V.sa_ring_done) - (P.my_job + 1u)) < 0) LCV_SPIN();
+                __syncwarp();
+                LCV_FENCE();
+                st2 = (int)((lcv_sa_ld32(V.sa_bits + 4u * (key2 >> 4)) >> shift2) & 3u);
+            }
+            if (LCV_OPT_SPEC) lcv_stage_wait(); // (the speculative copy may still be landing in the slot)
             lcv_prefetch_staged(V, lane, st2, key2, gw, V.sa_stage + 64u * (uint32_t)((pos + 1) & 1));
         }
         key = key2; st = st2;
         LCP_MARK(3);
+        return true;
+    };
+    // the end of a row: write it out, see whether the updater gave up, swap the row buffers
+    auto row_done = [&]() -> bool {
+        lcv_flush_row(V.rows + (row_cur - V.sa_rows), 0, C, out + (pos + 1 - C), deq_table,
+                      deq_out ? deq_out + (pos + 1 - C) : (float *)0, lane);
+        const uint32_t ab = lcv_sa_ld32(V.sa_abort);
+        if (ab) { status = (int)ab; return false; }
+        const lcv_sa t_ = row_cur; row_cur = row_prev; row_prev = t_;
+        r = r + 1 == F.R ? 0 : r + 1; // (the next image of the stream starts without a row above)
+        up_ok = r > 0; next_ok = r + 1 != F.R;
+        return true;
+    };
+    bool done_row = false; // the fault position's row is partly decoded unless the fault came at a row end
+    if (LCV_OPT_ROWLOOP) {
+        bool ok = true;
+        while (ok && pos < F.total) {
+            LCV_UNROLL(LCV_OPT_UNROLL)
+            for (c = 0; c < C - 1; c++, pos++)
+                if (!one_symbol(false)) { ok = false; break; }
+            if (!ok) break;
+            if (!one_symbol(true)) break;      // (c == C - 1)
+            ok = row_done();
+            pos++; c = 0;
+            if (!ok) { done_row = true; break; }
+        }
+    } else {
+        for (; pos < F.total; pos++) {
+            const bool last = c + 1 == C;
+            if (!one_symbol(last)) break;
+            if (last) {
+                const bool ok = row_done();
+                c = 0;
+                if (!ok) { pos++; done_row = true; break; }
+            } else c++;
+        }
     }
     LCP_FLUSH();
     // release the updaters
@@ -887,7 +1042,7 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     {
         // symbols of the unfinished row (c of them; none when the stream ended on a row boundary), zeros after a fault
         const int done = pos;
-        const int part = (c < C) ? c : 0;
+        const int part = done_row ? 0 : c;
         if (part > 0) lcv_flush_row(V.rows + (row_cur - V.sa_rows), 0, part, out + (done - part), deq_table,
                                     deq_out ? deq_out + (done - part) : (float *)0, lane);
         for (int z = done + lane; z < F.total; z += 32) { out.store(z, 0); if (deq_out) deq_out[z] = 0.0f; }

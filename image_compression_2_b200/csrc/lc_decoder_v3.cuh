@@ -84,8 +84,10 @@ __device__ __forceinline__ void lc3_decoder(LcFast &F, const LcV2 &V, const LcV3
         // ---- decode_symbol (:272-292)
         int s = 0, s1 = 0, fell_back = 0;
         uint32_t nlo = 0u, nhi = 0u;
+        LcvRinv rv3; // (this variant computes the reciprocal of the range at the head of every symbol)
+        rv3.d = lc_rcp_fast(lc_ll2d_small((long long)(hi - lo) + 1)); rv3.f = lcv_rcp_f32((float)(hi - lo));
         const int fs = lcv_decode_symbol<false>(F, V, st, gw, q0, q1, q2, q3, lo, hi, code, s, s1, nlo, nhi, fell_back,
-                                         [](int) {});
+                                         [](int) {}, rv3);
         if (fs != LC_OK) { status = fs; break; }
         if (lane == 0) lcv_st_vol(M.sym, ((uint32_t)pos << 10) | (uint32_t)s); // the context warp takes it from here
         lo = nlo; hi = nhi;
