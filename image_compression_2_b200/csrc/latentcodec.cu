@@ -235,22 +235,28 @@ __device__ __forceinline__ int lc_argmin_sorted(const float *cb, int rep, int co
 }
 
 // Two lookups for WELL-SEPARATED ascending tables (every |entry| < 8, every gap > 1e-5 -- checked per block; true of any
-// linspace(-1, 1, n <= 4096) codebook): for |z| < 8 the rounded distances to neighbouring entries differ by far more
-// than an ulp, so ties only happen at exact midpoints, and once cb[k] <= z <= cb[k+1] is established the first minimum
-// is k or k+1 (k on a tie).  Below the first / above the last entry the answer is that entry.
-__device__ __forceinline__ int lc_argmin_separated(const float *cb, int rep, int copy, int n, float z, float guess_scale,
-                                                   float cb0, float cbl)
+// linspace(-1, 1, n <= 4096) codebook): the rounded distances to neighbouring entries then differ by far more than an
+// ulp, so ties only happen at exact midpoints, and once cb[k] <= z <= cb[k+1] is established the first minimum is k or
+// k+1 (k on a tie; fl(|z - hi|) = fl(hi - z), rounding is symmetric).  Everything else -- below the first or above the
+// last entry, NaN, a guess that is off by one -- leaves the hot loop.
+__device__ __noinline__ int lc_argmin_separated_edge(const float *cb, int rep, int copy, int n, float z, float guess_scale,
+                                                     float cb0, float cbl)
 {
-    if (fabsf(z) < 8.0f && n >= 2) {
-        float g = floorf((z - cb0) * guess_scale);
-        g = g < 0.0f ? 0.0f : (g > (float)(n - 2) ? (float)(n - 2) : g);
-        const int k = (int)g;
-        const float lo = LC_CB(k), hi = LC_CB(k + 1);
-        if (lo <= z && z <= hi) return lc_dist(z, hi) < lc_dist(z, lo) ? k + 1 : k;
+    if (fabsf(z) < 8.0f) {
         if (z < cb0) return 0;
         if (z > cbl) return n - 1;
     }
-    return lc_argmin_sorted(cb, rep, copy, n, z, guess_scale, cb0); // NaN, huge values, a guess that is off by one
+    return lc_argmin_sorted(cb, rep, copy, n, z, guess_scale, cb0);
+}
+__device__ __forceinline__ int lc_argmin_separated(const float *cb, int rep, int copy, int n, float z, float guess_scale,
+                                                   float cb0, float cbl)
+{
+    const int k = __float2int_rd((z - cb0) * guess_scale); // floor; NaN gives 0 and fails the bracket test below
+    if ((unsigned)k < (unsigned)(n - 1)) {
+        const float lo = LC_CB(k), hi = LC_CB(k + 1);
+        if (lo <= z && z <= hi) return __fsub_rn(hi, z) < __fsub_rn(z, lo) ? k + 1 : k;
+    }
+    return lc_argmin_separated_edge(cb, rep, copy, n, z, guess_scale, cb0, cbl);
 }
 
 __device__ __forceinline__ int lc_argmin_scan(const float *cb, int rep, int copy, int n, float z)
@@ -1026,7 +1032,7 @@ int lc_encode_batch_t(const void *idx, int idx_bytes, int B, int imgs, int R, in
         if (sparse_variant) {
             lc_v2_tables_kernel<<<cfg.n, 32, (size_t)cfg.n * 8, st>>>(cfg, tables);
             LC_LAUNCHED();
-            if (cfg.n <= LCS_T2_MAX_N && (long long)B * 1000 >= (long long)cfg.n * cfg.n) {
+            if (cfg.n > LCD_MAX_N && cfg.n <= LCS_T2_MAX_N && (long long)B * 1000 >= (long long)cfg.n * cfg.n) {
                 t2 = (char *)tables + ((lcv_tables_bytes(cfg.n) + 255) & ~(uint64_t)255);
                 const size_t t2_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;
                 lc_t2_kernel<<<lc_num_sms() * 4, 32 * LCS_BLOCK_WARPS, t2_smem, st>>>(cfg, tables, t2);

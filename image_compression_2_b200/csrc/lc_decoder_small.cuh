@@ -78,6 +78,19 @@ template <int N> __device__ __forceinline__ LcdCtx lcd_open(const double *vec, i
     return c;
 }
 
+// ContextModel.update_model (:119-144) on the lanes: lane l < N holds p[l] and gets its new value (lanes >= N: 0)
+template <int N> __device__ __forceinline__ double lcd_update(double p, int s, int lane, double rate)
+{
+    const bool valid = lane < N;
+    const double p_s = __shfl_sync(LC_FULL_MASK, p, s);
+    const double p_new = LC_DADD(p_s, LC_DMUL(rate, LC_DSUB(1.0, p_s)));
+    const double a = lane == s ? p_new : (valid ? p : 0.0);
+    const double tot = lcd_pairwise_total<N>(a, lane);
+    const double others = LC_DSUB(tot, p_new);
+    const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, p_new), others) : 0.0;
+    return lane == s ? p_new : (valid ? LC_DMUL(p, f) : 0.0);
+}
+
 template <int N>
 __device__ __forceinline__ void lcd_decode_stream(const LcCoderCfg &cfg, double *tab, unsigned char *rows, int lane,
                                                   const unsigned char *src, long long nbytes, LcIdxOut out,
@@ -145,13 +158,8 @@ __device__ __forceinline__ void lcd_decode_stream(const LcCoderCfg &cfg, double 
         }
         // ---- update_model (:119-144) on the lanes
         {
-            const double p_s = __shfl_sync(LC_FULL_MASK, M.p, s);
-            const double p_new = LC_DADD(p_s, LC_DMUL(rate, LC_DSUB(1.0, p_s)));
-            const double a = lane == s ? p_new : (valid ? M.p : 0.0);
-            const double tot = lcd_pairwise_total<N>(a, lane);
-            const double others = LC_DSUB(tot, p_new);
-            const double f = (others > 0.0) ? LC_DDIV(LC_DSUB(1.0, p_new), others) : 0.0;
-            if (valid) tab[(size_t)key * N + lane] = lane == s ? p_new : LC_DMUL(M.p, f);
+            const double pn = lcd_update<N>(M.p, s, lane, rate);
+            if (valid) tab[(size_t)key * N + lane] = pn;
         }
         __syncwarp(); // the row entry and the new vector are visible to every lane
         if (last) { // a row is complete: write it out
@@ -190,5 +198,33 @@ __device__ __forceinline__ void lcd_decode_block(const LcCoderCfg &cfg, const un
                              deq_out ? deq_out + (size_t)sidx * cfg.total : (float *)0, &st, &fi);
         if (lane == 0) { status[sidx] = st; fault[sidx] = fi; }
         __syncwarp();
+    }
+}
+
+// ---- the encoder's phase A for the same alphabets (lc_encoder_sparse.cuh calls it): one warp evolves ONE context's
+// dense vector through all its visits -- lane l holds p[l] in a register, the vector passes through a 128-byte
+// shared-memory image once per visit so that every lane can run the sequential np.cumsum up to its own element -- and
+// writes the exact (cum[s], cum[s+1]) of every visit from the third on (phase S already wrote the first two from
+// closed forms and the per-launch table).  The sparse-record phase A spent 376 warp instructions per symbol at 4 bits
+// (records of up to 16 entries, lane-parallel prefix sums with guard bands and exact re-evaluation); this is ~110.
+template <int N>
+__device__ __forceinline__ void lcd_enc_group(LcCodes codes, const uint32_t *skeys, const unsigned short *spos, int j0,
+                                              int total, double rate, double *image, double *ivs, int lane)
+{
+    const uint32_t key = skeys[j0];
+    double p = lane < N ? LC_DDIV(1.0, (double)N) : 0.0;
+    p = lcd_update<N>(p, codes[spos[j0]], lane, rate);
+    p = lcd_update<N>(p, codes[spos[j0 + 1]], lane, rate);
+    for (int t = j0 + 2;; t++) {
+        const int pos = spos[t];
+        const int s = codes[pos];
+        const bool last = (t + 1 >= total) || (skeys[t + 1] != key);
+        __syncwarp();
+        if (lane < N) image[lane] = p;
+        __syncwarp();
+        const LcdCtx M = lcd_open<N>(image, lane);
+        if (lane == s) { ivs[2 * pos] = M.clo; ivs[2 * pos + 1] = M.chi; }
+        if (last) break; // the update after the last visit is never read
+        p = lcd_update<N>(p, s, lane, rate);
     }
 }

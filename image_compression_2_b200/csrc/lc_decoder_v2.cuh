@@ -133,8 +133,28 @@ static __device__ __forceinline__ void lcv_bar_arrive(unsigned long long *b) // 
 // b: shared-window address.  The suspend-time hint lets the hardware keep the warp asleep until the phase completes
 // instead of returning every ~80 cycles (the retry loop was 17 instructions per symbol on the updater warp, competing
 // for issue slots with the decoder warps of the same sub-partition).
+// LCV_OPT_SLEEP > 0: poll with a plain test_wait and sleep that many nanoseconds between polls instead of relying on
+// try_wait's suspend hint (the hardware returns from it every ~80 cycles: the retry loop was 26 warp instructions per
+// symbol, 8-20 % of everything the kernel issues).  A job is only needed when its context recurs, so a pick-up delay
+// of a few hundred cycles is rarely on the decoder warp's path.
+#ifndef LCV_OPT_SLEEP
+#define LCV_OPT_SLEEP 0
+#endif
 static __device__ __forceinline__ void lcv_bar_wait(uint32_t b, uint32_t parity) // acquire.cta
 {
+#if LCV_OPT_SLEEP > 0
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(LCV_OPT_SLEEP);
+    }
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -144,6 +164,7 @@ static __device__ __forceinline__ void lcv_bar_wait(uint32_t b, uint32_t parity)
         "bra LCV_WAIT;\n"
         "LCV_DONE:\n"
         "}\n" ::"r"(b), "r"(parity), "r"(0x989680u) : "memory");
+#endif
 }
 #endif
 

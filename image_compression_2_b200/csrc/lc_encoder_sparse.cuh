@@ -20,6 +20,7 @@
 #pragma once
 #include "lc_encoder_par.cuh"
 #include "lc_decoder_v2.cuh"
+#include "lc_decoder_small.cuh"
 
 #define LCS_TASK_GROUPS 16
 #define LCS_T2_MAX_N 256 // the table of models after two visits (lcv_t2_block) is built for alphabets up to this size
@@ -104,6 +105,19 @@ __device__ __forceinline__ void lc_enc_phase_a_sparse_block(const LcCoderCfg &cf
         double *ivs = ivs_all + 2 * o;
         const int fb = first_bad[sidx];
         const int total = fb < cfg.total ? fb : cfg.total;
+        if (cfg.n <= LCD_MAX_N) { // small alphabets: dense vector on the lanes (lc_decoder_small.cuh)
+            for (int g = g_lo; g < g_hi; g++) {
+                const int j0 = glist[g];
+                switch (cfg.n) {
+                case 2: lcd_enc_group<2>(codes, skeys, spos, j0, total, cfg.rate, F.dense, ivs, F.lane); break;
+                case 4: lcd_enc_group<4>(codes, skeys, spos, j0, total, cfg.rate, F.dense, ivs, F.lane); break;
+                case 8: lcd_enc_group<8>(codes, skeys, spos, j0, total, cfg.rate, F.dense, ivs, F.lane); break;
+                default: lcd_enc_group<16>(codes, skeys, spos, j0, total, cfg.rate, F.dense, ivs, F.lane); break;
+                }
+                __syncwarp();
+            }
+            continue;
+        }
         for (int g = g_lo; g < g_hi; g++) {
             const int j0 = glist[g];
             const uint32_t key = skeys[j0];

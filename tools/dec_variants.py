@@ -13,9 +13,10 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
     "rowloop": (),
-    "outline": ("LCV_OPT_OUTLINE_LAT=true",),
-    "cold": ("LCV_OPT_COLD=1",),
-    "outline_cold": ("LCV_OPT_OUTLINE_LAT=true", "LCV_OPT_COLD=1"),
+    "sleep100": ("LCV_OPT_SLEEP=100",),
+    "sleep300": ("LCV_OPT_SLEEP=300",),
+    "sleep300_cold": ("LCV_OPT_SLEEP=300", "LCV_OPT_COLD=1"),
+    "sleep800": ("LCV_OPT_SLEEP=800",),
 }
 
 if len(sys.argv) > 1 and sys.argv[1] == "build":
