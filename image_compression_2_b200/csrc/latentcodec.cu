@@ -154,11 +154,23 @@ __global__ void __launch_bounds__(256) lc_quant_affine_kernel(const float *__res
     }
 }
 
+static __device__ __noinline__ float lc_qa_deq_cold(float q, float scale) { return lc_qa_deq(q, scale); }
+
+// Dequantiser A.  The value depends only on the index, and its IEEE division costs more instructions than the rest of
+// the kernel together (71 % of the HBM roofline when every element divides): for alphabets of at most 4096 symbols every
+// block tabulates the 2^bits values once in shared memory -- computed by the same three rounded operations -- and the
+// elements become one shared-memory lookup each; indices outside the table (int32 input may hold anything) and wider
+// alphabets are computed directly.
 template <typename T>
 __global__ void __launch_bounds__(256) lc_dequant_affine_kernel(const T *__restrict__ idx, long long n_elem, float scale,
-                                                                float *__restrict__ w_out)
+                                                                   int tab_n, float *__restrict__ w_out)
 {
     typedef typename LcIdx4<T>::V IV;
+    extern __shared__ float lc_deq_tab[];
+    for (int i = threadIdx.x; i < tab_n; i += blockDim.x) lc_deq_tab[i] = lc_qa_deq((float)i, scale);
+    __syncthreads();
+    auto deq = [&](int x) -> float { return (unsigned)x < (unsigned)tab_n ? lc_deq_tab[x] : lc_qa_deq_cold((float)x, scale); };
+    const unsigned tn = (unsigned)tab_n;
     const long long n4 = n_elem >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * LC_EW_UNROLL) {
@@ -174,13 +186,16 @@ __global__ void __launch_bounds__(256) lc_dequant_affine_kernel(const T *__restr
             if (i >= n4) break;
             const int4 x = LcIdx4<T>::unpack(v[u]);
             float4 o;
-            o.x = lc_qa_deq((float)x.x, scale); o.y = lc_qa_deq((float)x.y, scale);
-            o.z = lc_qa_deq((float)x.z, scale); o.w = lc_qa_deq((float)x.w, scale);
+            if (((unsigned)x.x < tn) & ((unsigned)x.y < tn) & ((unsigned)x.z < tn) & ((unsigned)x.w < tn)) {
+                o.x = lc_deq_tab[x.x]; o.y = lc_deq_tab[x.y]; o.z = lc_deq_tab[x.z]; o.w = lc_deq_tab[x.w];
+            } else {
+                o.x = deq(x.x); o.y = deq(x.y); o.z = deq(x.z); o.w = deq(x.w);
+            }
             __stcs(reinterpret_cast<float4 *>(w_out) + i, o);
         }
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride)
-        w_out[i] = lc_qa_deq((float)(int)idx[i], scale);
+        w_out[i] = deq((int)idx[i]);
 }
 
 // =================================================================================================
@@ -270,29 +285,59 @@ __device__ __forceinline__ int lc_argmin_scan(const float *cb, int rep, int copy
     return bi;
 }
 
-#define LC_K2_THREADS 512 // one 32 KB table copy set per 512 threads: four blocks = 2048 threads per SM
-template <typename T>
-__global__ void __launch_bounds__(LC_K2_THREADS) lc_quant_codebook_kernel(const float *__restrict__ z, long long n_elem,
-                                                                const float *__restrict__ codebook, int n, int rep,
-                                                                int sorted, T *__restrict__ idx_out,
-                                                                float *__restrict__ deq_out)
+// No lookup at all for NEAR-UNIFORM well-separated tables (true of any torch.linspace table; every block measures the
+// largest deviation `dev` of an entry from cb0 + k*step, in steps): t = (z - cb0) * (n-1)/span places z on the index
+// axis with an error below 3e-7 * n (three fp32 roundings at |t| <= n), the decision boundary between entries k and k+1
+// sits within dev of k + 0.5, and the rounded distances only tie within 1e-7 of it.  So whenever t is further than
+// band = 2 * (dev + 3e-7 * n) from every half-integer, rint(t) IS torch.argmin's answer (band = 1.7e-4 for
+// linspace(-1, 1, 256)); the values inside the band (0.03 %; a warp of 128 values calls the exact path every 25th
+// vector -- at 0.4 % it was every other vector and the "rare" path cost as much as the loop), everything outside the
+// table, NaN and +-inf take the two-lookup path, which decides exactly.  The rounding is done with the 1.5 * 2^23
+// constant: integer and fraction from two FADDs, nothing on the conversion pipe: ~11 instructions per value instead
+// of ~28 (profiles/r02_hbm_kernels.md).
+__device__ __forceinline__ bool lc_argmin_uniform(float z, float cb0, float guess_scale, int n, float frac_max, int &k)
+{
+    const float t = __fmul_rn(__fsub_rn(z, cb0), guess_scale);
+    const float tm = __fadd_rn(t, 12582912.0f);           // 1.5 * 2^23: the sum's low mantissa bits are rint(t)
+    k = __float_as_int(tm) - 0x4B400000;
+    const float frac = __fsub_rn(t, __fsub_rn(tm, 12582912.0f)); // t - rint(t), exact when k is inside the table
+    // inside the table (k in [0, n) <=> tm in [1.5*2^23, 1.5*2^23 + n) <=> t in [-0.5, n - 0.5]: NaN, +-inf and huge values
+    // fail here) and clear of the decision boundaries
+    return (fabsf(frac) <= frac_max) & ((unsigned)k < (unsigned)n);
+}
+// the four values of a vector whose no-lookup test failed for at least one of them (one vector in ~60)
+static __device__ __noinline__ int4 lc_k2_exact4(const float *cb, int rep, int copy, int n, float4 v, float guess_scale,
+                                                 float cb0, float cbl)
+{
+    int4 o;
+    o.x = lc_argmin_separated(cb, rep, copy, n, v.x, guess_scale, cb0, cbl);
+    o.y = lc_argmin_separated(cb, rep, copy, n, v.y, guess_scale, cb0, cbl);
+    o.z = lc_argmin_separated(cb, rep, copy, n, v.z, guess_scale, cb0, cbl);
+    o.w = lc_argmin_separated(cb, rep, copy, n, v.w, guess_scale, cb0, cbl);
+    return o;
+}
+
+#define LC_K2_THREADS 512 // one 32 KB table copy set per 512 threads
+struct LcK2Args {
+    const float *z; long long n_elem; const float *cb; int n, rep, copy;
+    float cb0, cbl, guess_scale, frac_max;
+    void *idx_out; float *deq_out;
+};
+// The vector loop of one search mode (0 full scan, 1 three-lookup search, 2 two-lookup search, 3 no lookup), one loop
+// per mode: with the mode tested inside one unrolled loop the four unrolled copies of the mode in use lay 15 KB apart
+// (the other modes' code between them) and the streaming loop did not stay in the instruction cache.  Inlined: as
+// real functions the kernel's register count became the largest mode's (95) and halved the occupancy.
+template <typename T, int MODE>
+static __device__ __forceinline__ void lc_k2_loop(const LcK2Args &a)
 {
     typedef typename LcIdx4<T>::V IV;
-    extern __shared__ float cb[];
-    __shared__ int s_separated;
-    if (threadIdx.x == 0) s_separated = 1;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n * rep; i += blockDim.x) cb[i] = codebook[i / rep];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float c = codebook[i];
-        if (!(fabsf(c) < 8.0f) || (i > 0 && !(c - codebook[i - 1] > 1e-5f))) s_separated = 0;
-    }
-    __syncthreads();
-    const int copy = (int)(threadIdx.x & (unsigned)(rep - 1));
-    const int mode = !sorted ? 0 : (s_separated ? 2 : 1); // full scan / three-lookup search / two-lookup search
-    const float cb0 = cb[0], cbl = cb[(n - 1) * rep], span = cbl - cb0;
-    const float guess_scale = (sorted && span > 0.0f) ? (float)(n - 1) / span : 0.0f;
-    const long long n4 = n_elem >> 2;
+    const float *cb = a.cb;
+    const int rep = a.rep, copy = a.copy, n = a.n;
+    const float cb0 = a.cb0, cbl = a.cbl, guess_scale = a.guess_scale, frac_max = a.frac_max;
+    const float *__restrict__ z = a.z;
+    T *__restrict__ idx_out = (T *)a.idx_out;
+    float *__restrict__ deq_out = a.deq_out;
+    const long long n4 = a.n_elem >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * LC_EW_UNROLL) {
         float4 v[LC_EW_UNROLL];
@@ -306,12 +351,18 @@ __global__ void __launch_bounds__(LC_K2_THREADS) lc_quant_codebook_kernel(const 
             const long long i = i0 + u * stride;
             if (i >= n4) break;
             int4 o;
-            if (mode == 2) {
+            if (MODE == 3) {
+                bool ok = lc_argmin_uniform(v[u].x, cb0, guess_scale, n, frac_max, o.x);
+                ok &= lc_argmin_uniform(v[u].y, cb0, guess_scale, n, frac_max, o.y);
+                ok &= lc_argmin_uniform(v[u].z, cb0, guess_scale, n, frac_max, o.z);
+                ok &= lc_argmin_uniform(v[u].w, cb0, guess_scale, n, frac_max, o.w);
+                if (!ok) o = lc_k2_exact4(cb, rep, copy, n, v[u], guess_scale, cb0, cbl);
+            } else if (MODE == 2) {
                 o.x = lc_argmin_separated(cb, rep, copy, n, v[u].x, guess_scale, cb0, cbl);
                 o.y = lc_argmin_separated(cb, rep, copy, n, v[u].y, guess_scale, cb0, cbl);
                 o.z = lc_argmin_separated(cb, rep, copy, n, v[u].z, guess_scale, cb0, cbl);
                 o.w = lc_argmin_separated(cb, rep, copy, n, v[u].w, guess_scale, cb0, cbl);
-            } else if (mode == 1) {
+            } else if (MODE == 1) {
                 o.x = lc_argmin_sorted(cb, rep, copy, n, v[u].x, guess_scale, cb0);
                 o.y = lc_argmin_sorted(cb, rep, copy, n, v[u].y, guess_scale, cb0);
                 o.z = lc_argmin_sorted(cb, rep, copy, n, v[u].z, guess_scale, cb0);
@@ -327,11 +378,75 @@ __global__ void __launch_bounds__(LC_K2_THREADS) lc_quant_codebook_kernel(const 
             }
         }
     }
-    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += stride) {
-        const int o = sorted ? lc_argmin_sorted(cb, rep, copy, n, z[i], guess_scale, cb0) : lc_argmin_scan(cb, rep, copy, n, z[i]);
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_elem; i += stride) {
+        const int o = MODE ? lc_argmin_sorted(cb, rep, copy, n, z[i], guess_scale, cb0) : lc_argmin_scan(cb, rep, copy, n, z[i]);
         idx_out[i] = (T)o;
         if (deq_out) deq_out[i] = LC_CB(o);
     }
+}
+
+// Search mode for a table: 0 full scan (unsorted) / 1 three-lookup search / 2 two-lookup search / 3 no lookup; every
+// block classifies the table itself (n <= 4096 values, L2-resident) while it fills its shared-memory copies.
+__device__ __forceinline__ int lc_k2_setup(const float *__restrict__ codebook, int n, int rep, int sorted, float *cb, LcK2Args &a)
+{
+    __shared__ int s_separated;
+    __shared__ unsigned s_dev; // largest deviation of an entry from cb0 + k*step, in steps (bit pattern of a float >= 0)
+    if (threadIdx.x == 0) { s_separated = 1; s_dev = 0u; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * rep; i += blockDim.x) cb[i] = codebook[i / rep];
+    {
+        const float c0 = codebook[0], step = (codebook[n - 1] - c0) / (float)(n > 1 ? n - 1 : 1);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float c = codebook[i];
+            if (!(fabsf(c) < 8.0f) || (i > 0 && !(c - codebook[i - 1] > 1e-5f))) s_separated = 0;
+            float dev = fabsf(c - (c0 + (float)i * step)) / step;
+            if (!(dev >= 0.0f && dev < 1.0f)) dev = 1.0f; // (NaN, step <= 0: not uniform)
+            atomicMax(&s_dev, __float_as_uint(dev));
+        }
+    }
+    __syncthreads();
+    a.cb = cb; a.n = n; a.rep = rep; a.copy = (int)(threadIdx.x & (unsigned)(rep - 1));
+    a.cb0 = cb[0]; a.cbl = cb[(n - 1) * rep];
+    const float span = a.cbl - a.cb0;
+    a.guess_scale = (sorted && span > 0.0f) ? (float)(n - 1) / span : 0.0f;
+    // half-width of the band around every half-integer that goes to the exact path: twice (the table's deviation + the
+    // three fp32 roundings of t, 3e-7 * n), see lc_argmin_uniform
+    const float band = 2.0f * (__uint_as_float(s_dev) + 3e-7f * (float)n) + 1e-6f;
+    a.frac_max = 0.5f - band;
+    const int s_uniform = band < 0.05f;
+    return !sorted ? 0 : (s_separated ? ((s_uniform && n >= 2 && n <= 1024) ? 3 : 2) : 1);
+}
+
+// Two kernels, launched one after the other for a sorted table; each classifies the table and returns at once when the
+// table is the other one's.  The no-lookup loop on its own needs 32 registers and no table per lane, so 2048 threads
+// per SM keep 128 KB of loads in flight; inside the general kernel (64 registers for the search modes, 32 KB of table
+// copies per block) it ran at half that occupancy and 65-76 % of the HBM roofline.
+template <typename T>
+__global__ void __launch_bounds__(256) lc_quant_codebook_uniform_kernel(const float *__restrict__ z, long long n_elem,
+                                                                           const float *__restrict__ codebook, int n, int rep,
+                                                                           T *__restrict__ idx_out, float *__restrict__ deq_out)
+{
+    extern __shared__ float cb[];
+    LcK2Args a;
+    a.z = z; a.n_elem = n_elem; a.idx_out = idx_out; a.deq_out = deq_out;
+    if (lc_k2_setup(codebook, n, rep, 1, cb, a) != 3) return;
+    lc_k2_loop<T, 3>(a);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LC_K2_THREADS) lc_quant_codebook_kernel(const float *__restrict__ z, long long n_elem,
+                                                                const float *__restrict__ codebook, int n, int rep,
+                                                                int sorted, T *__restrict__ idx_out,
+                                                                float *__restrict__ deq_out)
+{
+    extern __shared__ float cb[];
+    LcK2Args a;
+    a.z = z; a.n_elem = n_elem; a.idx_out = idx_out; a.deq_out = deq_out;
+    const int mode = lc_k2_setup(codebook, n, rep, sorted, cb, a);
+    if (mode == 3) return; // (lc_quant_codebook_uniform_kernel, launched just before, did it)
+    if (mode == 2) lc_k2_loop<T, 2>(a);
+    else if (mode == 1) lc_k2_loop<T, 1>(a);
+    else lc_k2_loop<T, 0>(a);
 }
 #undef LC_CB
 
@@ -907,12 +1022,14 @@ int lc_dequantize_affine_t(const void *idx, int idx_bytes, int64_t n_elem, int b
     if (n_elem == 0) return 0;
     if ((((uintptr_t)idx | (uintptr_t)w_out) & 15) != 0) return -22;
     const float scale = (float)((1 << bits) - 1);
-    const int grid = lc_ew_grid(n_elem);
+    const int tab_n = bits <= 12 ? (1 << bits) : 0; // values tabulated per block (lc_dequant_affine_kernel)
+    const size_t sm = (size_t)tab_n * 4;
+    const int grid = lc_ew_grid(n_elem, sm);
     cudaStream_t st = (cudaStream_t)stream;
-    if (idx_bytes == 4) lc_dequant_affine_kernel<int><<<grid, 256, 0, st>>>((const int *)idx, n_elem, scale, w_out);
+    if (idx_bytes == 4) lc_dequant_affine_kernel<int><<<grid, 256, sm, st>>>((const int *)idx, n_elem, scale, tab_n, w_out);
     else if (idx_bytes == 2)
-        lc_dequant_affine_kernel<unsigned short><<<grid, 256, 0, st>>>((const unsigned short *)idx, n_elem, scale, w_out);
-    else lc_dequant_affine_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char *)idx, n_elem, scale, w_out);
+        lc_dequant_affine_kernel<unsigned short><<<grid, 256, sm, st>>>((const unsigned short *)idx, n_elem, scale, tab_n, w_out);
+    else lc_dequant_affine_kernel<unsigned char><<<grid, 256, sm, st>>>((const unsigned char *)idx, n_elem, scale, tab_n, w_out);
     LC_LAUNCHED();
     return 0;
 }
@@ -934,6 +1051,19 @@ int lc_quantize_codebook_t(const float *z, int64_t n_elem, const float *codebook
     const size_t sm = (size_t)n * rep * 4;
     const int grid = lc_ew_grid(n_elem, sm, LC_K2_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
+    if (so && n >= 2 && n <= 1024) { // near-uniform tables (any linspace): the no-lookup kernel; others return at once
+        int rep_u = 8; // (its table copies only serve the exact path of the values near a decision boundary, and deq_out)
+        while (rep_u > 1 && (size_t)n * rep_u * 4 > 8 * 1024) rep_u >>= 1;
+        const size_t sm_u = (size_t)n * rep_u * 4;
+        const int grid_u = lc_ew_grid(n_elem, sm_u, 256);
+        if (idx_bytes == 4)
+            lc_quant_codebook_uniform_kernel<int><<<grid_u, 256, sm_u, st>>>(z, n_elem, codebook, n, rep_u, (int *)idx_out, deq_out);
+        else if (idx_bytes == 2)
+            lc_quant_codebook_uniform_kernel<unsigned short><<<grid_u, 256, sm_u, st>>>(z, n_elem, codebook, n, rep_u, (unsigned short *)idx_out, deq_out);
+        else
+            lc_quant_codebook_uniform_kernel<unsigned char><<<grid_u, 256, sm_u, st>>>(z, n_elem, codebook, n, rep_u, (unsigned char *)idx_out, deq_out);
+        LC_LAUNCHED();
+    }
     if (idx_bytes == 4)
         lc_quant_codebook_kernel<int><<<grid, LC_K2_THREADS, sm, st>>>(z, n_elem, codebook, n, rep, so, (int *)idx_out, deq_out);
     else if (idx_bytes == 2)

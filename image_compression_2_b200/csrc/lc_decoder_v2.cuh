@@ -1070,6 +1070,13 @@ __device__ __forceinline__ void lcv_decode_stream(LcFast &F, const LcV2 &V, LcvP
     }
 }
 
+// LCV_OPT_FLAT: the decoder warp runs the flat loop of lc_decoder_v2_flat.cuh (one dispatch, a branch-free tail, one
+// rarely taken region per symbol) instead of lcv_decode_stream above
+#ifndef LCV_OPT_FLAT
+#define LCV_OPT_FLAT 1
+#endif
+#include "lc_decoder_v2_flat.cuh"
+
 // Block entry: LCV_WARPS warps, persistent over streams.  FN/FC/FR > 0 fix the alphabet size and the image shape at
 // compile time (one image per stream): keys, shifts, margins and loop bounds become immediates on the serial chain.
 template <int FN, int FC, int FR, bool OUTLINE = false>
@@ -1078,7 +1085,13 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
                                                  const float *deq_table, float *deq_out, int *status, int *fault,
                                                  char *scratch, const double *tables, const char *t2, char *smem)
 {
-    const int warp = (int)(threadIdx.x >> 5);
+    // LCV_OPT_ROLE_SWAP: odd blocks run the decoder on their second warp.  Warps go to the SM's four schedulers by
+    // their slot number, a block's two warps take neighbouring slots, so with the decoder always on warp 0 every
+    // decoder warp of an SM lands on two of the four schedulers and they compete for issue slots with each other.
+#ifndef LCV_OPT_ROLE_SWAP
+#define LCV_OPT_ROLE_SWAP 0
+#endif
+    const int warp = (LCV_OPT_ROLE_SWAP && LCV_WARPS == 2) ? (int)((threadIdx.x >> 5) ^ (blockIdx.x & 1u)) : (int)(threadIdx.x >> 5);
     LcV2 V;
     V.sbits = (uint32_t *)(smem + vc.sm_bits);
     V.rows = (unsigned char *)(smem + vc.sm_rows);
@@ -1125,8 +1138,12 @@ __device__ __forceinline__ void lcv_decode_block(const LcCoderCfg &cfg, const Lc
         if (warp == 0) {
             int fi = 0, st = 0;
             const long long nby = ((long long)nbits[sidx] + 7) >> 3;
-            lcv_decode_stream<OUTLINE>(F, V, P, bytes + offsets[sidx], nby, out + (size_t)sidx * cfg.total, deq_table,
-                              deq_out ? deq_out + (size_t)sidx * cfg.total : (float *)0, &st, &fi);
+            if (LCV_OPT_FLAT)
+                lcv_decode_stream_flat<OUTLINE>(F, V, P, bytes + offsets[sidx], nby, out + (size_t)sidx * cfg.total, deq_table,
+                                                deq_out ? deq_out + (size_t)sidx * cfg.total : (float *)0, &st, &fi);
+            else
+                lcv_decode_stream<OUTLINE>(F, V, P, bytes + offsets[sidx], nby, out + (size_t)sidx * cfg.total, deq_table,
+                                           deq_out ? deq_out + (size_t)sidx * cfg.total : (float *)0, &st, &fi);
             if (F.lane == 0) { status[sidx] = st; fault[sidx] = fi; }
         } else {
             lcv_updater(F, V, ujob);

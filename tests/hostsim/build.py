@@ -14,6 +14,7 @@ SRCS = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "cuda_emul.h"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_par.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_fast.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v2.cuh"),
+        os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v2_flat.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_v3.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_decoder_small.cuh"),
         os.path.join(ROOT, "image_compression_2_b200", "csrc", "lc_encoder_sparse.cuh"),

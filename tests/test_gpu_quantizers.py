@@ -88,3 +88,49 @@ def test_cpu_tensor_is_refused():
     from image_compression_2_b200 import codec
     with pytest.raises(RuntimeError):
         codec.quantize_affine(torch.zeros(16), 8)
+
+
+@pytest.mark.parametrize("n", [2, 16, 64, 256, 1024])
+def test_quantiser_b_decision_boundaries(n):
+    """Quantiser B's no-lookup path (near-uniform tables) must hand every value near a decision boundary to the exact
+    path: every midpoint of neighbouring entries, +-1..3 ulps and +-1e-3..3e-3 of a step around it, the entries
+    themselves, values just outside the table, huge values, specials; int32 / uint16 / uint8 index outputs."""
+    from image_compression_2_b200 import codec
+    cb = torch.linspace(-1, 1, n).float().numpy()
+    mid = ((cb[:-1].astype(np.float64) + cb[1:].astype(np.float64)) / 2).astype(np.float32)
+    step = np.float32(2.0 / (n - 1))
+    pts = [cb, mid]
+    for k in (1, 2, 3):
+        up, dn = mid.copy(), mid.copy()
+        for _ in range(k):
+            up = np.nextafter(up, np.float32(np.inf)); dn = np.nextafter(dn, np.float32(-np.inf))
+        pts += [up, dn]
+    for f in (1e-3, 1.9e-3, 2.1e-3, 3e-3, 0.4, 0.49, 0.499):
+        pts += [mid + np.float32(f) * step, mid - np.float32(f) * step, cb + np.float32(f) * step, cb - np.float32(f) * step]
+    pts.append(np.array([-1.0000001, 1.0000001, -1.5, 1.5, -7.9, 7.9, -8.1, 8.1, 1e9, -1e9, 3e38, -3e38, np.inf, -np.inf,
+                         np.nan, 0.0, -0.0, 1e-30], np.float32))
+    rng = np.random.default_rng(n)
+    pts.append(rng.uniform(-1.2, 1.2, 20000).astype(np.float32))
+    z = np.concatenate(pts).astype(np.float32)
+    z = np.concatenate([z, z[: (-len(z)) % 4 + 1]])  # ragged tail
+    ref = O.quantize_codebook(z, cb)
+    zg, cbg = torch.from_numpy(z).cuda(), torch.from_numpy(cb).cuda()
+    for dt in (torch.int32, torch.int16, torch.uint8):
+        if dt == torch.uint8 and n > 256:
+            continue
+        idx, deq = codec.quantize_codebook(zg, cbg, want_deq=True, idx_dtype=dt)
+        got = idx.cpu().numpy().astype(np.int64) & (0xFFFF if dt == torch.int16 else 0xFFFFFFFF if dt == torch.int32 else 0xFF)
+        assert np.array_equal(got, ref.astype(np.int64)), (n, dt, np.flatnonzero(got != ref)[:8], z[got != ref][:8])
+        assert _eq_f32(deq.cpu().numpy(), cb[ref])
+
+
+def test_dequantiser_a_table_and_out_of_table_indices():
+    """Dequantiser A tabulates the 2^bits values per block; int32 indices outside the table take the arithmetic."""
+    from image_compression_2_b200 import codec
+    rng = np.random.default_rng(5)
+    for bits in (1, 4, 8, 10, 12, 13, 16):
+        hi = (1 << bits) - 1
+        idx = np.concatenate([np.arange(0, min(hi, 5000) + 1), rng.integers(0, hi + 1, 10001),
+                              np.array([-1, -5, hi + 1, hi + 100, 1 << 20, -(1 << 20)])]).astype(np.int32)
+        got = codec.dequantize_affine(torch.from_numpy(idx).cuda(), bits).cpu().numpy()
+        assert _eq_f32(got, O.dequantize_affine(idx, bits)), bits

@@ -12,19 +12,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
-    "rowloop": (),
-    "sleep100": ("LCV_OPT_SLEEP=100",),
-    "sleep300": ("LCV_OPT_SLEEP=300",),
-    "sleep300_cold": ("LCV_OPT_SLEEP=300", "LCV_OPT_COLD=1"),
-    "sleep800": ("LCV_OPT_SLEEP=800",),
+    "old": ("LCV_OPT_FLAT=0",),
+    "flat": (),
+    "flat_renorm2": ("LCVF_RENORM2=1",),
+    "flat_nosync": ("LCVF_NO_SYNCWARP=1",),
+    "flat_swap": ("LCV_OPT_ROLE_SWAP=1",),
+    "old_swap": ("LCV_OPT_FLAT=0", "LCV_OPT_ROLE_SWAP=1"),
+    "flat_all": ("LCVF_RENORM2=1", "LCVF_NO_SYNCWARP=1", "LCV_OPT_ROLE_SWAP=1"),
 }
 
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     from image_compression_2_b200 import build
     os.makedirs(VDIR, exist_ok=True)
     extra = tuple(sys.argv[2:])
-    for name, defs in VARIANTS.items():
-        print(build.build_library(out=os.path.join(VDIR, "lib_%s.so" % name), defines=defs + extra))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(4) as ex:
+        for r in ex.map(lambda kv: build.build_library(out=os.path.join(VDIR, "lib_%s.so" % kv[0]), defines=kv[1] + extra),
+                        VARIANTS.items()):
+            print(r)
     sys.exit(0)
 
 if len(sys.argv) > 1 and sys.argv[1] == "run":
