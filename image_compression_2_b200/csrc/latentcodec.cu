@@ -387,15 +387,17 @@ static __device__ __forceinline__ void lc_k2_loop(const LcK2Args &a)
 
 // Search mode for a table: 0 full scan (unsorted) / 1 three-lookup search / 2 two-lookup search / 3 no lookup; every
 // block classifies the table itself (n <= 4096 values, L2-resident) while it fills its shared-memory copies.
-__device__ __forceinline__ int lc_k2_setup(const float *__restrict__ codebook, int n, int rep, int sorted, float *cb, LcK2Args &a)
+// `only_if`: return at once with the mode when it differs (no table copies filled): -1 = fill for any mode but 3.
+__device__ __forceinline__ int lc_k2_setup(const float *__restrict__ codebook, int n, int rep, int sorted, int only_if, float *cb,
+                                           LcK2Args &a)
 {
     __shared__ int s_separated;
     __shared__ unsigned s_dev; // largest deviation of an entry from cb0 + k*step, in steps (bit pattern of a float >= 0)
     if (threadIdx.x == 0) { s_separated = 1; s_dev = 0u; }
     __syncthreads();
-    for (int i = threadIdx.x; i < n * rep; i += blockDim.x) cb[i] = codebook[i / rep];
+    const float c0 = codebook[0], cl = codebook[n - 1], span = cl - c0;
     {
-        const float c0 = codebook[0], step = (codebook[n - 1] - c0) / (float)(n > 1 ? n - 1 : 1);
+        const float step = span / (float)(n > 1 ? n - 1 : 1);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const float c = codebook[i];
             if (!(fabsf(c) < 8.0f) || (i > 0 && !(c - codebook[i - 1] > 1e-5f))) s_separated = 0;
@@ -405,16 +407,18 @@ __device__ __forceinline__ int lc_k2_setup(const float *__restrict__ codebook, i
         }
     }
     __syncthreads();
-    a.cb = cb; a.n = n; a.rep = rep; a.copy = (int)(threadIdx.x & (unsigned)(rep - 1));
-    a.cb0 = cb[0]; a.cbl = cb[(n - 1) * rep];
-    const float span = a.cbl - a.cb0;
-    a.guess_scale = (sorted && span > 0.0f) ? (float)(n - 1) / span : 0.0f;
     // half-width of the band around every half-integer that goes to the exact path: twice (the table's deviation + the
     // three fp32 roundings of t, 3e-7 * n), see lc_argmin_uniform
     const float band = 2.0f * (__uint_as_float(s_dev) + 3e-7f * (float)n) + 1e-6f;
+    const int mode = !sorted ? 0 : (s_separated ? ((band < 0.05f && n >= 2 && n <= 1024) ? 3 : 2) : 1);
+    if (only_if >= 0 ? mode != only_if : mode == 3) return mode;
+    for (int i = threadIdx.x; i < n * rep; i += blockDim.x) cb[i] = codebook[i / rep];
+    __syncthreads();
+    a.cb = cb; a.n = n; a.rep = rep; a.copy = (int)(threadIdx.x & (unsigned)(rep - 1));
+    a.cb0 = c0; a.cbl = cl;
+    a.guess_scale = (sorted && span > 0.0f) ? (float)(n - 1) / span : 0.0f;
     a.frac_max = 0.5f - band;
-    const int s_uniform = band < 0.05f;
-    return !sorted ? 0 : (s_separated ? ((s_uniform && n >= 2 && n <= 1024) ? 3 : 2) : 1);
+    return mode;
 }
 
 // Two kernels, launched one after the other for a sorted table; each classifies the table and returns at once when the
@@ -422,14 +426,14 @@ __device__ __forceinline__ int lc_k2_setup(const float *__restrict__ codebook, i
 // per SM keep 128 KB of loads in flight; inside the general kernel (64 registers for the search modes, 32 KB of table
 // copies per block) it ran at half that occupancy and 65-76 % of the HBM roofline.
 template <typename T>
-__global__ void __launch_bounds__(256) lc_quant_codebook_uniform_kernel(const float *__restrict__ z, long long n_elem,
+__global__ void __launch_bounds__(256, 4) lc_quant_codebook_uniform_kernel(const float *__restrict__ z, long long n_elem,
                                                                            const float *__restrict__ codebook, int n, int rep,
                                                                            T *__restrict__ idx_out, float *__restrict__ deq_out)
 {
     extern __shared__ float cb[];
     LcK2Args a;
     a.z = z; a.n_elem = n_elem; a.idx_out = idx_out; a.deq_out = deq_out;
-    if (lc_k2_setup(codebook, n, rep, 1, cb, a) != 3) return;
+    if (lc_k2_setup(codebook, n, rep, 1, 3, cb, a) != 3) return;
     lc_k2_loop<T, 3>(a);
 }
 
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(LC_K2_THREADS) lc_quant_codebook_kernel(const 
     extern __shared__ float cb[];
     LcK2Args a;
     a.z = z; a.n_elem = n_elem; a.idx_out = idx_out; a.deq_out = deq_out;
-    const int mode = lc_k2_setup(codebook, n, rep, sorted, cb, a);
+    const int mode = lc_k2_setup(codebook, n, rep, sorted, -1, cb, a);
     if (mode == 3) return; // (lc_quant_codebook_uniform_kernel, launched just before, did it)
     if (mode == 2) lc_k2_loop<T, 2>(a);
     else if (mode == 1) lc_k2_loop<T, 1>(a);

@@ -37,7 +37,7 @@
 //   LCVF_NO_SYNCWARP     no __syncwarp() between lane 0's shared-memory stores and the other lanes' later loads: the
 //                        warp is converged and its shared-memory instructions execute in program order
 #ifndef LCVF_RENORM2
-#define LCVF_RENORM2 0
+#define LCVF_RENORM2 1
 #endif
 #ifndef LCVF_NO_SYNCWARP
 #define LCVF_NO_SYNCWARP 0

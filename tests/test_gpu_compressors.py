@@ -141,6 +141,31 @@ def test_pipeline_host_roundtrip():
         assert res["h2d_bytes"] > lat.numel() * 4 and res["d2h_bytes"] > lat.numel() * 4
 
 
+def test_pipeline_host_stream_of_batches():
+    """roundtrip_host_stream: different batches in flight at once (two and three slots; a size hint that is too small)
+    give, batch by batch, what the oracle says."""
+    from image_compression_2_b200 import LatentPipeline
+    from tests.helpers import synth_latents
+    kinds = ["enc_like", "wide", "enc_like", "uniform", "hier", "enc_like", "wide"]
+    batches = [synth_latents(k, 24 if i % 2 else 32, 900 + i).pin_memory() for i, k in enumerate(kinds)]
+    for depth, hint in ((2, 0), (3, 0), (2, 100)):
+        pipe = LatentPipeline(n_symbols=256)
+        pipe._bytes_hint = hint  # 100: too small for any stream -- the batches in flight are redone one at a time
+        cb = pipe.codebook.cpu().numpy()
+        seen = 0
+        for lat, res in zip(batches, pipe.roundtrip_host_stream(batches, depth=depth)):
+            idx = O.quantize_codebook(lat.numpy(), cb)
+            assert not res["enc_status"].numpy().any() and not res["dec_status"].numpy().any()
+            assert np.array_equal(res["deq"].numpy().view(np.uint32), cb[idx].view(np.uint32)), (depth, seen)
+            offs, nbits, blob = res["offsets"].numpy(), res["nbits"].numpy(), res["bytes"].numpy()
+            for b in (0, lat.shape[0] - 1):
+                ref = O.encode_stream(idx[b:b + 1], 256, "repaired")
+                assert nbits[b] == ref["nbits"]
+                assert blob[offs[b]:offs[b] + len(ref["packed"])].tobytes() == ref["packed"]
+            seen += 1
+        assert seen == len(batches)
+
+
 def test_bitrate_stats_of_a_coded_batch():
     from image_compression_2_b200 import LatentPipeline, stats
     from tests.helpers import synth_latents
