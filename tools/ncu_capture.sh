@@ -9,6 +9,7 @@ ncu --set full --clock-control none --profile-from-start off -o /tmp/r02_all pyt
 echo "ncu all rc=$?"
 python tools_ncu_summary.py /tmp/r02_all.ncu-rep gpurun_out/r02_ncu_all_kernels.md > gpurun_out/summary.log 2>&1
 ncu -i /tmp/r02_all.ncu-rep --page raw --csv > gpurun_out/r02_all_raw.csv 2>/dev/null
+python tools/make_kernel_facts.py gpurun_out/r02_all_raw.csv gpurun_out/r02_kernel_facts.json "profiles/r02_ncu_all_kernels.md (ncu --set full, B200, tools/ncu_all_kernels.py: config 2 = 1024 streams x 8192 symbols at 8 bits; throughput decoder at 8192 streams)" > gpurun_out/facts.log 2>&1
 python bench.py --steps 1 --warmup 3 --no-sweep --no-cpu-baseline > gpurun_out/plain_dec.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:lc_decode_v2_w8_kernel -s 3 -c 1 -o gpurun_out/r02_dec python bench.py --steps 1 --warmup 3 --no-sweep --no-cpu-baseline > gpurun_out/ncu_dec.log 2>&1
 echo "ncu dec rc=$?"
