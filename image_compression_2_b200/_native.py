@@ -49,6 +49,7 @@ ABI_VERSION = 2
 # `flags` of the _t entry points (include/latentcodec.h)
 FLAG_DEC_LATENCY_BUILD, FLAG_DEC_THROUGHPUT_BUILD, FLAG_DEC_GENERIC_SHAPE = 1, 2, 4
 FLAG_DEC_REGISTER_MODEL, FLAG_DEC_SERIAL, FLAG_ENC_SERIAL, FLAG_DEC_NO_SMALL = 8, 16, 32, 64
+FLAG_ENC_SORT_V1 = 128
 
 
 class NativeLibraryError(RuntimeError):

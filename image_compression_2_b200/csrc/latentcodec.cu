@@ -20,6 +20,7 @@
 #include "lc_decoder_v3.cuh"
 #endif
 #include "lc_encoder_sparse.cuh"
+#include "lc_encoder_sort.cuh"
 #include "lc_encoder_pack.cuh"
 #include "lc_stateful.cuh"
 
@@ -705,6 +706,17 @@ __global__ void __launch_bounds__(LC_SORT_THREADS) lc_enc_sort_kernel(LcCoderCfg
     if (threadIdx.x == 0) ngroups[blockIdx.x] = g_total;
 }
 
+// Phase S, second version (lc_encoder_sort.cuh): two-pass radix sort from warp primitives, 256 threads per stream
+__global__ void __launch_bounds__(LCS2_THREADS) lc_enc_sort2_kernel(LcCoderCfg cfg, LcCodes codes, uint32_t *skeys,
+                                                                    unsigned short *spos, int *__restrict__ first_bad,
+                                                                    unsigned short *__restrict__ glist,
+                                                                    int *__restrict__ ngroups, double *__restrict__ ivs,
+                                                                    const double *__restrict__ tables)
+{
+    extern __shared__ __align__(16) char lc_smem[];
+    lcs2_block(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs, tables, lc_smem);
+}
+
 #ifdef LC_DEBUG_VARIANTS // the dense warp-per-group phase A (4.1 ms on the benchmark against 1.3 ms): debug builds only
 __global__ void __launch_bounds__(256) lc_enc_phase_a_kernel(LcCoderCfg cfg, LcCodes codes, int B,
                                                              const uint32_t *__restrict__ skeys,
@@ -881,6 +893,7 @@ static void lc_prepare_device()
     const int dev = lc_cur_device();
     if (dev >= 0 && dev < LC_MAX_DEVICES && g_attrs_set[dev].load(std::memory_order_acquire)) return;
     cudaFuncSetAttribute(lc_enc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LcBlockSort::TempStorage));
+    cudaFuncSetAttribute(lc_enc_sort2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LCS2_SMEM);
     cudaFuncSetAttribute(lc_enc_phase_b2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(lc_enc_phase_a_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LCS_BLOCK_WARPS * 1024 * 8);
     cudaFuncSetAttribute(lc_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -1184,8 +1197,12 @@ int lc_encode_batch_t(const void *idx, int idx_bytes, int B, int imgs, int R, in
             int *ngroups = (int *)ws;                         ws += (size_t)nb * 4;
             unsigned int *task_counter = (unsigned int *)ws;
             const LcCodes codes = all_codes + (size_t)b0 * cfg.total;
-            lc_enc_sort_kernel<<<nb, LC_SORT_THREADS, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs,
-                                                           sparse_variant ? tables : (const double *)0);
+            if (flags & LC_FLAG_ENC_SORT_V1)
+                lc_enc_sort_kernel<<<nb, LC_SORT_THREADS, sort_smem, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs,
+                                                               sparse_variant ? tables : (const double *)0);
+            else
+                lc_enc_sort2_kernel<<<nb, LCS2_THREADS, LCS2_SMEM, st>>>(cfg, codes, skeys, spos, first_bad, glist, ngroups, ivs,
+                                                                 sparse_variant ? tables : (const double *)0);
             LC_LAUNCHED();
             if (sparse_variant) {
                 const size_t sp_smem = (size_t)LCS_BLOCK_WARPS * cfg.n * 8;

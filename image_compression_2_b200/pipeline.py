@@ -151,7 +151,7 @@ class LatentPipeline:
         return dict(bytes=bytes_host, offsets=offs_out, nbits=nbits_out, enc_status=status_out, deq=deq_host,
                     dec_status=st_host, h2d_bytes=h2d, d2h_bytes=d2h, chunks=chunks, compressed_bytes=used_total)
 
-    def _enqueue_trip(self, lat_host, st, ws, cap, bytes_seg, meta_host, deq_host, st_host):
+    def _enqueue_trip(self, lat_host, st, ws, cap, bytes_seg, meta_host, deq_host, st_host, dec_flags=0):
         """Enqueue one batch's whole trip on CUDA stream `st` (no host wait): latents up, quantise, encode, compressed
         bytes down into `bytes_seg` (at most `cap`) and up again, decode with the dequantised rows written straight
         into the pinned `deq_host`.  meta_host receives offsets[Bc+1] | nbits[Bc] | status[Bc]."""
@@ -178,7 +178,7 @@ class LatentPipeline:
             # (the decoder writes the dequantised rows straight into the pinned host buffer as it goes; a
             # stream cut short by the cap decodes garbage inside its own slot and is redone by the caller)
             _, _, dstatus, _ = self.decode(data_dev, meta_back[:Bc + 1], nbits_dev, Bc, ws, deq_out=deq_host,
-                                           want_idx=False, reuse_output=True)
+                                           want_idx=False, reuse_output=True, flags=dec_flags)
             st_host.copy_(dstatus, non_blocking=True)
 
     def _roundtrip_chunks(self, latents_host, bounds, caps, which, main, deq_host, st_host, meta_all, bytes_host):
@@ -203,7 +203,7 @@ class LatentPipeline:
         return redo
 
     # ---- streaming: several batches in flight ---------------------------------------------------
-    def roundtrip_host_stream(self, batches, depth=2):
+    def roundtrip_host_stream(self, batches, depth=2, dec_flags=0):
         """Generator over results (same dict as roundtrip_host, in order) for an iterable of pinned host batches,
         with up to `depth` batches in flight: every batch makes the same full trip as in roundtrip_host, on its own
         CUDA stream with its own workspace and pinned output buffers, so the host->device copy of the next batch's
@@ -215,11 +215,11 @@ class LatentPipeline:
         for k, lat in enumerate(batches):
             if len(pending) >= depth:
                 yield self._stream_collect(pending.popleft())
-            pending.append(self._stream_submit(lat, k % depth))
+            pending.append(self._stream_submit(lat, k % depth, dec_flags))
         while pending:
             yield self._stream_collect(pending.popleft())
 
-    def _stream_submit(self, latents_host, slot):
+    def _stream_submit(self, latents_host, slot, dec_flags=0):
         B = latents_host.shape[0]
         while len(self._stream_ctx) <= slot:
             self._stream_ctx.append((torch.cuda.Stream(device=self.device), codec.CoderWorkspace()))
@@ -233,7 +233,7 @@ class LatentPipeline:
                     bytes=self._pin(("s_bytes", slot, cap), (cap,), torch.uint8))
         with torch.cuda.device(self.device):
             st.wait_stream(torch.cuda.current_stream(self.device))
-            self._enqueue_trip(latents_host, st, ws, cap, bufs["bytes"], bufs["meta"], bufs["deq"], bufs["st"])
+            self._enqueue_trip(latents_host, st, ws, cap, bufs["bytes"], bufs["meta"], bufs["deq"], bufs["st"], dec_flags)
             ev = torch.cuda.Event()
             ev.record(st)
         return dict(lat=latents_host, B=B, cap=cap, ev=ev, **bufs)

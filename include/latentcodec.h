@@ -55,6 +55,7 @@ extern "C" {
 #define LC_FLAG_DEC_SERIAL 16           /* the generic serial decoder only                                            */
 #define LC_FLAG_ENC_SERIAL 32           /* the serial warp-per-stream encoder instead of the phase-split one          */
 #define LC_FLAG_DEC_NO_SMALL 64         /* not the dense shared-memory decoder of alphabets up to 32 symbols          */
+#define LC_FLAG_ENC_SORT_V1 128         /* phase S of the phase-split encoder with cub::BlockRadixSort (round 1)     */
 #define LC_FLAG_DEBUG_DEC_V3 256        /* builds with -DLC_DEBUG_VARIANTS only: three-warp decoder                   */
 #define LC_FLAG_DEBUG_ENC_DENSE_PHASE_A 512 /* builds with -DLC_DEBUG_VARIANTS only: dense warp-per-context phase A   */
 

@@ -89,7 +89,7 @@ def test_flags_select_kernels_without_changing_results():
     layout = codec.layout_independent(idx32.shape)
     dev_idx = torch.from_numpy(idx32).cuda().reshape(-1)
     refs = [O.encode_stream(idx32[b:b + 1], n, "repaired") for b in range(B)]
-    for eflags in (0, _native.FLAG_ENC_SERIAL):
+    for eflags in (0, _native.FLAG_ENC_SERIAL, _native.FLAG_ENC_SORT_V1):
         enc = codec.encode_batch(dev_idx, layout, n, flags=eflags)
         streams, nbits, status, _ = enc.to_host()
         assert not status.any()
