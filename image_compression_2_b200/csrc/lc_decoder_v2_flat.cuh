@@ -155,7 +155,9 @@ __device__ __forceinline__ void lcvf_ring_room(const LcV2 &V, LcvPost &P)
 
 #ifdef LC_HOSTSIM
 static inline int lcvf_clz(uint32_t x) { return x ? __clz((int)x) : 32; }
+static inline uint32_t lcvf_d2u(double x) { return (uint32_t)(long long)x; }
 #else
+static __device__ __forceinline__ uint32_t lcvf_d2u(double x) { return __double2uint_rz(x); } // x in [0, 2^32)
 static __device__ __forceinline__ int lcvf_clz(uint32_t x) // x == 0 gives a value above 32 (the caller's "rare" case)
 {
 #if LCVF_CLZ_FLOAT
@@ -260,8 +262,8 @@ __device__ __forceinline__ void lcv_decode_stream_flat(LcFast &F, const LcV2 &V,
             const double tgt = nd - cfix * rd; // ~ v*range; |error| < 3e-6 for range <= 2^32
             if (pre_ok && tgt - xl > 1e-5 && xh1 - tgt >= 1e-5) { // cum[sc] < v <= cum[sc+1], decided with margin
                 s = sc; done = true;
-                nlo = lo + (uint32_t)LC_D2LL(xl);
-                nhi = lo + (uint32_t)LC_D2LL(LC_DSUB(xh1, 1.0));
+                nlo = lo + lcvf_d2u(xl); // (both in [0, 2^32) here: 32-bit conversions, 19 cycles against 28)
+                nhi = lo + lcvf_d2u(LC_DSUB(xh1, 1.0));
                 lcvf_post(V, P, lane, key, LCV_PAY(s, 1, s1));
             }
         } else if (st == 2) {

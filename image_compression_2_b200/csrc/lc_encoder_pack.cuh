@@ -48,6 +48,12 @@ static __device__ __forceinline__ void lc_b1_wait_ahead() // all but the LC_B1_A
     asm volatile("cp.async.wait_group %0;" ::"n"(LC_B1_AHEAD) : "memory");
 }
 #endif
+// (uint32_t)int(x) for x in [-1, 2^32): Python's int() truncates toward zero; -1 (a collapsed interval) wraps
+#ifdef LC_HOSTSIM
+static inline uint32_t lc_b1_d2u(double x) { return (uint32_t)(long long)x; }
+#else
+static __device__ __forceinline__ uint32_t lc_b1_d2u(double x) { return x <= -1.0 ? 0xffffffffu : __double2uint_rz(x); }
+#endif
 __device__ __forceinline__ int lc_enc_b1_stream(int lane, double *pairs, int limit, char *smem)
 {
     uint32_t lo = 0u, hi = 0xffffffffu;
@@ -55,22 +61,28 @@ __device__ __forceinline__ int lc_enc_b1_stream(int lane, double *pairs, int lim
     const lcv_sa ring = lcv_sa_of(smem);
     const int nchunks = (limit + LC_B1_CHUNK - 1) / LC_B1_CHUNK;
     // one symbol of the recurrence
+    // The chain per symbol is what this kernel costs (one warp per stream, ~185 cycles per symbol in the first version):
+    // leading-zero counts from the exponent of an int->float conversion instead of FLO (lcvf_clz: 12 cycles against 24,
+    // twice per symbol), the underflow count from the unshifted words (two dependent instructions fewer), 32-bit
+    // double->unsigned conversions instead of 64-bit ones (19 cycles against 28).  int(range*c_hi - 1) is -1 when the
+    // interval has collapsed (range 0): that one value is kept by hand, everything else is in [0, 2^32).
 #define LC_B1_STEP(iv_, pos_)                                                                                       \
     do {                                                                                                            \
         /* encode_symbol (:220-224): high = low + int(range*c_hi - 1), low = low + int(range*c_lo) */               \
         const double rd_ = lc_ll2d_small((long long)hi - (long long)lo + 1); /* 0 when the interval has collapsed */ \
-        const long long ah_ = LC_D2LL(LC_DSUB(LC_DMUL(rd_, (iv_).y), 1.0));                                         \
-        const long long al_ = LC_D2LL(LC_DMUL(rd_, (iv_).x));                                                       \
-        hi = lo + (uint32_t)ah_;                                                                                    \
-        lo = lo + (uint32_t)al_;                                                                                    \
-        const int d_ = __clz((int)(lo ^ hi)); /* leading bits low and high share: that many bits are emitted */     \
-        const uint32_t lo_d_ = __funnelshift_lc(0u, lo, d_), hi_d_ = __funnelshift_lc(0xffffffffu, hi, d_);         \
-        const int e_ = __clz((int)~((lo_d_ & ~hi_d_) << 1)); /* underflow steps: low = 01.., high = 10.. */         \
+        const double xh_ = LC_DSUB(LC_DMUL(rd_, (iv_).y), 1.0), xl_ = LC_DMUL(rd_, (iv_).x);                        \
+        const uint32_t ah_ = lc_b1_d2u(xh_), al_ = lc_b1_d2u(xl_);                                                  \
+        hi = lo + ah_;                                                                                              \
+        lo = lo + al_;                                                                                              \
+        int d_ = lcvf_clz(lo ^ hi); /* leading bits low and high share: that many bits are emitted */               \
+        d_ = d_ > 32 ? 32 : d_;                                                                                     \
+        int e_ = lcvf_clz(~__funnelshift_lc(0u, lo & ~hi, d_ + 1)); /* underflow steps: low = 01.., high = 10.. */   \
+        e_ = e_ > 32 ? 32 : e_;                                                                                     \
         if (lane == 0)                                                                                              \
             rec[2 * (pos_)] = (unsigned long long)hi | ((unsigned long long)(uint32_t)(d_ | (e_ << 8)) << 32);      \
         const uint32_t em_ = e_ ? 0x80000000u : 0u;                                                                 \
-        lo = __funnelshift_lc(0u, lo_d_, e_) & ~em_;                                                                \
-        hi = __funnelshift_lc(0xffffffffu, hi_d_, e_) | em_;                                                        \
+        lo = __funnelshift_lc(0u, lo, d_ + e_) & ~em_; /* (counts above 32 clamp: zeros / ones, like two steps) */   \
+        hi = __funnelshift_lc(0xffffffffu, hi, d_ + e_) | em_;                                                      \
     } while (0)
 #define LC_B1_ISSUE(k_)                                                                                             \
     do {                                                                                                            \
