@@ -18,7 +18,7 @@ rows = list(csv.reader(open(raw)))
 h = rows[0]
 col = {k: i for i, k in enumerate(h)}
 WANT = {"lc_quant_codebook_uniform_kernel": 1024, "lc_quant_codebook_kernel": 1024, "lc_v2_tables_kernel": 1024,
-        "lc_t2_kernel": 1024, "lc_enc_sort_kernel": 1024, "lc_enc_phase_a_sparse_kernel": 1024,
+        "lc_t2_kernel": 1024, "lc_enc_sort_kernel": 1024, "lc_enc_sort2_kernel": 1024, "lc_enc_phase_a_sparse_kernel": 1024,
         "lc_enc_phase_b1_kernel": 1024, "lc_enc_phase_b2_kernel": 1024, "lc_scan_sizes_kernel": 1024,
         "lc_compact_kernel": 1024, "lc_decode_v2_w8_kernel": 1024, "lc_decode_v2_w8_thr_kernel": 8192}
 
