@@ -14,11 +14,8 @@ VDIR = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
     "old": ("LCV_OPT_FLAT=0",),
     "flat": (),
-    "flat_renorm2": ("LCVF_RENORM2=1",),
-    "flat_nosync": ("LCVF_NO_SYNCWARP=1",),
-    "flat_swap": ("LCV_OPT_ROLE_SWAP=1",),
-    "old_swap": ("LCV_OPT_FLAT=0", "LCV_OPT_ROLE_SWAP=1"),
-    "flat_all": ("LCVF_RENORM2=1", "LCVF_NO_SYNCWARP=1", "LCV_OPT_ROLE_SWAP=1"),
+    "flat_outline": ("LCV_OPT_OUTLINE_LAT=true",),
+    "flat_all": ("LCVF_NO_SYNCWARP=1", "LCV_OPT_ROLE_SWAP=1"),
 }
 
 if len(sys.argv) > 1 and sys.argv[1] == "build":
