@@ -42,10 +42,25 @@ def build_library(force=False, verbose=False, out=None, defines=()):
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build liblatentcodec.so")
-    cmd = ([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
-           ["-o", target + ".tmp"] + SOURCES)
-    subprocess.check_call(cmd)
-    os.replace(target + ".tmp", target)
+    # Several processes may get here at once (every rank under torchrun finds the library stale): one builds, the others
+    # wait on the lock and find it fresh; every build writes its own temporary file and renames it into place.
+    import fcntl
+    with open(target + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if out is None and not force and not needs_build():
+                return LIB
+            tmp = "%s.%d.tmp" % (target, os.getpid())
+            cmd = ([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+                   ["-o", tmp] + SOURCES)
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, target)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return target
 
 
