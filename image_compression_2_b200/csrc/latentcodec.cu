@@ -234,7 +234,7 @@ __device__ __noinline__ int lc_argmin_sorted_slow(const float *cb, int rep, int 
 }
 
 // Fast path: the rounded distances fl(|z - cb[k]|) of an ascending table are unimodal in k (rounding is monotone), so
-// if the guessed entry k satisfies d(k-1) > d(k) <= d(k+1) it is torch.argmin's first minimum -- three independent
+// if the guessed entry k satisfies d(k-1) > d(k) < d(k+1) it is torch.argmin's first minimum -- three independent
 // lookups, no loop.  A guess that is off (non-uniform table, |z| so large that distances tie over several entries,
 // +-inf) takes the exact search.
 __device__ __forceinline__ int lc_argmin_sorted(const float *cb, int rep, int copy, int n, float z, float guess_scale, float cb0)
@@ -245,7 +245,12 @@ __device__ __forceinline__ int lc_argmin_sorted(const float *cb, int rep, int co
     const int k = (int)g;
     const int kl = k > 0 ? k - 1 : 0, kr = k < n - 1 ? k + 1 : n - 1;
     const float dl = lc_dist(z, LC_CB(kl)), dm = lc_dist(z, LC_CB(k)), dr = lc_dist(z, LC_CB(kr));
-    const bool left_ok = k == 0 || dl > dm, right_ok = k == n - 1 || dr >= dm;
+    // STRICT on both sides: the rounded distances are non-increasing up to the nearest entry and non-decreasing after it,
+    // so a strict local minimum is the global one -- but with duplicate entries, or entries closer together than an ulp
+    // of their distance to z, the sequence has plateaus anywhere, and "d(k) <= d(k+1)" held on a plateau far from the
+    // minimum (found by tests/test_gpu_quantizers.py::test_quantiser_b_sorted_non_uniform_tables).  An exact tie at the
+    // minimum (z midway between two entries) now takes the exact search, which returns the first of the two.
+    const bool left_ok = k == 0 || dl > dm, right_ok = k == n - 1 || dr > dm;
     if (left_ok && right_ok) return k;
     return lc_argmin_sorted_slow(cb, rep, copy, n, z, guess_scale);
 }

@@ -134,3 +134,23 @@ def test_dequantiser_a_table_and_out_of_table_indices():
                               np.array([-1, -5, hi + 1, hi + 100, 1 << 20, -(1 << 20)])]).astype(np.int32)
         got = codec.dequantize_affine(torch.from_numpy(idx).cuda(), bits).cpu().numpy()
         assert _eq_f32(got, O.dequantize_affine(idx, bits)), bits
+
+
+def test_quantiser_b_sorted_non_uniform_tables():
+    """A trained codebook is sorted but not a linspace: the two-lookup path (well-separated entries) and the
+    three-lookup / exact-search path (entries closer than 1e-5, duplicates) against the oracle."""
+    from image_compression_2_b200 import codec
+    g = torch.Generator().manual_seed(11)
+    z = torch.cat([torch.randn(50001, generator=g) * 0.5, torch.tensor([-3.0, 3.0, 0.0, float("nan"), float("inf"), -float("inf")])])
+    base = torch.sort(torch.rand(256, generator=g) * 2 - 1).values
+    close = base.clone()
+    close[100] = close[99] + 2e-6      # closer than the separation the two-lookup path needs
+    close[200] = close[199]            # a duplicate entry: argmin must return the first
+    close = torch.sort(close).values
+    warped = torch.sort(torch.tanh(torch.linspace(-2, 2, 64))).values  # smooth but far from uniform
+    for cb in (base, close, warped):
+        ref = O.quantize_codebook(z.numpy(), cb.numpy())
+        for dt in (torch.int32, torch.uint8):
+            idx, deq = codec.quantize_codebook(z.cuda(), cb.cuda(), want_deq=True, idx_dtype=dt)
+            assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref.astype(np.int64))
+            assert _eq_f32(deq.cpu().numpy(), cb.numpy()[ref])
