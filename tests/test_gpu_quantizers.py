@@ -154,3 +154,26 @@ def test_quantiser_b_sorted_non_uniform_tables():
             idx, deq = codec.quantize_codebook(z.cuda(), cb.cuda(), want_deq=True, idx_dtype=dt)
             assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref.astype(np.int64))
             assert _eq_f32(deq.cpu().numpy(), cb.numpy()[ref])
+
+
+@pytest.mark.parametrize("amp", [1e-3, 0.02, 0.03])
+def test_quantiser_b_nearly_uniform_tables(amp):
+    """A linspace whose entries are displaced by up to `amp` steps: the no-lookup path widens its exact band to the
+    table's measured deviation (amp = 0.03 is past its limit and takes the two-lookup path); dense sampling around every
+    decision boundary."""
+    from image_compression_2_b200 import codec
+    n = 256
+    rng = np.random.default_rng(int(amp * 1e6))
+    step = 2.0 / (n - 1)
+    cb = (np.linspace(-1, 1, n) + rng.uniform(-amp, amp, n) * step).astype(np.float32)
+    cb[0], cb[-1] = -1.0, 1.0
+    assert (np.diff(cb) > 0).all()
+    mid = ((cb[:-1].astype(np.float64) + cb[1:].astype(np.float64)) / 2).astype(np.float32)
+    pts = [rng.uniform(-1.1, 1.1, 40000).astype(np.float32), cb, mid]
+    for f in np.linspace(-2.5 * amp - 1e-3, 2.5 * amp + 1e-3, 41):
+        pts.append(mid + np.float32(f * step))
+    z = np.concatenate(pts).astype(np.float32)
+    ref = O.quantize_codebook(z, cb)
+    idx, _ = codec.quantize_codebook(torch.from_numpy(z).cuda(), torch.from_numpy(cb).cuda(), idx_dtype=torch.uint8)
+    got = idx.cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, ref.astype(np.int64)), (amp, np.flatnonzero(got != ref)[:8], z[got != ref][:8])
