@@ -150,6 +150,26 @@ def test_corrupt_streams_fault_like_the_oracle():
         assert np.array_equal(dec[b], ref["symbols"][0])
 
 
+@pytest.mark.parametrize("shape,n", [((1, 16, 512), 256), ((1, 4, 128), 256), ((1, 8, 64), 64)])
+def test_truncated_streams_read_zeros_like_the_reference(shape, n):
+    """The reference reads zero bits past the end of the stream (:260-270).  Valid streams cut at every byte alignment
+    -- 0..13 bytes, and 1..9 bytes short of their length -- decode like the oracle (symbols, status, fault index): the
+    decoder's bit reader keeps its next word pre-masked and loads words that straddle the end on its rare path.  The
+    [16,512] shape takes the kernel specialised for W+ latents, the others the generic instantiation."""
+    from image_compression_2_b200 import coder
+    rng = np.random.default_rng(n + shape[1])
+    codes = np.clip(np.round(rng.normal(n / 2, n * 0.07, shape)), 0, n - 1).astype(np.int32)
+    full = bytes(O.encode_stream(codes, n)["packed"])
+    cuts = sorted(set(list(range(0, 14)) + [len(full) - k for k in range(0, 10)] + [len(full) // 2, len(full) // 2 + 1,
+                                                                                     len(full) // 2 + 2, len(full) // 2 + 3]))
+    streams = [full[:c] for c in cuts if 0 <= c <= len(full)]
+    dec, status, fault = coder.cabac_decode_batch(streams, (len(streams),) + shape[1:], n_symbols=n)
+    for b, s in enumerate(streams):
+        ref = O.decode_stream(s, n, shape)
+        assert status[b] == ref["status"] and fault[b] == ref["fault_index"], (len(s), status[b], ref["status"], fault[b], ref["fault_index"])
+        assert np.array_equal(dec[b], ref["symbols"][0]), len(s)
+
+
 def _model_of(cm):
     """coder.ContextModel state as the oracle's {(left, up): (vector, count)} (global context: (-2, -2))."""
     return {((-2, -2) if len(k) == 0 else (int(k[0]), int(k[1]))): (np.asarray(v, np.float64), int(cm.context_counts.get(k, 0)))
