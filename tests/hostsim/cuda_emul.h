@@ -168,6 +168,9 @@ void run_block(void (*fn)(void *), void *arg, unsigned block, unsigned grid, uns
 #define __ballot_sync(mask, pred) emu::ballot((pred), __LINE__)
 #define __syncwarp() ((void)emu::rendezvous(__LINE__))
 #define __syncthreads() (emu::block_barrier(__LINE__))
+/* a __shared__ variable inside a device function: blocks run one after the other here, so one static instance is the
+ * block's (the emulator's warps of a block are coroutines on this thread) */
+#define __shared__ static
 
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
@@ -192,9 +195,11 @@ static inline double __ll2double_rn(long long a) { return (double)a; }
 static inline double __int2double_rn(int a) { return (double)a; }
 static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { unsigned int o = *p; *p = o + v; return o; }
 static inline unsigned int atomicOr(unsigned int *p, unsigned int v) { unsigned int o = *p; *p = o | v; return o; }
+static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 static inline unsigned int atomicXor(unsigned int *p, unsigned int v) { unsigned int o = *p; *p = o ^ v; return o; }
 static inline unsigned int atomicCAS(unsigned int *p, unsigned int c, unsigned int v) { unsigned int o = *p; if (o == c) *p = v; return o; }
 struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline unsigned int __funnelshift_lc(unsigned int lo, unsigned int hi, unsigned int sh)
 {

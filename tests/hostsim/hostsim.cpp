@@ -15,6 +15,7 @@
 #include "../../image_compression_2_b200/csrc/lc_decoder_v3.cuh"
 #include "../../image_compression_2_b200/csrc/lc_decoder_small.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_sparse.cuh"
+#include "../../image_compression_2_b200/csrc/lc_encoder_sort.cuh"
 #include "../../image_compression_2_b200/csrc/lc_encoder_pack.cuh"
 #include <algorithm>
 #include <numeric>
@@ -330,8 +331,8 @@ extern "C" void hostsim_stats(long long *out, int reset)
     if (reset) memset(&g_lc_stats, 0, sizeof(g_lc_stats));
 }
 
-// ---- parallel encoder: phase S restated on the host (the real kernel uses a CUB block sort and is
-// checked on the GPU), phases A and B run through the emulator
+// ---- parallel encoder: phase S restated on the host AND (sparse variant) run as the real kernel body through the
+// emulator (lc_encoder_sort.cuh, eight warps per stream), the two compared array by array; phases A and B emulated
 struct ParAArgs { LcCoderCfg cfg; const int *codes; int B; const uint32_t *skeys; const unsigned short *spos;
                   const int *first_bad; double *ivs; char *smem; unsigned short *glist; int *ngroups; unsigned int *task_counter;
                   double *tables; char *t2; };
@@ -372,6 +373,14 @@ static void glist_body(void *p)
                                                a->glist + (size_t)b * LC_PAR_MAX_GROUPS);
         if (lane == 0) a->ngroups[b] = ng;
     }
+}
+// the real phase S (lc_encoder_sort.cuh: radix sort from warp ballots, 8 warps per stream) under the emulator
+struct Sort2Args { LcCoderCfg cfg; const int *codes; uint32_t *skeys; unsigned short *spos; int *first_bad;
+                   unsigned short *glist; int *ngroups; double *ivs; const double *tables; char *smem; };
+static void sort2_body(void *p)
+{
+    Sort2Args *a = (Sort2Args *)p;
+    lcs2_block(a->cfg, LcCodes(a->codes), a->skeys, a->spos, a->first_bad, a->glist, a->ngroups, a->ivs, a->tables, a->smem);
 }
 static void parb_body(void *p)
 {
@@ -441,6 +450,21 @@ extern "C" int hostsim_encode_par(const int *codes, int B, int imgs, int R, int 
     if (nwarps == 0) { // sparse variant: second visits from the table, one warp per context visited three times or more
         for (int b = 0; b < 3; b++) emu::run_warp(para_tables_body, &a, (unsigned)b, 3u);
         for (int b = 0; b < grid; b++) emu::run_warp(glist_body, &a, (unsigned)b, (unsigned)grid);
+        {   // ... and the kernel that does all of phase S on the GPU must leave exactly the same arrays
+            std::vector<uint32_t> skeys2((size_t)B * LC_PAR_MAX_SYMBOLS, 0u);
+            std::vector<unsigned short> spos2((size_t)B * LC_PAR_MAX_SYMBOLS, 0), glist2((size_t)B * LC_PAR_MAX_GROUPS, 0);
+            std::vector<int> first_bad2(B, -1), ngroups2(B, -1);
+            std::vector<double> ivs2((size_t)B * LC_PAR_MAX_SYMBOLS * 2, -1.0);
+            std::vector<char> smem_s(LCS2_SMEM + 64);
+            Sort2Args sa{cfg, codes, skeys2.data(), spos2.data(), first_bad2.data(), glist2.data(), ngroups2.data(), ivs2.data(),
+                         tables.data(), (char *)(((uintptr_t)smem_s.data() + 15) & ~(uintptr_t)15)};
+            for (int b = 0; b < B; b++) emu::run_block(sort2_body, &sa, (unsigned)b, (unsigned)B, LCS2_WARPS);
+            if (skeys2 != skeys || spos2 != spos || first_bad2 != first_bad || ngroups2 != ngroups) return -99;
+            for (int b = 0; b < B; b++)
+                for (int g = 0; g < ngroups[b]; g++)
+                    if (glist2[(size_t)b * LC_PAR_MAX_GROUPS + g] != glist[(size_t)b * LC_PAR_MAX_GROUPS + g]) return -98;
+            if (memcmp(ivs2.data(), ivs.data(), ivs.size() * sizeof(double)) != 0) return -97;
+        }
         if (a.t2)
             for (int b = 0; b < 2; b++)
                 for (int w = 0; w < 2; w++) emu::run_warp(para_t2_body, &a, (unsigned)b, 2u, (unsigned)w, 2u);
