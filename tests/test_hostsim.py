@@ -299,6 +299,23 @@ def test_decoder_v2_wide_contexts_and_images_sharing_a_model(ver):
     assert st[0] == ref["status"] and np.array_equal(dec.ravel()[:k], ref["symbols"].ravel()[:k])
 
 
+def test_decoder_v2_truncated_streams_read_zeros():
+    """Valid streams cut at every byte alignment (the flat loop's bit reader keeps its next word pre-masked and loads a
+    word that straddles the end of the stream on its rare path): symbols, status and fault index of the oracle decoder."""
+    rng = np.random.default_rng(5)
+    n, shape = 256, (1, 4, 128)
+    codes = np.clip(np.round(rng.normal(128, 18, shape)), 0, n - 1).astype(np.int32)
+    full = bytes(O.encode_stream(codes, n)["packed"])
+    cuts = sorted(set(list(range(0, 10)) + [len(full) - k for k in range(0, 7)] + [len(full) // 2 + k for k in range(4)]))
+    streams = [full[:c] for c in cuts]
+    dec, st, fi, _ = H.decode(streams, n, (len(streams),) + shape[1:], 1, fast="v2", grid=2)
+    for b, s in enumerate(streams):
+        ref = O.decode_stream(s, n, shape)
+        k = int(ref["fault_index"]) if ref["status"] else codes.size
+        assert st[b] == ref["status"] and (ref["status"] == 0 or fi[b] == k), (len(s), st[b], ref["status"])
+        assert np.array_equal(dec[b].ravel()[:k], ref["symbols"].ravel()[:k]), len(s)
+
+
 # ---- small-alphabet decoder (dense shared-memory model, n <= 16) ----
 
 def test_small_decoder_matches_reference_vectors():
